@@ -1,0 +1,728 @@
+// Fused chain kernel: mixer -> real-tap FIR -> integer decimation -> FM discriminator.
+//
+// Replaces one chunk of the reference's
+//   commSignal(fs, x, chunker).offsetFreq(f).filter(fir).bwLim(bw).funcApply(demod_fm().demod)
+// (comm.py:63-78, filters.py:64-70, comm.py:118-129, demod_fm.py:40-49; the loop body of
+// decode_noaa.py:623).  See DESIGN.md "Fused chain kernel" for the derivation.
+//
+// Formulation ("input-stationary polyphase blocks").  With output positions
+// n_m = off + m*D and y[m] = sum_k b[k] x'[n_m - k] (x' = mixed input), cut the input into
+// blocks of D samples, block j = [B_j, B_j + D) with B_j = n_j + s - D + 1 (s in {0,1} makes
+// B_j even so every block is 16-byte aligned).  Block j contributes to outputs j..j+Q-1:
+//     P_q[j] = sum_a T[q][a] * x'[B_j + a],    T[q][a] = b[q*D + D-1-a-s]  (0 outside [0,K))
+//     y[m]   = sum_{q<Q} P_q[m-q],             Q = ceil((K+s)/D)
+// One thread owns one block: every input sample is read from shared memory exactly once, by
+// exactly one thread, which also applies the mixer to it.  The taps are warp-uniform
+// (broadcast loads).  The partial sums are exchanged through a small shared array and the
+// discriminator is applied to consecutive y[m].  HBM traffic is the algorithmic minimum
+// (8 B in per sample, 4/D B out) plus a Q/(NT-Q) halo re-read that is served by L2.
+//
+// Staging.  A CTA walks tiles of NT blocks (NT*D contiguous samples).  Each tile is brought
+// into a double-buffered shared-memory stage by the TMA engine with 1-D bulk copies
+// (cp.async.bulk, SASS UBLKCP) that signal an mbarrier; the first tile's copy is split
+// between the carried halo buffer and the chunk.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ddm_common.cuh"
+
+namespace ddm {
+
+constexpr int kChainThreads = 128;   // blocks (threads) per tile
+constexpr int kChainMaxQ = 8;
+constexpr int kChainCtasPerSm = 3;
+
+struct ChainParams {
+    const float2 *x;       // chunk, n samples
+    const float2 *halo;    // H samples that precede the chunk
+    void *out;             // f32 (FM) or cf32 (IQ)
+    const float *taps;     // [Q][DP]
+    const float2 *rot;     // [DP] exp(-j 2 pi r a)
+    long long n;           // chunk length
+    long long n0;          // global index of x[0]
+    long long M;           // output positions in this chunk
+    long long b0;          // B_0 = off + s + 1 - D: first sample of block 0 (chunk coords)
+    long long num_tiles;
+    double r_hi, r_lo;
+    int D, DP, H, s, has_prev;
+};
+
+// ------------------------------------------------------------------------------------
+// fast path: D even, Q <= 8
+// ------------------------------------------------------------------------------------
+template <int Q, bool MIX, int OUT>
+__global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm)
+chain_fused_kernel(const ChainParams P) {
+    constexpr int NT = kChainThreads;
+    constexpr int J = NT - Q;                      // outputs per tile
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int D = P.D, DP = P.DP;
+    // ---- shared memory carve-up ----
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 barriers
+    float *s_taps = reinterpret_cast<float *>(smem_raw + 16);                // Q*DP floats
+    float2 *s_rot = reinterpret_cast<float2 *>(s_taps + Q * DP);             // DP float2
+    float2 *s_e = s_rot + DP;                                                // 2*Q*NT float2
+    const size_t stage_bytes = static_cast<size_t>(NT) * D * sizeof(float2);
+    unsigned char *s_stage0 = reinterpret_cast<unsigned char *>(
+        (reinterpret_cast<uintptr_t>(s_e + 2 * Q * NT) + 127) & ~static_cast<uintptr_t>(127));
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < Q * DP; i += NT) s_taps[i] = P.taps[i];
+    for (int i = tid; i < DP; i += NT) s_rot[i] = P.rot[i];
+    __syncthreads();
+
+    const long long n_even = P.n & ~1LL;
+    const long long end_all = P.b0 + P.M * D;      // end of the last needed block
+
+    // thread 0: start the TMA copies that fill one stage with tile `tile`
+    auto issue = [&](long long tile, int stage) {
+        unsigned char *dst = s_stage0 + stage * stage_bytes;
+        const long long S = P.b0 + (tile * J - Q) * D;             // first sample (may be < 0)
+        long long E = S + static_cast<long long>(NT) * D;
+        if (E > end_all) E = end_all;
+        uint32_t bytes = 0;
+        const long long h_end = E < 0 ? E : 0;
+        const long long c_beg = S > 0 ? S : 0;
+        const long long c_end = E < n_even ? E : n_even;
+        if (S < 0) bytes += static_cast<uint32_t>((h_end - S) * 8);
+        if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 8);
+        // tail: the odd last sample of the chunk and the zero pad behind it
+        long long t_beg = c_beg > n_even ? c_beg : n_even;
+        for (long long i = t_beg; i < E; ++i) {
+            float2 v = i < P.n ? P.x[i] : make_float2(0.f, 0.f);
+            reinterpret_cast<float2 *>(dst)[i - S] = v;
+        }
+        mbar_arrive_expect_tx(&mbar[stage], bytes);
+        if (S < 0)
+            bulk_g2s(dst, P.halo + (P.H + S), static_cast<uint32_t>((h_end - S) * 8), &mbar[stage]);
+        if (c_end > c_beg)
+            bulk_g2s(dst + (c_beg - S) * 8, P.x + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8),
+                     &mbar[stage]);
+    };
+
+    long long tile = blockIdx.x;
+    if (tid == 0 && tile < P.num_tiles) issue(tile, 0);
+
+    const int D4 = D & ~3;
+    for (int it = 0; tile < P.num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const long long nxt = tile + gridDim.x;
+        if (tid == 0 && nxt < P.num_tiles) {
+            fence_proxy_async();
+            issue(nxt, stage ^ 1);
+        }
+        mbar_wait(&mbar[stage], (it >> 1) & 1);
+
+        const long long jblk = tile * J - Q + tid;          // this thread's block index
+        float2 *e_buf = s_e + (it & 1) * (Q * NT);
+        if (jblk < P.M) {
+            const unsigned char *sp = s_stage0 + stage * stage_bytes +
+                                      static_cast<size_t>(tid) * D * sizeof(float2);
+            const float4 *sp4 = reinterpret_cast<const float4 *>(sp);
+            const float4 *rot4 = reinterpret_cast<const float4 *>(s_rot);
+            float2 acc[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc[q] = make_float2(0.f, 0.f);
+
+            int a = 0;
+#pragma unroll 2
+            for (; a < D4; a += 4) {
+                const float4 v0 = sp4[(a >> 1)], v1 = sp4[(a >> 1) + 1];
+                float2 m0, m1, m2, m3;
+                if (MIX) {
+                    const float4 r0 = rot4[(a >> 1)], r1 = rot4[(a >> 1) + 1];
+                    m0 = cmul(make_float2(v0.x, v0.y), make_float2(r0.x, r0.y));
+                    m1 = cmul(make_float2(v0.z, v0.w), make_float2(r0.z, r0.w));
+                    m2 = cmul(make_float2(v1.x, v1.y), make_float2(r1.x, r1.y));
+                    m3 = cmul(make_float2(v1.z, v1.w), make_float2(r1.z, r1.w));
+                } else {
+                    m0 = make_float2(v0.x, v0.y);
+                    m1 = make_float2(v0.z, v0.w);
+                    m2 = make_float2(v1.x, v1.y);
+                    m3 = make_float2(v1.z, v1.w);
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
+                    acc[q].x = fmaf(t.x, m0.x, acc[q].x);
+                    acc[q].y = fmaf(t.x, m0.y, acc[q].y);
+                    acc[q].x = fmaf(t.y, m1.x, acc[q].x);
+                    acc[q].y = fmaf(t.y, m1.y, acc[q].y);
+                    acc[q].x = fmaf(t.z, m2.x, acc[q].x);
+                    acc[q].y = fmaf(t.z, m2.y, acc[q].y);
+                    acc[q].x = fmaf(t.w, m3.x, acc[q].x);
+                    acc[q].y = fmaf(t.w, m3.y, acc[q].y);
+                }
+            }
+            if (a < D) {                                    // D % 4 == 2
+                const float4 v0 = sp4[(a >> 1)];
+                float2 m0, m1;
+                if (MIX) {
+                    const float4 r0 = rot4[(a >> 1)];
+                    m0 = cmul(make_float2(v0.x, v0.y), make_float2(r0.x, r0.y));
+                    m1 = cmul(make_float2(v0.z, v0.w), make_float2(r0.z, r0.w));
+                } else {
+                    m0 = make_float2(v0.x, v0.y);
+                    m1 = make_float2(v0.z, v0.w);
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
+                    acc[q].x = fmaf(t.x, m0.x, acc[q].x);
+                    acc[q].y = fmaf(t.x, m0.y, acc[q].y);
+                    acc[q].x = fmaf(t.y, m1.x, acc[q].x);
+                    acc[q].y = fmaf(t.y, m1.y, acc[q].y);
+                }
+            }
+            if (MIX) {
+                const long long g = P.n0 + P.b0 + jblk * D;  // global index of the block start
+                const float2 w0 = phase_rotator(P.r_hi, P.r_lo, g);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) acc[q] = cmul(acc[q], w0);
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) e_buf[q * NT + tid] = acc[q];
+        }
+        __syncthreads();
+
+        // ---- outputs of this tile: m = tile*J + tid, tid < J ----
+        const long long m = tile * J + tid;
+        if (tid < J && m < P.M) {
+            float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float2 p = e_buf[q * NT + (tid + Q - q)];
+                y.x += p.x;
+                y.y += p.y;
+            }
+            if (OUT == DDM_CHAIN_OUT_IQ) {
+                reinterpret_cast<float2 *>(P.out)[m] = y;
+            } else if (m > 0 || P.has_prev) {
+                float2 yp = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float2 p = e_buf[q * NT + (tid + Q - 1 - q)];
+                    yp.x += p.x;
+                    yp.y += p.y;
+                }
+                const float re = fmaf(y.x, yp.x, y.y * yp.y);
+                const float im = fmaf(y.y, yp.x, -y.x * yp.y);
+                reinterpret_cast<float *>(P.out)[m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// general path (any D, any tap count): one thread per decimated sample, direct form.
+// Correct for every configuration; used when the fast path's constraints do not hold.
+// ------------------------------------------------------------------------------------
+struct GenericParams {
+    const float2 *x;
+    const float2 *halo;
+    float2 *y;             // y[m+1] for m = -1..M-1
+    const float *taps;     // K taps
+    long long n, n0, M, off;
+    double r_hi, r_lo;
+    int K, D, H, mix;
+};
+
+__global__ void chain_generic_y_kernel(const GenericParams P) {
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx > P.M) return;
+    const long long m = idx - 1;
+    const long long pos = P.off + m * P.D;          // chunk coordinates, may be negative
+    float2 acc = make_float2(0.f, 0.f);
+    for (int k = 0; k < P.K; ++k) {
+        const long long i = pos - k;
+        if (i < -static_cast<long long>(P.H)) break;
+        float2 v = i >= 0 ? P.x[i] : P.halo[P.H + i];
+        if (P.mix) v = cmul(v, phase_rotator(P.r_hi, P.r_lo, P.n0 + i));
+        const float t = P.taps[k];
+        acc.x = fmaf(t, v.x, acc.x);
+        acc.y = fmaf(t, v.y, acc.y);
+    }
+    P.y[idx] = acc;
+}
+
+__global__ void chain_generic_out_kernel(const float2 *y, void *out, long long M, int has_prev,
+                                         int out_mode) {
+    const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (m >= M) return;
+    const float2 c = y[m + 1];
+    if (out_mode == DDM_CHAIN_OUT_IQ) {
+        reinterpret_cast<float2 *>(out)[m] = c;
+        return;
+    }
+    if (m == 0 && !has_prev) return;
+    const float2 p = y[m];
+    const float re = fmaf(c.x, p.x, c.y * p.y);
+    const float im = fmaf(c.y, p.x, -c.x * p.y);
+    reinterpret_cast<float *>(out)[m - (has_prev ? 0 : 1)] = atan2f(im, re);
+}
+
+}  // namespace ddm
+
+// ======================================================================================
+// host side
+// ======================================================================================
+struct ddm_chain {
+    int device = 0;
+    int K = 0, D = 1, out_mode = 0, in_format = 0;
+    double freq = 0, fs = 1;
+    bool mix = false, fast = false;
+    double r_hi = 0, r_lo = 0;
+    int64_t n0 = 0, dec_off = 0;
+    int has_prev = 0;
+    int H = 0, DP = 0;
+    int Q[2] = {0, 0};
+    int per_sm[2] = {0, 0};                  // resident CTAs per SM of the fused kernel, per s
+    float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
+    float *d_taps_lin = nullptr;             // K
+    float2 *d_rot = nullptr;                 // DP
+    float2 *d_halo[2] = {nullptr, nullptr};
+    float2 *d_halo_init = nullptr;           // the reference's initial condition as raw history
+    int cur = 0;
+    float2 *d_ytmp = nullptr;
+    size_t ytmp_cap = 0;
+    void *d_in = nullptr, *d_out = nullptr;  // staging for the _host entry point
+    size_t in_cap = 0, out_cap = 0;
+    std::vector<double> taps;
+    int sms = 148;
+};
+
+namespace {
+
+using namespace ddm;
+
+size_t chain_smem_bytes(int Q, int D, int DP) {
+    size_t fixed = 16 + sizeof(float) * Q * DP + sizeof(float2) * DP +
+                   sizeof(float2) * 2 * Q * kChainThreads;
+    fixed = (fixed + 127) & ~static_cast<size_t>(127);
+    return fixed + 128 + 2 * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
+}
+
+template <int Q, bool MIX, int OUT>
+int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
+    const size_t smem = chain_smem_bytes(Q, c->D, c->DP);
+    auto kern = chain_fused_kernel<Q, MIX, OUT>;
+    int &per_sm = c->per_sm[p.s];
+    if (per_sm == 0) {   // first launch of this variant on this handle's device
+        DDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+        DDM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kChainThreads, smem));
+        if (per_sm < 1) {
+            per_sm = 0;
+            set_error("fused chain kernel does not fit: %zu bytes of shared memory", smem);
+            return DDM_ERR_UNSUPPORTED;
+        }
+    }
+    long long grid = static_cast<long long>(c->sms) * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    kern<<<static_cast<unsigned>(grid), kChainThreads, smem, st>>>(p);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+template <bool MIX, int OUT>
+int launch_fused_mo(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
+    switch (Q) {
+        case 1: return launch_fused_q<1, MIX, OUT>(c, p, st);
+        case 2: return launch_fused_q<2, MIX, OUT>(c, p, st);
+        case 3: return launch_fused_q<3, MIX, OUT>(c, p, st);
+        case 4: return launch_fused_q<4, MIX, OUT>(c, p, st);
+        case 5: return launch_fused_q<5, MIX, OUT>(c, p, st);
+        case 6: return launch_fused_q<6, MIX, OUT>(c, p, st);
+        case 7: return launch_fused_q<7, MIX, OUT>(c, p, st);
+        case 8: return launch_fused_q<8, MIX, OUT>(c, p, st);
+    }
+    set_error("internal: Q=%d out of range", Q);
+    return DDM_ERR_UNSUPPORTED;
+}
+
+int launch_fused(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
+    if (c->mix) {
+        return c->out_mode == DDM_CHAIN_OUT_FM ? launch_fused_mo<true, DDM_CHAIN_OUT_FM>(c, Q, p, st)
+                                               : launch_fused_mo<true, DDM_CHAIN_OUT_IQ>(c, Q, p, st);
+    }
+    return c->out_mode == DDM_CHAIN_OUT_FM ? launch_fused_mo<false, DDM_CHAIN_OUT_FM>(c, Q, p, st)
+                                           : launch_fused_mo<false, DDM_CHAIN_OUT_IQ>(c, Q, p, st);
+}
+
+int64_t positive_mod(int64_t a, int64_t b) {
+    int64_t r = a % b;
+    return r < 0 ? r + b : r;
+}
+
+int64_t positions_in(const ddm_chain *c, int64_t n) {
+    if (n <= c->dec_off) return 0;
+    return (n - c->dec_off + c->D - 1) / c->D;
+}
+
+// the reference's initial condition expressed as raw input history: zi = lfilter_zi(b,[1])
+// (filters.py:45) is the state an all-ones *mixed* input leaves behind, so the raw halo is
+// exp(+j 2 pi f g / fs) for g = -H..-1.
+int build_initial_halo(ddm_chain *c) {
+    std::vector<float2> h(c->H);
+    for (int i = 0; i < c->H; ++i) {
+        if (!c->mix) {
+            h[i] = make_float2(1.f, 0.f);
+            continue;
+        }
+        const double g = static_cast<double>(i - c->H);
+        double t = c->r_hi * g;
+        t -= std::rint(t);
+        t += c->r_lo * g;
+        h[i] = make_float2(static_cast<float>(std::cos(2.0 * M_PI * t)),
+                           static_cast<float>(std::sin(2.0 * M_PI * t)));
+    }
+    DDM_CUDA(cudaMalloc(&c->d_halo_init, sizeof(float2) * c->H));
+    DDM_CUDA(cudaMemcpy(c->d_halo_init, h.data(), sizeof(float2) * c->H, cudaMemcpyHostToDevice));
+    return DDM_OK;
+}
+
+int fill_initial_halo(ddm_chain *c, cudaStream_t st) {
+    DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], c->d_halo_init, sizeof(float2) * c->H,
+                             cudaMemcpyDeviceToDevice, st));
+    return DDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddm_chain_create(int device, const double *taps, int ntaps, int decim, double freq_offset,
+                     double samp_rate, int out_mode, int in_format, ddm_chain **out) {
+    DDM_REQUIRE(out != nullptr, "ddm_chain_create: out is NULL");
+    *out = nullptr;
+    DDM_REQUIRE(taps != nullptr && ntaps >= 1, "ddm_chain_create: need at least one tap");
+    DDM_REQUIRE(decim >= 1, "ddm_chain_create: decimation must be >= 1 (got %d)", decim);
+    DDM_REQUIRE(samp_rate > 0, "ddm_chain_create: sampling rate must be positive");
+    DDM_REQUIRE(out_mode == DDM_CHAIN_OUT_FM || out_mode == DDM_CHAIN_OUT_IQ,
+                "ddm_chain_create: bad out_mode %d", out_mode);
+    if (in_format != DDM_IN_CF32) {
+        set_error("ddm_chain_create: input format %d not implemented", in_format);
+        return DDM_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    DDM_CUDA(cudaGetDeviceCount(&ndev));
+    DDM_REQUIRE(device >= 0 && device < ndev, "ddm_chain_create: no such device %d", device);
+    DeviceGuard guard(device);
+
+    ddm_chain *c = new (std::nothrow) ddm_chain();
+    if (!c) {
+        set_error("ddm_chain_create: out of host memory");
+        return DDM_ERR_NOMEM;
+    }
+    c->device = device;
+    c->K = ntaps;
+    c->D = decim;
+    c->freq = freq_offset;
+    c->fs = samp_rate;
+    c->out_mode = out_mode;
+    c->in_format = in_format;
+    c->mix = freq_offset != 0.0;
+    c->taps.assign(taps, taps + ntaps);
+    c->sms = sm_count(device);
+    // r = f/fs turns per sample as a double-double
+    c->r_hi = freq_offset / samp_rate;
+    c->r_lo = std::fma(-c->r_hi, samp_rate, freq_offset) / samp_rate;
+
+    const int D = decim, K = ntaps;
+    const int qmax = (K + 1 + D - 1) / D;
+    c->DP = (D + 3) & ~3;
+    c->fast = (D % 2 == 0) && qmax <= kChainMaxQ &&
+              chain_smem_bytes(qmax, D, c->DP) <= 227 * 1024;
+    c->H = (qmax + 1) * D;
+    if (c->H & 1) c->H += 1;
+
+    auto fail = [&](int code) {
+        ddm_chain_destroy(c);
+        return code;
+    };
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i) {
+        e = cudaMalloc(&c->d_halo[i], sizeof(float2) * c->H);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(halo) failed: %s", cudaGetErrorString(e));
+            return fail(DDM_ERR_NOMEM);
+        }
+    }
+    {
+        std::vector<float> lin(K);
+        for (int k = 0; k < K; ++k) lin[k] = static_cast<float>(taps[k]);
+        e = cudaMalloc(&c->d_taps_lin, sizeof(float) * K);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(c->d_taps_lin, lin.data(), sizeof(float) * K, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("tap upload failed: %s", cudaGetErrorString(e));
+            return fail(DDM_ERR_CUDA);
+        }
+    }
+    if (c->fast) {
+        for (int s = 0; s < 2; ++s) {
+            const int Q = (K + s + D - 1) / D;
+            c->Q[s] = Q;
+            std::vector<float> t(static_cast<size_t>(Q) * c->DP, 0.f);
+            for (int q = 0; q < Q; ++q)
+                for (int a = 0; a < D; ++a) {
+                    const int k = q * D + D - 1 - a - s;
+                    if (k >= 0 && k < K) t[static_cast<size_t>(q) * c->DP + a] = static_cast<float>(taps[k]);
+                }
+            e = cudaMalloc(&c->d_taps[s], sizeof(float) * t.size());
+            if (e == cudaSuccess)
+                e = cudaMemcpy(c->d_taps[s], t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                set_error("tap table upload failed: %s", cudaGetErrorString(e));
+                return fail(DDM_ERR_CUDA);
+            }
+        }
+        std::vector<float2> rot(c->DP, make_float2(1.f, 0.f));
+        for (int a = 0; a < D; ++a) {
+            double t = c->r_hi * a;
+            t -= std::rint(t);
+            t += c->r_lo * a;
+            rot[a] = make_float2(static_cast<float>(std::cos(2.0 * M_PI * t)),
+                                 static_cast<float>(-std::sin(2.0 * M_PI * t)));
+        }
+        e = cudaMalloc(&c->d_rot, sizeof(float2) * c->DP);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(c->d_rot, rot.data(), sizeof(float2) * c->DP, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("rotator table upload failed: %s", cudaGetErrorString(e));
+            return fail(DDM_ERR_CUDA);
+        }
+    }
+    int rc = build_initial_halo(c);
+    if (rc == DDM_OK) rc = fill_initial_halo(c, nullptr);
+    if (rc != DDM_OK) return fail(rc);
+    DDM_CUDA(cudaStreamSynchronize(nullptr));
+    *out = c;
+    return DDM_OK;
+}
+
+int ddm_chain_destroy(ddm_chain *c) {
+    if (!c) return DDM_OK;
+    DeviceGuard guard(c->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_halo[i]);
+        cudaFree(c->d_taps[i]);
+    }
+    cudaFree(c->d_halo_init);
+    cudaFree(c->d_taps_lin);
+    cudaFree(c->d_rot);
+    cudaFree(c->d_ytmp);
+    cudaFree(c->d_in);
+    cudaFree(c->d_out);
+    delete c;
+    return DDM_OK;
+}
+
+int ddm_chain_reset(ddm_chain *c) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_reset: NULL handle");
+    DeviceGuard guard(c->device);
+    c->n0 = 0;
+    c->dec_off = 0;
+    c->has_prev = 0;
+    return fill_initial_halo(c, nullptr);
+}
+
+int ddm_chain_halo_len(const ddm_chain *c, int64_t *n) {
+    DDM_REQUIRE(c != nullptr && n != nullptr, "ddm_chain_halo_len: NULL argument");
+    *n = c->H;
+    return DDM_OK;
+}
+
+int ddm_chain_out_count(const ddm_chain *c, int64_t n, int64_t *n_out) {
+    DDM_REQUIRE(c != nullptr && n_out != nullptr, "ddm_chain_out_count: NULL argument");
+    DDM_REQUIRE(n >= 0, "ddm_chain_out_count: negative length");
+    const int64_t M = positions_in(c, n);
+    if (c->out_mode == DDM_CHAIN_OUT_IQ) *n_out = M;
+    else *n_out = c->has_prev ? M : (M > 0 ? M - 1 : 0);
+    return DDM_OK;
+}
+
+int ddm_chain_get_position(const ddm_chain *c, int64_t *n0, int64_t *dec_off, int *has_prev) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_get_position: NULL handle");
+    if (n0) *n0 = c->n0;
+    if (dec_off) *dec_off = c->dec_off;
+    if (has_prev) *has_prev = c->has_prev;
+    return DDM_OK;
+}
+
+int ddm_chain_set_position(ddm_chain *c, int64_t n0, int64_t dec_off, int has_prev,
+                           const void *halo_dev, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_set_position: NULL handle");
+    DDM_REQUIRE(dec_off >= 0, "ddm_chain_set_position: negative decimation offset");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    c->n0 = n0;
+    c->dec_off = dec_off;
+    c->has_prev = has_prev ? 1 : 0;
+    if (halo_dev == nullptr) return fill_initial_halo(c, st);
+    DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], halo_dev, sizeof(float2) * c->H,
+                             cudaMemcpyDeviceToDevice, st));
+    return DDM_OK;
+}
+
+int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream) {
+    DDM_REQUIRE(c != nullptr && halo_dev != nullptr, "ddm_chain_get_halo: NULL argument");
+    DeviceGuard guard(c->device);
+    DDM_CUDA(cudaMemcpyAsync(halo_dev, c->d_halo[c->cur], sizeof(float2) * c->H,
+                             cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return DDM_OK;
+}
+
+int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
+                        int64_t out_capacity, int64_t *n_out, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_apply_dev: NULL handle");
+    DDM_REQUIRE(n >= 0, "ddm_chain_apply_dev: negative length");
+    DDM_REQUIRE(n == 0 || x_dev != nullptr, "ddm_chain_apply_dev: NULL input");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t M = positions_in(c, n);
+    int64_t produced = 0;
+    ddm_chain_out_count(c, n, &produced);
+    if (n_out) *n_out = produced;
+    if (produced > out_capacity) {
+        set_error("ddm_chain_apply_dev: output needs %lld samples, capacity is %lld",
+                  static_cast<long long>(produced), static_cast<long long>(out_capacity));
+        return DDM_ERR_CAPACITY;
+    }
+    DDM_REQUIRE(produced == 0 || out_dev != nullptr, "ddm_chain_apply_dev: NULL output");
+    const float2 *x = static_cast<const float2 *>(x_dev);
+    const int D = c->D;
+
+    if (M > 0) {
+        const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0;
+        if (c->fast && aligned) {
+            const int s = static_cast<int>((c->dec_off + 1) & 1);
+            const int Q = c->Q[s];
+            ChainParams p{};
+            p.x = x;
+            p.halo = c->d_halo[c->cur];
+            p.out = out_dev;
+            p.taps = c->d_taps[s];
+            p.rot = c->d_rot;
+            p.n = n;
+            p.n0 = c->n0;
+            p.M = M;
+            p.b0 = c->dec_off + s + 1 - D;
+            const int J = kChainThreads - Q;
+            p.num_tiles = (M + J - 1) / J;
+            p.r_hi = c->r_hi;
+            p.r_lo = c->r_lo;
+            p.D = D;
+            p.DP = c->DP;
+            p.H = c->H;
+            p.s = s;
+            p.has_prev = c->has_prev;
+            int rc = launch_fused(c, Q, p, st);
+            if (rc != DDM_OK) return rc;
+        } else {
+            const size_t need = static_cast<size_t>(M + 1);
+            if (need > c->ytmp_cap) {
+                DDM_CUDA(cudaStreamSynchronize(st));
+                cudaFree(c->d_ytmp);
+                c->d_ytmp = nullptr;
+                c->ytmp_cap = 0;
+                DDM_CUDA(cudaMalloc(&c->d_ytmp, sizeof(float2) * need));
+                c->ytmp_cap = need;
+            }
+            GenericParams g{};
+            g.x = x;
+            g.halo = c->d_halo[c->cur];
+            g.y = c->d_ytmp;
+            g.taps = c->d_taps_lin;
+            g.n = n;
+            g.n0 = c->n0;
+            g.M = M;
+            g.off = c->dec_off;
+            g.r_hi = c->r_hi;
+            g.r_lo = c->r_lo;
+            g.K = c->K;
+            g.D = D;
+            g.H = c->H;
+            g.mix = c->mix ? 1 : 0;
+            const int tb = 128;
+            chain_generic_y_kernel<<<static_cast<unsigned>((M + 1 + tb - 1) / tb), tb, 0, st>>>(g);
+            DDM_CUDA(cudaGetLastError());
+            chain_generic_out_kernel<<<static_cast<unsigned>((M + tb - 1) / tb), tb, 0, st>>>(
+                c->d_ytmp, out_dev, M, c->has_prev, c->out_mode);
+            DDM_CUDA(cudaGetLastError());
+            count_launch(2);
+        }
+    }
+
+    // ---- carry: halo <- last H samples of (halo ++ x) ----
+    if (n >= c->H) {
+        DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], x + (n - c->H), sizeof(float2) * c->H,
+                                 cudaMemcpyDeviceToDevice, st));
+    } else if (n > 0) {
+        const int nxt = c->cur ^ 1;
+        DDM_CUDA(cudaMemcpyAsync(c->d_halo[nxt], c->d_halo[c->cur] + n, sizeof(float2) * (c->H - n),
+                                 cudaMemcpyDeviceToDevice, st));
+        DDM_CUDA(cudaMemcpyAsync(c->d_halo[nxt] + (c->H - n), x, sizeof(float2) * n,
+                                 cudaMemcpyDeviceToDevice, st));
+        c->cur = nxt;
+    }
+    // comm.py:124  nextOff = (j - (len - off) % j) % j   (python modulo)
+    c->dec_off = positive_mod(D - positive_mod(n - c->dec_off, D), D);
+    c->n0 += n;
+    if (M > 0) c->has_prev = 1;
+    return DDM_OK;
+}
+
+int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_host,
+                         int64_t out_capacity, int64_t *n_out, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_apply_host: NULL handle");
+    DDM_REQUIRE(n >= 0, "ddm_chain_apply_host: negative length");
+    DDM_REQUIRE(n == 0 || x_host != nullptr, "ddm_chain_apply_host: NULL input");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int64_t produced = 0;
+    ddm_chain_out_count(c, n, &produced);
+    if (produced > out_capacity) {
+        if (n_out) *n_out = produced;
+        set_error("ddm_chain_apply_host: output needs %lld samples, capacity is %lld",
+                  static_cast<long long>(produced), static_cast<long long>(out_capacity));
+        return DDM_ERR_CAPACITY;
+    }
+    const size_t in_bytes = sizeof(float2) * static_cast<size_t>(n);
+    const size_t out_elem = c->out_mode == DDM_CHAIN_OUT_IQ ? sizeof(float2) : sizeof(float);
+    const size_t out_bytes = out_elem * static_cast<size_t>(produced);
+    if (in_bytes > c->in_cap) {
+        DDM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(c->d_in);
+        c->d_in = nullptr;
+        c->in_cap = 0;
+        DDM_CUDA(cudaMalloc(&c->d_in, in_bytes));
+        c->in_cap = in_bytes;
+    }
+    if (out_bytes > c->out_cap) {
+        DDM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(c->d_out);
+        c->d_out = nullptr;
+        c->out_cap = 0;
+        DDM_CUDA(cudaMalloc(&c->d_out, out_bytes));
+        c->out_cap = out_bytes;
+    }
+    if (n > 0) DDM_CUDA(cudaMemcpyAsync(c->d_in, x_host, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = ddm_chain_apply_dev(c, c->d_in, n, c->d_out, produced, n_out, stream);
+    if (rc != DDM_OK) return rc;
+    if (produced > 0)
+        DDM_CUDA(cudaMemcpyAsync(out_host, c->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaStreamSynchronize(st));
+    return DDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""Handle-level Python wrapper of the fused chain (ddm_chain_* in include/ddemod.h).
+
+One FusedChain == the state the reference spreads over a chunker ("freqoffset", "bwlim"
+variables, chunker.py:54-84), a filter object (filter.__zi, filters.py:45,69) and a
+demod_fm object (demod_fm.__last, demod_fm.py:44,48), for the chain
+offsetFreq -> FIR -> bwLim(non strict) -> [demod_fm] of decode_noaa.py:623.
+
+commSignal (comm.py) builds these lazily from the fluent chain; bench.py and the
+multi-GPU driver use them directly.  torch is only used to own device memory/streams.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(device_index):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class FusedChain:
+    def __init__(self, taps, decim, freq_offset, samp_rate, demod=True, device=None):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise RuntimeError("directdemod_b200 needs a CUDA device; there is no CPU fallback")
+        self._l = _lib.lib()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        taps = np.ascontiguousarray(np.asarray(taps, dtype=np.float64))
+        if taps.ndim != 1 or taps.size < 1:
+            raise ValueError("taps must be a non-empty 1-D array")
+        self.ntaps = int(taps.size)
+        self.decim = int(decim)
+        self.freq_offset = float(freq_offset)
+        self.samp_rate = float(samp_rate)
+        self.demod = bool(demod)
+        h = C.c_void_p()
+        _lib.check(self._l.ddm_chain_create(
+            self.device, taps.ctypes.data_as(C.POINTER(C.c_double)), self.ntaps, self.decim,
+            self.freq_offset, self.samp_rate,
+            _lib.CHAIN_OUT_FM if demod else _lib.CHAIN_OUT_IQ, _lib.IN_CF32, C.byref(h)),
+            "ddm_chain_create")
+        self._h = h
+        n = C.c_int64()
+        _lib.check(self._l.ddm_chain_halo_len(self._h, C.byref(n)), "ddm_chain_halo_len")
+        self.halo_len = int(n.value)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._l.ddm_chain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- carried state ----------------------------------------------------------------
+    def reset(self):
+        _lib.check(self._l.ddm_chain_reset(self._h), "ddm_chain_reset")
+
+    @property
+    def position(self):
+        """(global sample index, decimation offset, has-previous-sample flag)."""
+        n0, off, hp = C.c_int64(), C.c_int64(), C.c_int()
+        _lib.check(self._l.ddm_chain_get_position(self._h, C.byref(n0), C.byref(off), C.byref(hp)),
+                   "ddm_chain_get_position")
+        return int(n0.value), int(off.value), bool(hp.value)
+
+    def set_position(self, n0, dec_off, has_prev, halo=None):
+        """Place the chain at global index n0; `halo` = the halo_len raw samples before it
+        (cuda complex64 tensor) or None for the reference's initial condition."""
+        ptr = C.c_void_p(0)
+        if halo is not None:
+            torch = _torch()
+            if halo.dtype != torch.complex64 or not halo.is_cuda or halo.numel() != self.halo_len:
+                raise ValueError("halo must be a cuda complex64 tensor of halo_len samples")
+            halo = halo.contiguous()
+            ptr = C.c_void_p(halo.data_ptr())
+        _lib.check(self._l.ddm_chain_set_position(self._h, int(n0), int(dec_off), int(bool(has_prev)),
+                                                  ptr, _stream_ptr(self.device)),
+                   "ddm_chain_set_position")
+
+    def get_halo(self):
+        torch = _torch()
+        out = torch.empty(self.halo_len, dtype=torch.complex64, device="cuda:%d" % self.device)
+        _lib.check(self._l.ddm_chain_get_halo(self._h, C.c_void_p(out.data_ptr()),
+                                              _stream_ptr(self.device)), "ddm_chain_get_halo")
+        return out
+
+    def out_count(self, n):
+        m = C.c_int64()
+        _lib.check(self._l.ddm_chain_out_count(self._h, int(n), C.byref(m)), "ddm_chain_out_count")
+        return int(m.value)
+
+    # -- data path --------------------------------------------------------------------
+    def apply(self, x, out=None):
+        """x: cuda complex64 tensor (one chunk).  Returns a cuda tensor (float32 FM output or
+        complex64 IQ) holding exactly the samples the reference chain returns for it."""
+        torch = _torch()
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.complex64):
+            raise TypeError("apply() wants a cuda complex64 tensor; use apply_host() for numpy")
+        if x.dim() != 1:
+            raise TypeError("The signal array must be 1-D")
+        if x.device.index != self.device:
+            raise ValueError("tensor is on cuda:%d, chain on cuda:%d" % (x.device.index, self.device))
+        x = x.contiguous()
+        n = x.numel()
+        m = self.out_count(n)
+        dt = torch.float32 if self.demod else torch.complex64
+        if out is None:
+            out = torch.empty(m, dtype=dt, device=x.device)
+        elif out.dtype != dt or out.numel() < m or not out.is_contiguous():
+            raise ValueError("out tensor must be contiguous %s with >= %d elements" % (dt, m))
+        got = C.c_int64()
+        _lib.check(self._l.ddm_chain_apply_dev(self._h, C.c_void_p(x.data_ptr()), n,
+                                               C.c_void_p(out.data_ptr()), out.numel(),
+                                               C.byref(got), _stream_ptr(self.device)),
+                   "ddm_chain_apply_dev")
+        return out[:got.value]
+
+    def apply_host(self, x, out=None):
+        """x: host complex64 array (numpy, or a pinned torch tensor).  Copies in, runs the
+        chain, copies the result back; returns a numpy array."""
+        if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
+            x = x.numpy()
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        if x.ndim != 1:
+            raise TypeError("The signal array must be 1-D")
+        n = x.size
+        m = self.out_count(n)
+        dt = np.float32 if self.demod else np.complex64
+        if out is None:
+            out = np.empty(m, dtype=dt)
+        elif hasattr(out, "numpy") and not isinstance(out, np.ndarray):
+            out = out.numpy()
+        if out.dtype != dt or out.size < m or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous %s array with >= %d elements" % (dt, m))
+        got = C.c_int64()
+        _lib.check(self._l.ddm_chain_apply_host(self._h, C.c_void_p(x.ctypes.data), n,
+                                                C.c_void_p(out.ctypes.data), out.size,
+                                                C.byref(got), _stream_ptr(self.device)),
+                   "ddm_chain_apply_host")
+        return out[:got.value]

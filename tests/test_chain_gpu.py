@@ -1,0 +1,142 @@
+"""GPU parity of the fused chain (ddm_chain_* through the C ABI) against the oracle and the
+golden fixtures generated from the unmodified reference."""
+
+import numpy as np
+import pytest
+
+from oracle import ddoracle as O
+from tests.util import TOL, fm_tone_c64, noise_c64, oracle_chain, random_cuts, wrap_rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+def run_chain(x, fs, f, taps, decim, cuts, demod=True, host=True):
+    import torch
+    from directdemod_b200.fused import FusedChain
+    ch = FusedChain(taps, decim, f, fs, demod=demod)
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if host:
+            parts.append(np.array(ch.apply_host(x[a:b])))
+        else:
+            xd = torch.from_numpy(np.ascontiguousarray(x[a:b])).cuda()
+            parts.append(ch.apply(xd).cpu().numpy())
+    ch.close()
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("name", ["chain_noise_d34", "chain_fmtone_d34", "chain_fmtone_d68", "chain_noise_d50"])
+def test_chain_matches_reference_golden(golden, name):
+    g = golden(name)
+    x, fs, f, bw = g["x"], int(g["fs"]), float(g["f_off"]), int(g["bw"])
+    taps = O.taps_blackman_harris(151)[0]
+    decim = int(fs / bw)
+    for tag, cs in (("whole", len(x) + 1), ("c2500", 2500), ("c1111", 1111), ("c97", 97)):
+        cuts = [a for a, _ in O.chunk_bounds(len(x), cs)] + [len(x)]
+        fm = run_chain(x, fs, f, taps, decim, cuts, demod=True)
+        assert fm.shape == g["fm_" + tag].shape, tag
+        assert wrap_rel_rms(fm, g["fm_" + tag]) <= TOL, (tag, wrap_rel_rms(fm, g["fm_" + tag]))
+        iq = run_chain(x, fs, f, taps, decim, cuts, demod=False)
+        assert iq.shape == g["iq_" + tag].shape, tag
+        assert O.rel_rms(iq, g["iq_" + tag]) <= TOL, (tag, O.rel_rms(iq, g["iq_" + tag]))
+
+
+CASES = [
+    # ntaps, decim, fs, f_off, n, n_cuts
+    (151, 34, 2048000, 30000.0, 300000, 7),
+    (151, 50, 10000000, -125000.0, 200000, 5),
+    (151, 68, 2048000, 12345.678, 200000, 9),
+    (151, 34, 2048000, 0.0, 100000, 3),        # no mixer
+    (31, 2, 48000, 1000.0, 50000, 6),
+    (7, 4, 40, 3.0, 5000, 12),
+    (255, 32, 2400000, 100000.0, 150000, 4),
+    (492, 64, 2048000, -30000.0, 150000, 4),
+    (1, 2, 1000, 10.0, 4000, 3),               # single tap
+    (151, 33, 2048000, 30000.0, 60000, 5),     # odd decimation -> general path
+    (151, 1, 60235, 500.0, 20000, 4),          # no decimation -> general path
+    (600, 8, 2048000, 30000.0, 30000, 3),      # Q > 8 -> general path
+]
+
+
+@pytest.mark.parametrize("ntaps,decim,fs,f,n,ncuts", CASES)
+@pytest.mark.parametrize("demod", [True, False])
+def test_chain_matches_oracle_random_chunking(ntaps, decim, fs, f, n, ncuts, demod):
+    taps = O.taps_blackman_harris(ntaps)[0] if ntaps > 1 else np.array([0.7])
+    x = fm_tone_c64(ntaps * 1000 + decim, n, fs, f, fs / decim / 40.0, 2.0) if demod \
+        else noise_c64(ntaps * 1000 + decim, n)
+    cuts = random_cuts(decim, n, ncuts, small=2)
+    want, _ = oracle_chain(x, fs, f, taps, fs / decim, cuts, demod)
+    got = run_chain(x, fs, f, taps, decim, cuts, demod, host=(ncuts % 2 == 0))
+    assert got.shape == want.shape
+    err = wrap_rel_rms(got, want) if demod else O.rel_rms(got, want)
+    assert err <= TOL, err
+
+
+def test_tiny_chunks_shorter_than_decimation_and_halo():
+    # chunks of 1..40 samples with D = 34: many calls produce no output at all
+    fs, f, decim = 2048000, 30000.0, 34
+    taps = O.taps_blackman_harris(151)[0]
+    x = fm_tone_c64(5, 3000, fs, f, 2000.0, 2.0)
+    rng = np.random.default_rng(9)
+    cuts = [0]
+    while cuts[-1] < len(x):
+        cuts.append(min(len(x), cuts[-1] + int(rng.integers(1, 41))))
+    # the reference itself raises on an empty decimated chunk (demod_fm.py:44 indexes sig[-1]),
+    # so compare the un-demodulated IQ, which it does define, plus FM against the whole-run
+    want_iq, _ = oracle_chain(x, fs, f, taps, fs / decim, cuts, demod=False)
+    got_iq = run_chain(x, fs, f, taps, decim, cuts, demod=False)
+    assert got_iq.shape == want_iq.shape and O.rel_rms(got_iq, want_iq) <= TOL
+    want_fm, _ = oracle_chain(x, fs, f, taps, fs / decim, [0, len(x)], demod=True)
+    got_fm = run_chain(x, fs, f, taps, decim, cuts, demod=True)
+    assert got_fm.shape == want_fm.shape and wrap_rel_rms(got_fm, want_fm) <= TOL
+
+
+def test_empty_chunk_and_capacity_error():
+    import torch
+    from directdemod_b200 import _lib
+    from directdemod_b200.fused import FusedChain
+    ch = FusedChain(O.taps_blackman_harris(151)[0], 34, 30000.0, 2048000)
+    assert ch.apply_host(np.zeros(0, dtype=np.complex64)).size == 0
+    assert ch.position == (0, 0, False)
+    x = torch.zeros(34 * 10, dtype=torch.complex64, device="cuda")
+    small = torch.empty(3, dtype=torch.float32, device="cuda")
+    with pytest.raises(ValueError):
+        ch.apply(x, out=small)
+    out = ch.apply(x)
+    assert out.numel() == 9 and ch.position == (340, 0, True)
+    with pytest.raises(_lib.DdmError):
+        FusedChain([1.0], 0, 0.0, 48000)
+    ch.close()
+
+
+def test_full_chunk_tone_property_and_chunk_invariance():
+    """Size-independent checks at the reference's real chunk size (20 M samples): a pure tone
+    at f_off + df must demodulate to the constant 2*pi*df*D/fs everywhere (including at
+    global indices ~1.8e9 where fp32 phase would be useless), and splitting the stream at
+    arbitrary points must not change the result."""
+    import torch
+    from directdemod_b200.fused import FusedChain
+    fs, f, decim, df = 2048000, 30000.0, 34, 1500.0
+    taps = O.taps_blackman_harris(151)[0]
+    n = 20000000
+    n_start = 1800000000                      # near the end of a 15-minute pass
+    idx = torch.arange(n_start, n_start + n, device="cuda", dtype=torch.float64)
+    ph = torch.remainder(idx * ((f + df) / fs), 1.0) * (2 * np.pi)
+    x = torch.polar(torch.full_like(ph, 50.0), ph).to(torch.complex64)
+    del idx, ph
+    ch = FusedChain(taps, decim, f, fs)
+    ch.set_position(n_start, 0, False)
+    y = ch.apply(x)
+    want = 2 * np.pi * df * decim / fs
+    steady = y[10:]
+    assert steady.numel() == (n + decim - 1) // decim - 1 - 10
+    assert float((steady - want).abs().max()) < 2e-5
+    # same stream in three uneven pieces
+    ch2 = FusedChain(taps, decim, f, fs)
+    ch2.set_position(n_start, 0, False)
+    parts = [ch2.apply(x[:7000001]), ch2.apply(x[7000001:7000050]), ch2.apply(x[7000050:])]
+    y2 = torch.cat(parts)
+    assert y2.shape == y.shape
+    assert float((y2 - y).abs().max()) < 1e-5
+    ch.close()
+    ch2.close()

@@ -1,0 +1,54 @@
+"""Helpers shared by the parity tests."""
+
+import numpy as np
+
+from oracle import ddoracle as O
+
+# Tolerance of BASELINE.json's north_star: fp32 compute vs the reference's float64 scipy
+# path, relative RMS error <= 1e-5.
+TOL = 1e-5
+
+
+def wrap_rel_rms(got, want):
+    """Relative RMS error of phase-valued data, compared modulo 2*pi (an FM sample sitting
+    at +-pi may legitimately land on either side)."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    err = np.angle(np.exp(1j * (got - want)))
+    den = np.sqrt(np.mean(want ** 2))
+    return float(np.sqrt(np.mean(err ** 2)) / den) if den > 0 else float(np.sqrt(np.mean(err ** 2)))
+
+
+def noise_c64(seed, n, scale=40.0):
+    rng = np.random.default_rng(seed)
+    return ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * scale).astype(np.complex64)
+
+
+def fm_tone_c64(seed, n, fs, f_off, f_mod, beta, amp=60.0, noise=2.0):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    ph = 2 * np.pi * f_off * t + beta * np.sin(2 * np.pi * f_mod * t)
+    x = amp * np.exp(1j * ph) + noise * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x.astype(np.complex64)
+
+
+def random_cuts(seed, n, k, small=0):
+    """k random chunk boundaries over [0, n], optionally with a few tiny chunks mixed in."""
+    rng = np.random.default_rng(seed)
+    cuts = set(rng.integers(1, n, size=k).tolist()) if n > 1 else set()
+    base = sorted(cuts)
+    for c in base[:small]:
+        for d in (1, 2, 3):
+            if c + d < n:
+                cuts.add(c + d)
+    return [0] + sorted(cuts) + [n]
+
+
+def oracle_chain(x, fs, f, taps, target, cuts, demod=True):
+    st = O.ChainState(taps)
+    parts = []
+    rate = None
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        y, rate = O.chain_chunk(x[a:b], fs, f, taps, target, st, demod)
+        parts.append(y)
+    return np.concatenate(parts), rate
