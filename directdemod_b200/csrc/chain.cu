@@ -18,7 +18,7 @@
 // (8 B in per sample, 4/D B out) plus a Q/(NT-Q) halo re-read that is served by L2.
 //
 // Staging.  A CTA walks tiles of NT blocks (NT*D contiguous samples).  Each tile is brought
-// into a double-buffered shared-memory stage by the TMA engine with 1-D bulk copies
+// into a shared-memory ring of kChainStages stages by the TMA engine with 1-D bulk copies
 // (cp.async.bulk, SASS UBLKCP) that signal an mbarrier; the first tile's copy is split
 // between the carried halo buffer and the chunk.
 #include <cmath>
@@ -32,7 +32,8 @@ namespace ddm {
 
 constexpr int kChainThreads = 128;   // blocks (threads) per tile
 constexpr int kChainMaxQ = 8;
-constexpr int kChainCtasPerSm = 3;
+constexpr int kChainCtasPerSm = 2;
+constexpr int kChainStages = 2;      // TMA stages per CTA (3 stages drop occupancy to 1 CTA/SM: measured slower)
 
 struct ChainParams {
     const float2 *x;       // chunk, n samples
@@ -62,8 +63,9 @@ chain_fused_kernel(const ChainParams P) {
     const int tid = threadIdx.x;
     const int D = P.D, DP = P.DP;
     // ---- shared memory carve-up ----
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);                 // 2 barriers
-    float *s_taps = reinterpret_cast<float *>(smem_raw + 16);                // Q*DP floats
+    constexpr int S = kChainStages;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);                 // S barriers (<= 4)
+    float *s_taps = reinterpret_cast<float *>(smem_raw + 32);                // Q*DP floats
     float2 *s_rot = reinterpret_cast<float2 *>(s_taps + Q * DP);             // DP float2
     float2 *s_e = s_rot + DP;                                                // 2*Q*NT float2
     const size_t stage_bytes = static_cast<size_t>(NT) * D * sizeof(float2);
@@ -71,8 +73,7 @@ chain_fused_kernel(const ChainParams P) {
         (reinterpret_cast<uintptr_t>(s_e + 2 * Q * NT) + 127) & ~static_cast<uintptr_t>(127));
 
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
         fence_mbar_init();
     }
     for (int i = tid; i < Q * DP; i += NT) s_taps[i] = P.taps[i];
@@ -85,41 +86,48 @@ chain_fused_kernel(const ChainParams P) {
     // thread 0: start the TMA copies that fill one stage with tile `tile`
     auto issue = [&](long long tile, int stage) {
         unsigned char *dst = s_stage0 + stage * stage_bytes;
-        const long long S = P.b0 + (tile * J - Q) * D;             // first sample (may be < 0)
-        long long E = S + static_cast<long long>(NT) * D;
+        const long long S0 = P.b0 + (tile * J - Q) * D;            // first sample (may be < 0)
+        long long E = S0 + static_cast<long long>(NT) * D;
         if (E > end_all) E = end_all;
         uint32_t bytes = 0;
         const long long h_end = E < 0 ? E : 0;
-        const long long c_beg = S > 0 ? S : 0;
+        const long long c_beg = S0 > 0 ? S0 : 0;
         const long long c_end = E < n_even ? E : n_even;
-        if (S < 0) bytes += static_cast<uint32_t>((h_end - S) * 8);
+        if (S0 < 0) bytes += static_cast<uint32_t>((h_end - S0) * 8);
         if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 8);
         // tail: the odd last sample of the chunk and the zero pad behind it
         long long t_beg = c_beg > n_even ? c_beg : n_even;
         for (long long i = t_beg; i < E; ++i) {
             float2 v = i < P.n ? P.x[i] : make_float2(0.f, 0.f);
-            reinterpret_cast<float2 *>(dst)[i - S] = v;
+            reinterpret_cast<float2 *>(dst)[i - S0] = v;
         }
         mbar_arrive_expect_tx(&mbar[stage], bytes);
-        if (S < 0)
-            bulk_g2s(dst, P.halo + (P.H + S), static_cast<uint32_t>((h_end - S) * 8), &mbar[stage]);
+        if (S0 < 0)
+            bulk_g2s(dst, P.halo + (P.H + S0), static_cast<uint32_t>((h_end - S0) * 8), &mbar[stage]);
         if (c_end > c_beg)
-            bulk_g2s(dst + (c_beg - S) * 8, P.x + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8),
+            bulk_g2s(dst + (c_beg - S0) * 8, P.x + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8),
                      &mbar[stage]);
     };
 
     long long tile = blockIdx.x;
-    if (tid == 0 && tile < P.num_tiles) issue(tile, 0);
+    if (tid == 0) {
+        for (int i = 0; i < S - 1; ++i) {
+            const long long t = tile + static_cast<long long>(i) * gridDim.x;
+            if (t < P.num_tiles) issue(t, i);
+        }
+    }
 
     const int D4 = D & ~3;
     for (int it = 0; tile < P.num_tiles; tile += gridDim.x, ++it) {
-        const int stage = it & 1;
-        const long long nxt = tile + gridDim.x;
+        const int stage = it % S;
+        const long long nxt = tile + static_cast<long long>(S - 1) * gridDim.x;
         if (tid == 0 && nxt < P.num_tiles) {
+            // the stage being refilled was consumed in iteration it-1 (all threads are past
+            // that iteration's __syncthreads)
             fence_proxy_async();
-            issue(nxt, stage ^ 1);
+            issue(nxt, (it + S - 1) % S);
         }
-        mbar_wait(&mbar[stage], (it >> 1) & 1);
+        mbar_wait(&mbar[stage], (it / S) & 1);
 
         const long long jblk = tile * J - Q + tid;          // this thread's block index
         float2 *e_buf = s_e + (it & 1) * (Q * NT);
@@ -228,8 +236,8 @@ chain_fused_kernel(const ChainParams P) {
 struct GenericParams {
     const float2 *x;
     const float2 *halo;
-    float2 *y;             // y[m+1] for m = -1..M-1
-    const float *taps;     // K taps
+    double2 *y;            // y[m+1] for m = -1..M-1
+    const double *taps;    // K taps
     long long n, n0, M, off;
     double r_hi, r_lo;
     int K, D, H, mix;
@@ -240,33 +248,35 @@ __global__ void chain_generic_y_kernel(const GenericParams P) {
     if (idx > P.M) return;
     const long long m = idx - 1;
     const long long pos = P.off + m * P.D;          // chunk coordinates, may be negative
-    float2 acc = make_float2(0.f, 0.f);
+    // fp64 accumulation: at D = 1 consecutive outputs differ by a tiny rotation, so the
+    // discriminator needs more than fp32's ~1e-7 rad floor to stay within 1e-5 relative
+    double ax = 0.0, ay = 0.0;
     for (int k = 0; k < P.K; ++k) {
         const long long i = pos - k;
         if (i < -static_cast<long long>(P.H)) break;
         float2 v = i >= 0 ? P.x[i] : P.halo[P.H + i];
         if (P.mix) v = cmul(v, phase_rotator(P.r_hi, P.r_lo, P.n0 + i));
-        const float t = P.taps[k];
-        acc.x = fmaf(t, v.x, acc.x);
-        acc.y = fmaf(t, v.y, acc.y);
+        const double t = P.taps[k];
+        ax = fma(t, static_cast<double>(v.x), ax);
+        ay = fma(t, static_cast<double>(v.y), ay);
     }
-    P.y[idx] = acc;
+    P.y[idx] = make_double2(ax, ay);
 }
 
-__global__ void chain_generic_out_kernel(const float2 *y, void *out, long long M, int has_prev,
+__global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
                                          int out_mode) {
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (m >= M) return;
-    const float2 c = y[m + 1];
+    const double2 c = y[m + 1];
     if (out_mode == DDM_CHAIN_OUT_IQ) {
-        reinterpret_cast<float2 *>(out)[m] = c;
+        reinterpret_cast<float2 *>(out)[m] = make_float2(static_cast<float>(c.x), static_cast<float>(c.y));
         return;
     }
     if (m == 0 && !has_prev) return;
-    const float2 p = y[m];
-    const float re = fmaf(c.x, p.x, c.y * p.y);
-    const float im = fmaf(c.y, p.x, -c.x * p.y);
-    reinterpret_cast<float *>(out)[m - (has_prev ? 0 : 1)] = atan2f(im, re);
+    const double2 p = y[m];
+    const double re = fma(c.x, p.x, c.y * p.y);
+    const double im = fma(c.y, p.x, -c.x * p.y);
+    reinterpret_cast<float *>(out)[m - (has_prev ? 0 : 1)] = static_cast<float>(atan2(im, re));
 }
 
 }  // namespace ddm
@@ -286,12 +296,12 @@ struct ddm_chain {
     int Q[2] = {0, 0};
     int per_sm[2] = {0, 0};                  // resident CTAs per SM of the fused kernel, per s
     float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
-    float *d_taps_lin = nullptr;             // K
+    double *d_taps_lin = nullptr;            // K
     float2 *d_rot = nullptr;                 // DP
     float2 *d_halo[2] = {nullptr, nullptr};
     float2 *d_halo_init = nullptr;           // the reference's initial condition as raw history
     int cur = 0;
-    float2 *d_ytmp = nullptr;
+    double2 *d_ytmp = nullptr;
     size_t ytmp_cap = 0;
     void *d_in = nullptr, *d_out = nullptr;  // staging for the _host entry point
     size_t in_cap = 0, out_cap = 0;
@@ -304,10 +314,10 @@ namespace {
 using namespace ddm;
 
 size_t chain_smem_bytes(int Q, int D, int DP) {
-    size_t fixed = 16 + sizeof(float) * Q * DP + sizeof(float2) * DP +
+    size_t fixed = 32 + sizeof(float) * Q * DP + sizeof(float2) * DP +
                    sizeof(float2) * 2 * Q * kChainThreads;
     fixed = (fixed + 127) & ~static_cast<size_t>(127);
-    return fixed + 128 + 2 * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
+    return fixed + 128 + kChainStages * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
 }
 
 template <int Q, bool MIX, int OUT>
@@ -458,11 +468,9 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
         }
     }
     {
-        std::vector<float> lin(K);
-        for (int k = 0; k < K; ++k) lin[k] = static_cast<float>(taps[k]);
-        e = cudaMalloc(&c->d_taps_lin, sizeof(float) * K);
+        e = cudaMalloc(&c->d_taps_lin, sizeof(double) * K);
         if (e == cudaSuccess)
-            e = cudaMemcpy(c->d_taps_lin, lin.data(), sizeof(float) * K, cudaMemcpyHostToDevice);
+            e = cudaMemcpy(c->d_taps_lin, taps, sizeof(double) * K, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             set_error("tap upload failed: %s", cudaGetErrorString(e));
             return fail(DDM_ERR_CUDA);
@@ -635,7 +643,7 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
                 cudaFree(c->d_ytmp);
                 c->d_ytmp = nullptr;
                 c->ytmp_cap = 0;
-                DDM_CUDA(cudaMalloc(&c->d_ytmp, sizeof(float2) * need));
+                DDM_CUDA(cudaMalloc(&c->d_ytmp, sizeof(double2) * need));
                 c->ytmp_cap = need;
             }
             GenericParams g{};

@@ -62,7 +62,10 @@ CASES = [
 @pytest.mark.parametrize("demod", [True, False])
 def test_chain_matches_oracle_random_chunking(ntaps, decim, fs, f, n, ncuts, demod):
     taps = O.taps_blackman_harris(ntaps)[0] if ntaps > 1 else np.array([0.7])
-    x = fm_tone_c64(ntaps * 1000 + decim, n, fs, f, fs / decim / 40.0, 2.0) if demod \
+    # keep the FM tone's sidebands inside the FIR passband (~fs/ntaps) so the demodulated
+    # signal -- the denominator of the relative error -- is the tone, not residual noise
+    f_mod = min(fs / decim / 40.0, 0.1 * fs / ntaps)
+    x = fm_tone_c64(ntaps * 1000 + decim, n, fs, f, f_mod, 2.0) if demod \
         else noise_c64(ntaps * 1000 + decim, n)
     cuts = random_cuts(decim, n, ncuts, small=2)
     want, _ = oracle_chain(x, fs, f, taps, fs / decim, cuts, demod)
