@@ -21,6 +21,7 @@ IN_CF32, IN_CU8 = 0, 1
 
 _vp, _i64, _int, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_double
 _pi64, _pint = C.POINTER(C.c_int64), C.POINTER(C.c_int)
+_pdbl = C.POINTER(C.c_double)
 
 # name -> (restype, argtypes); mirrors include/ddemod.h one to one
 SIGNATURES = {
@@ -28,7 +29,7 @@ SIGNATURES = {
     "ddm_last_error": (C.c_char_p, []),
     "ddm_launch_count": (_i64, []),
     "ddm_device_count": (_int, [_pint]),
-    "ddm_chain_create": (_int, [_int, C.POINTER(_dbl), _int, _int, _dbl, _dbl, _int, _int,
+    "ddm_chain_create": (_int, [_int, _pdbl, _int, _int, _dbl, _dbl, _int, _int,
                                 C.POINTER(_vp)]),
     "ddm_chain_destroy": (_int, [_vp]),
     "ddm_chain_reset": (_int, [_vp]),
@@ -37,8 +38,28 @@ SIGNATURES = {
     "ddm_chain_get_position": (_int, [_vp, _pi64, _pi64, _pint]),
     "ddm_chain_set_position": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "ddm_chain_get_halo": (_int, [_vp, _vp, _vp]),
+    "ddm_chain_export_state": (_int, [_vp, _pdbl, _pdbl, _vp]),
     "ddm_chain_apply_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _pi64, _vp]),
     "ddm_chain_apply_host": (_int, [_vp, _vp, _i64, _vp, _i64, _pi64, _vp]),
+    "ddm_mix_cf32": (_int, [_int, _vp, _i64, _dbl, _dbl, _i64, _vp]),
+    "ddm_mix_var_cf32": (_int, [_int, _vp, _vp, _i64, _dbl, _i64, _vp]),
+    "ddm_fm_demod": (_int, [_int, _vp, _i64, _vp, _vp, _pi64, _vp]),
+    "ddm_fm_angle_diff": (_int, [_int, _vp, _i64, _vp, _vp, _vp, _pi64, _vp]),
+    "ddm_abs": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
+    "ddm_stride_copy": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _pi64, _vp]),
+    "ddm_cu8_to_cf32": (_int, [_int, _vp, _i64, _vp, _vp]),
+    "ddm_filter_create": (_int, [_int, _pdbl, _int, _pdbl, _int, C.POINTER(_vp)]),
+    "ddm_filter_destroy": (_int, [_vp]),
+    "ddm_filter_state_len": (_int, [_vp, _pint]),
+    "ddm_filter_set_state": (_int, [_vp, _pdbl, _vp]),
+    "ddm_filter_get_state": (_int, [_vp, _pdbl, _vp]),
+    "ddm_filter_reset": (_int, [_vp, _vp]),
+    "ddm_filter_set_zi_base": (_int, [_vp, _pdbl]),
+    "ddm_filter_set_iir_mode": (_int, [_vp, _int]),
+    "ddm_filter_info": (_int, [_vp, _pint, _pi64, _pdbl]),
+    "ddm_filter_apply_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),
+    "ddm_filter_filtfilt_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "ddm_lfilter_zi": (_int, [_pdbl, _int, _pdbl, _int, _pdbl]),
 }
 
 _lib = None

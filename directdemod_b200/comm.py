@@ -1,0 +1,327 @@
+"""Signal container with chainable operators (directdemod/comm.py:15-181), GPU backed.
+
+Same constructor, properties and methods as the reference's ``commSignal``.  The samples
+live on the GPU between operators; ``.signal`` hands back a numpy array in the reference's
+dtype.  Operators that form the hot chain
+
+    offsetFreq(f) -> filter(<stateful FIR>) -> bwLim(rate) -> funcApply(demod_fm().demod)
+
+(decode_noaa.py:623, decode_fm.py:64-68, decode_afsk1200.py:79-91) are queued and executed
+as ONE fused kernel launch per chunk (directdemod_b200/fused.py, csrc/chain.cu); anything
+else runs operator by operator on the device.  All carried state (mixer sample index and
+decimation phase in the chunker, filter delay line, FM last sample) keeps the reference's
+meaning and can move between the fused and the stand-alone kernels at any chunk boundary.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _dev, _lib, constants
+from . import demod_fm as _demod_fm
+from . import filters as _filters
+from .fused import FusedChain
+
+
+def _is_cuda_tensor(x):
+    return _dev.is_tensor(x) and x.is_cuda
+
+
+class commSignal:
+    def __init__(self, sampRate, sig=np.array([]), chunker=None):
+        """sampRate: Hz, forced to int, must be > 0 (ValueError); sig: 1-D array (TypeError
+        otherwise), copied; chunker: chunker object when the signal is processed in chunks."""
+        self._chunker = chunker
+        self._len = len(sig)
+        self._sampRate = int(sampRate)
+        if self._sampRate <= 0:
+            raise ValueError("The sampling rate must be greater than zero")
+        self._pending = []
+        self._host = None
+        self._dev = None
+        if _is_cuda_tensor(sig):
+            if sig.dim() != 1:
+                raise TypeError("The signal array must be 1-D")
+            self._dev = _dev.to_device(sig).clone()
+            self._complex = bool(sig.is_complex())
+        else:
+            arr = np.array(sig)
+            if arr.ndim != 1:
+                raise TypeError("The signal array must be 1-D")
+            self._host = arr
+            self._complex = bool(np.iscomplexobj(arr))
+
+    # ---- properties -----------------------------------------------------------------
+    @property
+    def length(self):
+        return self._len
+
+    @property
+    def sampRate(self):
+        return self._sampRate
+
+    @property
+    def signal(self):
+        """The samples as a numpy array (float64 / complex128 once an operator has run)."""
+        self._flush()
+        if self._host is None:
+            self._host = _dev.to_host(self._dev)
+            self._dev = None          # the caller may now mutate the array it was given
+        return self._host
+
+    @property
+    def deviceSignal(self):
+        """The samples as a cuda tensor (float32 / complex64), without a host round trip."""
+        self._flush()
+        return self._device_array()
+
+    def _device_array(self):
+        if self._dev is None:
+            self._dev = _dev.to_device(self._host)
+            self._host = None
+        return self._dev
+
+    # ---- operators ------------------------------------------------------------------
+    def offsetFreq(self, freqOffset):
+        """x[n] *= exp(-j 2 pi f (n0 + n) / fs) with the global sample index n0 carried in the
+        chunker variable "freqoffset" (comm.py:63-78).  f may be a per-sample array."""
+        offset = 0
+        if self._chunker is not None:
+            offset = self._chunker.get(constants.CHUNK_FREQOFFSET, 0)
+            self._chunker.set(constants.CHUNK_FREQOFFSET, offset + self.length)
+        if not self._complex:
+            # the reference multiplies a real array by a complex one in place -> numpy refuses
+            raise TypeError("Cannot cast ufunc 'multiply' output from dtype('complex128') to a real dtype")
+        if np.ndim(freqOffset) != 0:
+            f = np.ascontiguousarray(np.asarray(freqOffset, dtype=np.float64).ravel())
+            if f.size != self.length:
+                raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)"
+                                 % (self.length, f.size))
+            self._flush()
+            self._run_mix_var(f, offset)
+            return self
+        if self._pending:            # a mixer can only open a fused chain
+            self._flush()
+        self._pending.append(("mix", float(freqOffset), int(offset), self._sampRate))
+        return self
+
+    def filter(self, filt):
+        """Apply a filter object (anything with ``applyOn``), comm.py:80-92."""
+        if isinstance(filt, _filters.filter):
+            fusable = (filt.isFIR and filt._storeState and not filt._needs_lfiltic and self._complex
+                       and all(op[0] == "mix" for op in self._pending))
+            if not fusable:
+                self._flush()
+            self._claim(filt)
+            self._pending.append(("filter", filt))
+            return self
+        self._flush()
+        if getattr(filt, "_ddm_native", False):
+            self._set_device(filt.applyOn(self._device_array()))
+        else:
+            self.updateSignal(filt.applyOn(self.signal))
+        return self
+
+    def bwLim(self, tsampRate, strict=False, uniq="abcd"):
+        """Limit the bandwidth by decimation (comm.py:94-130).  Non strict: keep every
+        int(fs/t)-th sample, phase carried in chunker variable "bwlim"+uniq, new rate
+        int(fs/j).  strict: FFT resample of this chunk to exactly t (no carry)."""
+        if self._sampRate < tsampRate:
+            raise ValueError("The target sampling rate must be less than current sampling rate")
+        if strict:
+            from . import fftops
+            self._flush()
+            num = int(tsampRate * self.length / self.sampRate)
+            self._set_device(fftops.resample(self._device_array(), num))
+            self._sampRate = tsampRate
+            return self
+        jump = int(self.sampRate / tsampRate)
+        offset = 0
+        if self._chunker is not None:
+            offset = self._chunker.get(constants.CHUNK_BWLIM + uniq, 0)
+            nxt = (jump - (self.length - offset) % jump) % jump
+            self._chunker.set(constants.CHUNK_BWLIM + uniq, nxt)
+        if not (self._pending and self._pending[-1][0] == "filter"):
+            self._flush()
+        self._pending.append(("decim", jump, int(offset)))
+        self._len = len(range(offset, self._len, jump))
+        self._sampRate = int(self.sampRate / jump)
+        return self
+
+    def funcApply(self, func):
+        """Apply a callable to the signal array (comm.py:132-144)."""
+        owner = getattr(func, "__self__", None)
+        if isinstance(owner, _demod_fm.demod_fm) and getattr(func, "__name__", "") == "demod":
+            if not self._complex:
+                self._flush()
+                self._set_device(owner.demod(self._device_array()))
+                return self
+            if owner._storeState and self._len == 0:
+                self._flush()
+                raise IndexError("index -1 is out of bounds for axis 0 with size 0")
+            self._claim(owner)
+            has_prev = owner._storeState and not owner._fresh
+            self._pending.append(("fm", owner))
+            self._len = self._len if has_prev else max(self._len - 1, 0)
+            self._complex = False
+            self._flush()            # the discriminator closes the fusable pattern
+            return self
+        self._flush()
+        if getattr(owner, "_ddm_native", False):
+            self._set_device(func(self._device_array()))
+        else:
+            self.updateSignal(func(self.signal))
+        return self
+
+    def extend(self, sig):
+        """Append another commSignal (comm.py:146-164)."""
+        if self.length == 0:
+            self._sampRate = sig.sampRate
+        if not self._sampRate == sig.sampRate:
+            raise TypeError("Signals must have same sampling rate to be extended")
+        self.updateSignal(np.concatenate([self.signal, sig.signal]))
+        return self
+
+    def updateSignal(self, sig):
+        """Replace the samples (comm.py:166-181)."""
+        self._pending = []
+        if _is_cuda_tensor(sig):
+            if sig.dim() != 1:
+                raise TypeError("The signal array must be 1-D")
+            self._set_device(_dev.to_device(sig))
+            return self
+        arr = np.array(sig)
+        if arr.ndim != 1:
+            raise TypeError("The signal array must be 1-D")
+        self._host = arr
+        self._dev = None
+        self._len = len(arr)
+        self._complex = bool(np.iscomplexobj(arr))
+        return self
+
+    # ---- execution ------------------------------------------------------------------
+    def _set_device(self, tensor):
+        self._dev = tensor
+        self._host = None
+        self._len = int(tensor.numel())
+        self._complex = bool(tensor.is_complex())
+
+    def _claim(self, obj):
+        """A stateful operator object may be queued in one signal at a time; run whoever
+        queued it before so state is consumed in call order."""
+        other = getattr(obj, "_pending_owner", None)
+        if other is not None and other is not self:
+            other._flush()
+        obj._pending_owner = self
+
+    def _flush(self):
+        ops = self._pending
+        if not ops:
+            return
+        self._pending = []
+        x = self._device_array()
+        i = 0
+        try:
+            while i < len(ops):
+                took, y = self._try_fused(ops, i, x)
+                if took:
+                    x = y
+                    i += took
+                    continue
+                x = self._run_single(ops[i], x)
+                i += 1
+        finally:
+            for op in ops:
+                if op[0] in ("filter", "fm") and getattr(op[1], "_pending_owner", None) is self:
+                    op[1]._pending_owner = None
+        self._dev = x
+        self._host = None
+        self._len = int(x.numel())
+        self._complex = bool(x.is_complex())
+
+    def _try_fused(self, ops, i, x):
+        """Match [mix] filter [decim] [fm] at ops[i:] and run it as one fused launch."""
+        j = i
+        mix = filt = dec = fm = None
+        if j < len(ops) and ops[j][0] == "mix":
+            mix = ops[j]
+            j += 1
+        if j < len(ops) and ops[j][0] == "filter":
+            filt = ops[j][1]
+            j += 1
+        else:
+            return 0, None
+        if j < len(ops) and ops[j][0] == "decim":
+            dec = ops[j]
+            j += 1
+        if j < len(ops) and ops[j][0] == "fm":
+            fm = ops[j][1]
+            j += 1
+        if dec is None or dec[1] < 2 or not x.is_complex():
+            return 0, None          # without a decimator the stand-alone FIR kernel is the better tool
+        if not (filt.isFIR and filt._storeState and not filt._needs_lfiltic):
+            return 0, None
+        if fm is not None and not fm._storeState:
+            return 0, None
+        freq = mix[1] if mix is not None else 0.0
+        fs = mix[3] if mix is not None else 0
+        n0 = mix[2] if mix is not None else None
+        jump, off = dec[1], dec[2]
+        ch = filt._chain
+        key = (float(freq), int(fs), int(jump), fm is not None)
+        if ch is not None:
+            if getattr(ch, "_key", None) != key or ch.device != x.device.index:
+                return 0, None
+            pos_n0, pos_off, pos_prev = ch.position
+            if (n0 is not None and n0 != pos_n0) or off != pos_off:
+                return 0, None
+            if fm is not None and not (fm._chain is ch or (fm._fresh and not pos_prev)):
+                return 0, None
+        else:
+            if not filt._fresh or (n0 is not None and n0 != 0):
+                return 0, None
+            if fm is not None and not fm._fresh:
+                return 0, None
+            ch = FusedChain(filt._bd, jump, freq, fs if mix is not None else 1.0,
+                            demod=fm is not None, device=x.device.index)
+            ch._key = key
+            ch.set_position(0, off, False)
+        y = ch.apply(x)
+        filt._chain = ch
+        filt._used = True
+        if fm is not None:
+            fm._chain = ch
+            fm._last = None
+        return j - i, y
+
+    def _run_single(self, op, x):
+        kind = op[0]
+        if kind == "mix":
+            _lib.check(_lib.lib().ddm_mix_cf32(x.device.index, _dev.ptr(x), x.numel(), op[1], float(op[3]),
+                                               op[2], _dev.stream_ptr(x.device.index)), "ddm_mix_cf32")
+            return x
+        if kind == "filter":
+            return op[1]._apply_dev(x)
+        if kind == "decim":
+            jump, off = op[1], op[2]
+            n = x.numel()
+            m = len(range(off, n, jump))
+            out = _dev.empty_like_kind(m, x.is_complex(), x.device.index)
+            got = C.c_int64()
+            _lib.check(_lib.lib().ddm_stride_copy(x.device.index, _dev.ptr(x), n, 8 if x.is_complex() else 4,
+                                                  off, jump, _dev.ptr(out), C.byref(got),
+                                                  _dev.stream_ptr(x.device.index)), "ddm_stride_copy")
+            return out
+        if kind == "fm":
+            return op[1]._demod_dev(x)
+        raise RuntimeError("unknown queued operator %r" % (kind,))
+
+    def _run_mix_var(self, f, offset):
+        t = _dev.torch()
+        x = self._device_array()
+        fd = t.from_numpy(f).to(x.device)
+        _lib.check(_lib.lib().ddm_mix_var_cf32(x.device.index, _dev.ptr(x), _dev.ptr(fd), x.numel(),
+                                               float(self._sampRate), int(offset),
+                                               _dev.stream_ptr(x.device.index)), "ddm_mix_var_cf32")

@@ -590,6 +590,66 @@ int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream) {
     return DDM_OK;
 }
 
+int ddm_chain_export_state(const ddm_chain *c, double *zi_c128_host, double *last_c128_host,
+                           void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_export_state: NULL handle");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<float2> h(c->H);
+    DDM_CUDA(cudaMemcpyAsync(h.data(), c->d_halo[c->cur], sizeof(float2) * c->H, cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaStreamSynchronize(st));
+    // mixed history x'[g], g = n0-H .. n0-1, rounded to complex64 like the reference's in-place mixer
+    std::vector<double> xr(c->H), xi(c->H);
+    for (int i = 0; i < c->H; ++i) {
+        double re = h[i].x, im = h[i].y;
+        if (c->mix) {
+            const double g = static_cast<double>(c->n0 - c->H + i);
+            const double p = c->r_hi * g;
+            const double e = std::fma(c->r_hi, g, -p);
+            double t = p - std::rint(p);
+            t += e + c->r_lo * g;
+            const double cs = std::cos(2.0 * M_PI * t), sn = -std::sin(2.0 * M_PI * t);
+            const double mr = re * cs - im * sn, mi = re * sn + im * cs;
+            re = static_cast<double>(static_cast<float>(mr));
+            im = static_cast<double>(static_cast<float>(mi));
+        }
+        xr[i] = re;
+        xi[i] = im;
+    }
+    const int K = c->K;
+    if (zi_c128_host) {
+        // zi[i] = sum_{k>i} b[k] x'[n0 + i - k]
+        for (int i = 0; i < K - 1; ++i) {
+            double ar = 0, ai = 0;
+            for (int k = i + 1; k < K; ++k) {
+                const int j = c->H + i - k;
+                if (j < 0) break;
+                ar += c->taps[k] * xr[j];
+                ai += c->taps[k] * xi[j];
+            }
+            zi_c128_host[2 * i] = ar;
+            zi_c128_host[2 * i + 1] = ai;
+        }
+    }
+    if (last_c128_host) {
+        // last decimated sample y[m_last], at chunk-relative position dec_off - D
+        last_c128_host[0] = last_c128_host[1] = 0.0;
+        if (c->has_prev) {
+            const long long pos = static_cast<long long>(c->H) + c->dec_off - c->D;
+            double ar = 0, ai = 0;
+            for (int k = 0; k < K; ++k) {
+                const long long j = pos - k;
+                if (j < 0) break;
+                ar += c->taps[k] * xr[j];
+                ai += c->taps[k] * xi[j];
+            }
+            last_c128_host[0] = ar;
+            last_c128_host[1] = ai;
+        }
+    }
+    return DDM_OK;
+}
+
 int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
                         int64_t out_capacity, int64_t *n_out, void *stream) {
     DDM_REQUIRE(c != nullptr, "ddm_chain_apply_dev: NULL handle");

@@ -1,0 +1,324 @@
+// Stand-alone element-wise operators of the hot path (each also exists fused inside
+// chain.cu; these serve arbitrary user chains built from the reference's fluent API).
+//
+//   ddm_mix_cf32      commSignal.offsetFreq         comm.py:63-78
+//   ddm_mix_var_cf32  offsetFreq with a per-sample frequency array (decode_funcube.py:228)
+//   ddm_fm_demod      demod_fm.demod                demod_fm.py:29-51
+//   ddm_fm_angle_diff demod_fmAD.demod              demod_fm.py:74-96
+//   ddm_abs           np.abs (demod_am.py:29,62)
+//   ddm_stride_copy   x[off::j] of bwLim            comm.py:127
+//   ddm_cu8_to_cf32   source.read                   source.py:117-118, :209-210
+//
+// All of them are HBM-bound streaming kernels: 16-byte vector accesses where alignment
+// allows, grid = SMs x 8 CTAs grid-striding over the array.
+#include "ddm_common.cuh"
+
+namespace ddm {
+
+constexpr int kOpsThreads = 256;
+
+static inline unsigned ops_grid(int device, long long work_items) {
+    long long blocks = (work_items + kOpsThreads - 1) / kOpsThreads;
+    const long long cap = static_cast<long long>(sm_count(device)) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return static_cast<unsigned>(blocks);
+}
+
+// ---- mixer -----------------------------------------------------------------------------
+// Each thread handles 2 consecutive samples (one 16-byte access); the rotator of the first
+// is computed from the exactly reduced double-double phase, the second is first * step.
+__global__ void mix_kernel(float2 *x, long long n, long long n0, double r_hi, double r_lo,
+                           float2 step) {
+    const long long pairs = n >> 1;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < pairs;
+         p += stride) {
+        float4 v = reinterpret_cast<float4 *>(x)[p];
+        const float2 w0 = phase_rotator(r_hi, r_lo, n0 + 2 * p);
+        const float2 w1 = cmul(w0, step);
+        const float2 a = cmul(make_float2(v.x, v.y), w0);
+        const float2 b = cmul(make_float2(v.z, v.w), w1);
+        reinterpret_cast<float4 *>(x)[p] = make_float4(a.x, a.y, b.x, b.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        x[n - 1] = cmul(x[n - 1], phase_rotator(r_hi, r_lo, n0 + n - 1));
+    }
+}
+
+// generic (unaligned base pointer): one sample per thread
+__global__ void mix_kernel_scalar(float2 *x, long long n, long long n0, double r_hi, double r_lo) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        x[i] = cmul(x[i], phase_rotator(r_hi, r_lo, n0 + i));
+}
+
+// per-sample frequency: phase = f[i] * (n0 + i) / fs turns, reduced in float64
+__global__ void mix_var_kernel(float2 *x, const double *f, long long n, long long n0, double fs) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const double r = f[i] / fs;
+        const double e = fma(-r, fs, f[i]) / fs;                 // residual of the division
+        x[i] = cmul(x[i], phase_rotator(r, e, n0 + i));
+    }
+}
+
+// ---- FM discriminator ------------------------------------------------------------------
+// out[i - first] = arg(x[i] * conj(x[i-1])), i = first..n-1, where x[-1] = *prev when given.
+__global__ void fm_kernel(const float2 *x, const float2 *prev, float *out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long first = prev ? 0 : 1;
+    for (long long i = first + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += stride) {
+        const float2 c = x[i];
+        const float2 p = i > 0 ? x[i - 1] : *prev;
+        const float re = fmaf(c.x, p.x, c.y * p.y);
+        const float im = fmaf(c.y, p.x, -c.x * p.y);
+        out[i - first] = atan2f(im, re);
+    }
+}
+
+// demod_fmAD: diff(unwrap(angle(x))).  The cumulative 2*pi corrections of np.unwrap cancel
+// in the difference, so every output only needs its own two angles:
+//   d = a[i] - a[i-1];  dd = mod(d + pi, 2 pi) - pi;  if (dd == -pi && d > 0) dd = pi;
+//   out = |d| < pi ? d : dd                       (numpy/lib/function_base.py unwrap)
+__global__ void fm_ad_kernel(const float2 *x, const float *prev_angle, float *out, float *last_angle,
+                             long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long first = prev_angle ? 0 : 1;
+    const double pi = 3.14159265358979323846;
+    for (long long i = first + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += stride) {
+        const double a1 = atan2(static_cast<double>(x[i].y), static_cast<double>(x[i].x));
+        const double a0 = i > 0 ? atan2(static_cast<double>(x[i - 1].y), static_cast<double>(x[i - 1].x))
+                                : static_cast<double>(*prev_angle);
+        const double d = a1 - a0;
+        double dd = d + pi;
+        dd = dd - floor(dd / (2 * pi)) * (2 * pi) - pi;
+        if (dd == -pi && d > 0) dd = pi;
+        out[i - first] = static_cast<float>(fabs(d) < pi ? d : dd);
+        if (i == n - 1 && last_angle) *last_angle = static_cast<float>(a1);
+    }
+}
+
+// ---- misc ------------------------------------------------------------------------------
+template <typename T>
+__global__ void abs_kernel(const T *x, float *out, long long n);
+
+template <>
+__global__ void abs_kernel<float2>(const float2 *x, float *out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        out[i] = hypotf(x[i].x, x[i].y);
+}
+
+template <>
+__global__ void abs_kernel<float>(const float *x, float *out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        out[i] = fabsf(x[i]);
+}
+
+template <typename T>
+__global__ void stride_copy_kernel(const T *x, T *out, long long m, long long off, long long step) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < m; i += stride)
+        out[i] = x[off + i * step];
+}
+
+// 8 samples (16 input bytes) per thread
+__global__ void cu8_kernel(const unsigned char *in, float2 *out, long long n) {
+    const long long groups = n >> 3;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long g = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; g < groups;
+         g += stride) {
+        const uint4 v = reinterpret_cast<const uint4 *>(in)[g];
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        float4 *o = reinterpret_cast<float4 *>(out + g * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = make_float4(static_cast<float>(w[k] & 255u) - 127.5f,
+                               static_cast<float>((w[k] >> 8) & 255u) - 127.5f,
+                               static_cast<float>((w[k] >> 16) & 255u) - 127.5f,
+                               static_cast<float>(w[k] >> 24) - 127.5f);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (long long i = groups << 3; i < n; ++i)
+            out[i] = make_float2(static_cast<float>(in[2 * i]) - 127.5f,
+                                 static_cast<float>(in[2 * i + 1]) - 127.5f);
+    }
+}
+
+__global__ void cu8_kernel_scalar(const unsigned char *in, float2 *out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        out[i] = make_float2(static_cast<float>(in[2 * i]) - 127.5f,
+                             static_cast<float>(in[2 * i + 1]) - 127.5f);
+}
+
+}  // namespace ddm
+
+using namespace ddm;
+
+#define DDM_CHECK_DEVICE(device, who)                                                   \
+    do {                                                                                \
+        int ndev__ = 0;                                                                 \
+        DDM_CUDA(cudaGetDeviceCount(&ndev__));                                          \
+        DDM_REQUIRE((device) >= 0 && (device) < ndev__, who ": no such device %d", (device)); \
+    } while (0)
+
+extern "C" {
+
+int ddm_mix_cf32(int device, void *x_dev, int64_t n, double freq_offset, double samp_rate,
+                 int64_t n0, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_mix_cf32: negative length");
+    DDM_REQUIRE(samp_rate > 0, "ddm_mix_cf32: sampling rate must be positive");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr, "ddm_mix_cf32: NULL signal");
+    DDM_CHECK_DEVICE(device, "ddm_mix_cf32");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double r_hi = freq_offset / samp_rate;
+    const double r_lo = std::fma(-r_hi, samp_rate, freq_offset) / samp_rate;
+    if ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0) {
+        const double t = r_hi - std::rint(r_hi);
+        const float2 step = make_float2(static_cast<float>(std::cos(2.0 * M_PI * t)),
+                                        static_cast<float>(-std::sin(2.0 * M_PI * t)));
+        mix_kernel<<<ops_grid(device, (n + 1) / 2), kOpsThreads, 0, st>>>(
+            static_cast<float2 *>(x_dev), n, n0, r_hi, r_lo, step);
+    } else {
+        mix_kernel_scalar<<<ops_grid(device, n), kOpsThreads, 0, st>>>(static_cast<float2 *>(x_dev), n,
+                                                                        n0, r_hi, r_lo);
+    }
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_mix_var_cf32(int device, void *x_dev, const double *freq_dev, int64_t n, double samp_rate,
+                     int64_t n0, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_mix_var_cf32: negative length");
+    DDM_REQUIRE(samp_rate > 0, "ddm_mix_var_cf32: sampling rate must be positive");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && freq_dev != nullptr, "ddm_mix_var_cf32: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_mix_var_cf32");
+    DeviceGuard guard(device);
+    mix_var_kernel<<<ops_grid(device, n), kOpsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float2 *>(x_dev), freq_dev, n, n0, samp_rate);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_fm_demod(int device, const void *x_dev, int64_t n, const void *prev_dev, void *out_dev,
+                 int64_t *n_out, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_fm_demod: negative length");
+    const int64_t m = prev_dev ? n : (n > 0 ? n - 1 : 0);
+    if (n_out) *n_out = m;
+    if (m == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_fm_demod: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_fm_demod");
+    DeviceGuard guard(device);
+    fm_kernel<<<ops_grid(device, m), kOpsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2 *>(x_dev), static_cast<const float2 *>(prev_dev),
+        static_cast<float *>(out_dev), n);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_angle_dev,
+                      void *out_dev, void *last_angle_dev, int64_t *n_out, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_fm_angle_diff: negative length");
+    const int64_t m = prev_angle_dev ? n : (n > 0 ? n - 1 : 0);
+    if (n_out) *n_out = m;
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr, "ddm_fm_angle_diff: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_fm_angle_diff");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (m > 0) {
+        DDM_REQUIRE(out_dev != nullptr, "ddm_fm_angle_diff: NULL output");
+        fm_ad_kernel<<<ops_grid(device, m), kOpsThreads, 0, st>>>(
+            static_cast<const float2 *>(x_dev), static_cast<const float *>(prev_angle_dev),
+            static_cast<float *>(out_dev), static_cast<float *>(last_angle_dev), n);
+        DDM_CUDA(cudaGetLastError());
+        count_launch();
+    } else if (last_angle_dev) {
+        // a single sample and no predecessor: only the carried angle is produced
+        float2 h;
+        DDM_CUDA(cudaMemcpyAsync(&h, x_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+        const float a = static_cast<float>(std::atan2(static_cast<double>(h.y), static_cast<double>(h.x)));
+        DDM_CUDA(cudaMemcpyAsync(last_angle_dev, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+    }
+    return DDM_OK;
+}
+
+int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_dev, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_abs: negative length");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_abs: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_abs");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (is_complex)
+        abs_kernel<float2><<<ops_grid(device, n), kOpsThreads, 0, st>>>(
+            static_cast<const float2 *>(x_dev), static_cast<float *>(out_dev), n);
+    else
+        abs_kernel<float><<<ops_grid(device, n), kOpsThreads, 0, st>>>(
+            static_cast<const float *>(x_dev), static_cast<float *>(out_dev), n);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, int64_t offset,
+                    int64_t step, void *out_dev, int64_t *n_out, void *stream) {
+    DDM_REQUIRE(n >= 0 && offset >= 0 && step >= 1, "ddm_stride_copy: bad length/offset/step");
+    DDM_REQUIRE(elem_bytes == 4 || elem_bytes == 8 || elem_bytes == 16,
+                "ddm_stride_copy: element size must be 4, 8 or 16 bytes");
+    const int64_t m = n > offset ? (n - offset + step - 1) / step : 0;
+    if (n_out) *n_out = m;
+    if (m == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_stride_copy: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_stride_copy");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = ops_grid(device, m);
+    if (elem_bytes == 4)
+        stride_copy_kernel<float><<<grid, kOpsThreads, 0, st>>>(
+            static_cast<const float *>(x_dev), static_cast<float *>(out_dev), m, offset, step);
+    else if (elem_bytes == 8)
+        stride_copy_kernel<float2><<<grid, kOpsThreads, 0, st>>>(
+            static_cast<const float2 *>(x_dev), static_cast<float2 *>(out_dev), m, offset, step);
+    else
+        stride_copy_kernel<double2><<<grid, kOpsThreads, 0, st>>>(
+            static_cast<const double2 *>(x_dev), static_cast<double2 *>(out_dev), m, offset, step);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_cu8_to_cf32(int device, const void *iq_u8_dev, int64_t n, void *out_dev, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_cu8_to_cf32: negative length");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(iq_u8_dev != nullptr && out_dev != nullptr, "ddm_cu8_to_cf32: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_cu8_to_cf32");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(iq_u8_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15) == 0;
+    if (aligned)
+        cu8_kernel<<<ops_grid(device, (n + 7) / 8), kOpsThreads, 0, st>>>(
+            static_cast<const unsigned char *>(iq_u8_dev), static_cast<float2 *>(out_dev), n);
+    else
+        cu8_kernel_scalar<<<ops_grid(device, n), kOpsThreads, 0, st>>>(
+            static_cast<const unsigned char *>(iq_u8_dev), static_cast<float2 *>(out_dev), n);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+}  // extern "C"

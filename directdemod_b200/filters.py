@@ -1,0 +1,286 @@
+"""Filters (directdemod/filters.py): same classes, arguments and state semantics as the
+reference; the arithmetic of ``applyOn`` runs on the GPU through libddemod.so
+(ddm_filter_* in include/ddemod.h).  Coefficient *design* stays on the host in scipy, so
+``b, a`` are identical to the reference's by construction.
+
+``applyOn(x)`` accepts a numpy array (returns a numpy array in the reference's dtype,
+float64 / complex128) or a cuda torch tensor (returns a cuda tensor, float32 / complex64 --
+the device-resident handoff commSignal uses to avoid PCIe round trips between operators).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.signal as signal
+
+from . import _dev, _lib, constants
+
+
+class filter:
+    """Parent of all filters (filters.py:15-89).
+
+    storeState: carry the lfilter delay line between calls (zi starts as the UNSCALED
+    ``lfilter_zi(b, a)``, filters.py:45).  zeroPhase: ``filtfilt`` instead, which disables
+    storeState and initOut (filters.py:38-42).  initOut: first call seeds zi with
+    ``lfiltic(b, a, x, initOut)`` (filters.py:66-67).
+    """
+
+    _ddm_native = True      # commSignal may hand this object device tensors
+
+    def __init__(self, b, a, storeState=True, zeroPhase=False, initOut=None):
+        self._storeState = bool(storeState)
+        self._zeroPhase = bool(zeroPhase)
+        self._initOut = initOut
+        if self._storeState and self._zeroPhase:
+            self._storeState = False
+        if self._initOut is not None and self._zeroPhase:
+            self._initOut = None
+        self._b = b
+        self._a = a
+        self._bd = np.atleast_1d(np.asarray(b, dtype=np.float64)).copy()
+        self._ad = np.atleast_1d(np.asarray(a, dtype=np.float64)).copy()
+        self._h = None              # ddm_filter handle, created on first use (needs the GPU)
+        self._needs_lfiltic = self._storeState and self._initOut is not None
+        self._chain = None          # fused chain currently holding this filter's state
+        self._used = False
+
+    # -- handle management ------------------------------------------------------------
+    def _handle(self):
+        if self._h is None:
+            _dev.require_cuda()
+            l = _lib.lib()
+            h = C.c_void_p()
+            _lib.check(l.ddm_filter_create(
+                _dev.device_index(), self._bd.ctypes.data_as(C.POINTER(C.c_double)), self._bd.size,
+                self._ad.ctypes.data_as(C.POINTER(C.c_double)), self._ad.size, C.byref(h)),
+                "ddm_filter_create")
+            self._h = h
+            self._dev_index = _dev.device_index()
+            if self._state_len() > 0 and (self._storeState or self._zeroPhase):
+                # scipy's own lfilter_zi, so even ill-conditioned filters start from the very
+                # bits the reference starts from (filters.py:45)
+                zi = np.ascontiguousarray(signal.lfilter_zi(self._b, self._a), dtype=np.float64)
+                _lib.check(l.ddm_filter_set_zi_base(h, zi.ctypes.data_as(C.POINTER(C.c_double))),
+                           "ddm_filter_set_zi_base")
+            if self._storeState and not self._needs_lfiltic:
+                _lib.check(l.ddm_filter_reset(h, _dev.stream_ptr()), "ddm_filter_reset")
+        return self._h
+
+    def setIIRMode(self, mode):
+        """0 auto (default), 1 segment-parallel, 2 sequential bit-exact replay (see ddemod.h)."""
+        _lib.check(_lib.lib().ddm_filter_set_iir_mode(self._handle(), int(mode)), "ddm_filter_set_iir_mode")
+        return self
+
+    def info(self):
+        """(is_fir, parallel warm-up length, measured float64 roundoff floor of the recursion)."""
+        fir, w, nf = C.c_int(), C.c_int64(), C.c_double()
+        _lib.check(_lib.lib().ddm_filter_info(self._handle(), C.byref(fir), C.byref(w), C.byref(nf)),
+                   "ddm_filter_info")
+        return bool(fir.value), int(w.value), float(nf.value)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None:
+                _lib.lib().ddm_filter_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def isFIR(self):
+        return bool(np.all(self._ad[1:] == 0.0))
+
+    @property
+    def _fresh(self):
+        """True until the filter has processed its first sample."""
+        return not self._used
+
+    def _state_len(self):
+        return max(self._bd.size, self._ad.size) - 1
+
+    def getState(self):
+        """The carried delay line as complex128 (what the reference keeps in filter.__zi)."""
+        self._release_chain()
+        z = np.zeros(2 * max(self._state_len(), 1))
+        _lib.check(_lib.lib().ddm_filter_get_state(self._handle(), z.ctypes.data_as(C.POINTER(C.c_double)),
+                                                   _dev.stream_ptr()), "ddm_filter_get_state")
+        return (z[0::2] + 1j * z[1::2])[:self._state_len()]
+
+    def setState(self, zi):
+        zi = np.asarray(zi, dtype=np.complex128).ravel()
+        if zi.size != self._state_len():
+            raise ValueError("state must have %d entries" % self._state_len())
+        z = np.zeros(2 * max(zi.size, 1))
+        z[0:2 * zi.size:2] = zi.real
+        z[1:2 * zi.size:2] = zi.imag
+        self._chain = None
+        _lib.check(_lib.lib().ddm_filter_set_state(self._handle(), z.ctypes.data_as(C.POINTER(C.c_double)),
+                                                   _dev.stream_ptr()), "ddm_filter_set_state")
+        self._needs_lfiltic = False
+
+    def _release_chain(self):
+        """If a fused chain owns this filter's state, take it back (commSignal fused this
+        filter into a mixer/decimator/FM kernel on earlier chunks)."""
+        ch = self._chain
+        if ch is not None:
+            self._chain = None
+            zi, _ = ch.export_state()
+            self.setState(zi)
+
+    # -- the operator -----------------------------------------------------------------
+    def applyOn(self, x):
+        """Apply the filter to a signal array (filters.py:53-75)."""
+        if _dev.is_tensor(x) and x.is_cuda:
+            return self._apply_dev(_dev.to_device(x))
+        xd = _dev.to_device(x)
+        return _dev.to_host(self._apply_dev(xd, host_x=x))
+
+    def _apply_dev(self, xd, host_x=None):
+        l = _lib.lib()
+        h = self._handle()
+        self._release_chain()
+        n = xd.numel()
+        cplx = xd.is_complex()
+        y = _dev.empty_like_kind(n, cplx, xd.device.index)
+        st = _dev.stream_ptr(xd.device.index)
+        if self._storeState:
+            if self._needs_lfiltic:
+                # filters.py:66-67: zi = lfiltic(b, a, x, initOut) -- only the first few
+                # samples of x enter, so this tiny design-time step stays on the host
+                m = max(self._bd.size, self._ad.size)
+                head = host_x[:m] if host_x is not None else _dev.to_host(xd[:m])
+                self.setState(signal.lfiltic(self._b, self._a, np.asarray(head), self._initOut))
+            _lib.check(l.ddm_filter_apply_dev(h, _dev.ptr(xd), n, int(cplx), _dev.ptr(y), 1, st),
+                       "ddm_filter_apply_dev")
+        elif self._zeroPhase:
+            padlen = 3 * max(self._bd.size, self._ad.size)
+            if n <= padlen:
+                raise ValueError("The length of the input vector x must be greater than padlen, "
+                                 "which is %d." % padlen)
+            _lib.check(l.ddm_filter_filtfilt_dev(h, _dev.ptr(xd), n, int(cplx), _dev.ptr(y), st),
+                       "ddm_filter_filtfilt_dev")
+        else:
+            _lib.check(l.ddm_filter_apply_dev(h, _dev.ptr(xd), n, int(cplx), _dev.ptr(y), 0, st),
+                       "ddm_filter_apply_dev")
+        if n > 0:
+            self._used = True
+        return y
+
+    @property
+    def getA(self):
+        return self._a
+
+    @property
+    def getB(self):
+        return self._b
+
+
+class rollingAverage(filter):
+    """Rolling average over n samples (filters.py:95-114)."""
+
+    def __init__(self, n=3, storeState=True, zeroPhase=False, initOut=None):
+        self._n = n
+        super().__init__([1.0 / n] * n, [1], storeState, zeroPhase, initOut)
+
+
+class blackmanHarris(filter):
+    """Blackman-Harris window as FIR taps, unnormalised (filters.py:120-139)."""
+
+    def __init__(self, n, storeState=True, zeroPhase=False, initOut=None):
+        self._n = n
+        super().__init__(signal.windows.blackmanharris(n), [1], storeState, zeroPhase, initOut)
+
+
+class hamming(filter):
+    """Hamming window as FIR taps, unnormalised (filters.py:180-199)."""
+
+    def __init__(self, n, storeState=True, zeroPhase=False, initOut=None):
+        self._n = n
+        super().__init__(signal.windows.hamming(n), [1], storeState, zeroPhase, initOut)
+
+
+class gaussian(filter):
+    """Gaussian window as FIR taps, unnormalised (filters.py:205-226)."""
+
+    def __init__(self, n, sigma, storeState=True, zeroPhase=False, initOut=None):
+        self._n = n
+        self._sigma = sigma
+        super().__init__(signal.windows.gaussian(n, sigma), [1], storeState, zeroPhase, initOut)
+
+
+class butter(filter):
+    """Butterworth filter in transfer-function form (filters.py:232-273)."""
+
+    def __init__(self, Fs, cutoffA, cutoffB=None, n=6, typeFlt=constants.FLT_LP, storeState=True,
+                 zeroPhase=False, initOut=None):
+        if typeFlt in (constants.FLT_BP, constants.FLT_BS) and cutoffB is None:
+            raise ValueError("CutoffB must be given")
+        nyq = 0.5 * Fs
+        if typeFlt == constants.FLT_LP:
+            b, a = signal.butter(n, cutoffA / nyq, btype="lowpass")
+        elif typeFlt == constants.FLT_HP:
+            b, a = signal.butter(n, cutoffA / nyq, btype="highpass")
+        elif typeFlt == constants.FLT_BP:
+            b, a = signal.butter(n, [cutoffA / nyq, cutoffB / nyq], btype="bandpass")
+        elif typeFlt == constants.FLT_BS:
+            b, a = signal.butter(n, [cutoffA / nyq, cutoffB / nyq], btype="bandstop")
+        else:
+            raise ValueError("Invalid filter type")
+        super().__init__(b, a, storeState, zeroPhase, initOut)
+
+
+class remez(filter):
+    """Parks-McClellan band filter (filters.py:279-314)."""
+
+    def __init__(self, Fs, bands, gains, ntaps=128, storeState=True, zeroPhase=False, initOut=None):
+        if len(bands) == 0:
+            raise ValueError("Atleast one band must be given")
+        if bands[-1][1] >= (Fs / 2):
+            raise ValueError("Last band must end before (Fs/2)Hz")
+        edges = []
+        for band in bands:
+            edges.extend(band)
+        if len(edges) != 2 * len(gains):
+            raise ValueError("Invalid bands/gains values")
+        super().__init__(signal.remez(ntaps, edges, gains, fs=Fs), [1], storeState, zeroPhase, initOut)
+
+
+class blackmanHarrisConv:
+    """Blackman-Harris by 'same' convolution (filters.py:145-174); stateless.
+
+    convolve(sig, w, 'same')[i] = sum_k w[k] sig[i + (n-1)//2 - k] with zeros outside, i.e.
+    a zero-state FIR whose output is advanced by (n-1)//2 samples."""
+
+    _ddm_native = True
+
+    def __init__(self, n=151):
+        self._n = n
+        self._fir = filter(signal.windows.blackmanharris(n), [1], storeState=False)
+
+    def applyOn(self, sig):
+        dev_in = _dev.is_tensor(sig) and sig.is_cuda
+        xd = _dev.to_device(sig)
+        t = _dev.torch()
+        n = xd.numel()
+        # 'same' keeps len(sig) samples centred on the full convolution (scipy.signal.convolve
+        # sizes the output after its FIRST argument, whichever operand is longer)
+        adv = (self._n - 1) // 2
+        padded = t.cat([xd, t.zeros(adv, dtype=xd.dtype, device=xd.device)])
+        y = self._fir._apply_dev(padded)[adv:adv + n]
+        y = y.contiguous()
+        return y if dev_in else _dev.to_host(y)
+
+
+class medianFilter:
+    """scipy medfilt wrapper (filters.py:322-326).  Not on the hot path: no decoder calls it
+    and the reference marks it 'to be implemented later'; it stays a host call."""
+
+    def __init__(self, n=5):
+        self._n = n
+
+    def applyOn(self, sig):
+        if _dev.is_tensor(sig):
+            sig = _dev.to_host(sig)
+        return signal.medfilt(sig, self._n)

@@ -99,6 +99,18 @@ class FusedChain:
                                               _stream_ptr(self.device)), "ddm_chain_get_halo")
         return out
 
+    def export_state(self):
+        """The carried state in the reference's terms: (zi complex128[ntaps-1] == filter.__zi,
+        last complex or None == demod_fm.__last).  Used when a stream moves from the fused
+        kernel to the stand-alone operators."""
+        zi = np.zeros(2 * max(self.ntaps - 1, 1))
+        last = np.zeros(2)
+        _lib.check(self._l.ddm_chain_export_state(
+            self._h, zi.ctypes.data_as(C.POINTER(C.c_double)), last.ctypes.data_as(C.POINTER(C.c_double)),
+            _stream_ptr(self.device)), "ddm_chain_export_state")
+        z = (zi[0::2] + 1j * zi[1::2])[:self.ntaps - 1]
+        return z, (complex(last[0], last[1]) if self.position[2] else None)
+
     def out_count(self, n):
         m = C.c_int64()
         _lib.check(self._l.ddm_chain_out_count(self._h, int(n), C.byref(m)), "ddm_chain_out_count")

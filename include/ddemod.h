@@ -100,6 +100,74 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n,
 int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n,
                          void *out_host, int64_t out_capacity, int64_t *n_out, void *stream);
 
+/* the chain's carried state in the reference's own terms, for handing a stream over to the
+ * un-fused operators: zi_c128_host receives ntaps-1 complex128 values = filter.__zi
+ * (filters.py:69) and last_c128_host one complex128 = demod_fm.__last (demod_fm.py:44,48;
+ * only meaningful when has_prev).  Synchronises the stream. */
+int ddm_chain_export_state(const ddm_chain *c, double *zi_c128_host, double *last_c128_host,
+                           void *stream);
+
+/* ---- stand-alone element-wise operators ----------------------------------------------- */
+/* comm.py:63-78  x[i] *= exp(-j 2 pi f (n0+i) / fs), in place on cf32 */
+int ddm_mix_cf32(int device, void *x_dev, int64_t n, double freq_offset, double samp_rate,
+                 int64_t n0, void *stream);
+/* same with a per-sample frequency array (f64, device) -- decode_funcube.py:228 */
+int ddm_mix_var_cf32(int device, void *x_dev, const double *freq_dev, int64_t n, double samp_rate,
+                     int64_t n0, void *stream);
+/* demod_fm.py:29-51  out = angle(x[i] conj x[i-1]); prev_dev = carried last sample (one cf32
+ * on the device) or NULL for the first chunk (then n-1 outputs).  *n_out = outputs written. */
+int ddm_fm_demod(int device, const void *x_dev, int64_t n, const void *prev_dev, void *out_dev,
+                 int64_t *n_out, void *stream);
+/* demod_fm.py:74-96  diff(unwrap(angle(x))); prev_angle_dev / last_angle_dev: one f32 each */
+int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_angle_dev,
+                      void *out_dev, void *last_angle_dev, int64_t *n_out, void *stream);
+/* np.abs of a cf32 (is_complex) or f32 array -> f32   (demod_am.py:29,62) */
+int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_dev, void *stream);
+/* comm.py:127  out = x[offset::step]; elem_bytes 4 (f32), 8 (cf32) or 16 (c128) */
+int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, int64_t offset,
+                    int64_t step, void *out_dev, int64_t *n_out, void *stream);
+/* source.py:117-118 / :209-210  interleaved u8 IQ -> cf32 minus (127.5 + 127.5j) */
+int ddm_cu8_to_cf32(int device, const void *iq_u8_dev, int64_t n, void *out_dev, void *stream);
+
+/* ---- stateful linear filters (filters.py:21-75) ----------------------------------------
+ * One handle = one filters.filter object: coefficients b, a (normalised by a[0] like scipy)
+ * and the carried delay line zi (scipy's direct-form-II-transposed state, max(na,nb)-1
+ * complex128 values).  FIR (a == [1]) runs on the FP32 pipes, IIR as a float64 blocked scan.
+ * Signals are f32 (is_complex = 0) or cf32 (is_complex = 1) on the handle's device. */
+typedef struct ddm_filter ddm_filter;
+int ddm_filter_create(int device, const double *b, int nb, const double *a, int na, ddm_filter **out);
+int ddm_filter_destroy(ddm_filter *f);
+int ddm_filter_state_len(const ddm_filter *f, int *n);
+/* host <-> handle copy of zi (interleaved re, im float64); both synchronise the stream */
+int ddm_filter_set_state(ddm_filter *f, const double *zi_c128_host, void *stream);
+int ddm_filter_get_state(const ddm_filter *f, double *zi_c128_host, void *stream);
+/* zi = lfilter_zi(b, a), used unscaled like filters.py:45 */
+int ddm_filter_reset(ddm_filter *f, void *stream);
+/* use_state = 1: y, zi = lfilter(b, a, x, zi=zi) (filters.py:69); 0: lfilter(b, a, x) (:75) */
+int ddm_filter_apply_dev(ddm_filter *f, const void *x_dev, int64_t n, int is_complex, void *y_dev,
+                         int use_state, void *stream);
+/* scipy.signal.filtfilt(b, a, x) with its defaults (filters.py:73); does not touch zi */
+int ddm_filter_filtfilt_dev(ddm_filter *f, const void *x_dev, int64_t n, int is_complex, void *y_dev,
+                            void *stream);
+/* replace the handle's lfilter_zi vector (used by reset and to seed filtfilt) -- a caller that
+ * already holds scipy's own lfilter_zi passes it here so that even ill-conditioned filters start
+ * from the reference's exact bits */
+int ddm_filter_set_zi_base(ddm_filter *f, const double *zi_host);
+/* IIR execution mode.  scipy's float64 transfer-function recursion has a filter-dependent
+ * roundoff noise floor (3e-4 relative for the reference's 12th-order NOAA band-pass,
+ * decode_noaa.py:274); a run that is not the very same sequential loop cannot agree with it
+ * better than that floor.  AUTO measures the floor at create time and replays the loop
+ * sequentially (one thread, bit-exact float64) when it exceeds 1e-7, otherwise runs
+ * segment-parallel. */
+#define DDM_IIR_AUTO 0
+#define DDM_IIR_PARALLEL 1
+#define DDM_IIR_SEQUENTIAL 2
+int ddm_filter_set_iir_mode(ddm_filter *f, int mode);
+/* is_fir, warm-up length of the segment-parallel IIR (-1: never decays), measured noise floor */
+int ddm_filter_info(const ddm_filter *f, int *is_fir, int64_t *warmup, double *noise_floor);
+/* scipy.signal.lfilter_zi restated; zi_out has max(na,nb)-1 entries */
+int ddm_lfilter_zi(const double *b, int nb, const double *a, int na, double *zi_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,345 @@
+"""GPU parity of the drop-in Python API (directdemod_b200.comm / filters / demod_fm / chunker)
+against the golden fixtures produced by the UNMODIFIED reference (oracle/gen_golden.py).  The
+test bodies mirror the generator line by line with ``directdemod_b200`` in place of
+``directdemod`` -- that is the drop-in claim."""
+
+import numpy as np
+import pytest
+
+from oracle import ddoracle as O
+from tests.util import TOL, wrap_rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+class _Src:
+    def __init__(self, n):
+        self.length = n
+
+
+def _mods():
+    from directdemod_b200 import chunker, comm, constants, demod_fm, filters
+    return chunker, comm, constants, demod_fm, filters
+
+
+@pytest.mark.parametrize("name", ["chain_noise_d34", "chain_fmtone_d34", "chain_fmtone_d68", "chain_noise_d50"])
+def test_fluent_chain_matches_reference(golden, name):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    from directdemod_b200 import _lib
+    g = golden(name)
+    x, fs, f_off, bw = g["x"], int(g["fs"]), float(g["f_off"]), int(g["bw"])
+    for tag, csize in (("whole", len(x) + 1), ("c2500", 2500), ("c1111", 1111), ("c97", 97)):
+        ck = chunker.chunker(_Src(len(x)), csize)
+        bh = filters.blackmanHarris(151)
+        fm = demod_fm.demod_fm()
+        out = comm.commSignal(1)
+        launches0 = _lib.launch_count()
+        for a, b in ck.getChunks:
+            s = comm.commSignal(fs, x[a:b], ck).offsetFreq(f_off).filter(bh).bwLim(bw, uniq="First")
+            s.funcApply(fm.demod)
+            out.extend(s)
+        # the whole chain must have run as ONE fused launch per chunk
+        assert _lib.launch_count() - launches0 == len(ck.getChunks), tag
+        assert out.sampRate == int(g["rate"])
+        assert out.signal.dtype == np.float64
+        assert out.signal.shape == g["fm_" + tag].shape, tag
+        assert wrap_rel_rms(out.signal, g["fm_" + tag]) <= TOL, tag
+
+
+def test_chain_iq_then_separate_fm_hands_state_over(golden):
+    """gen_golden reads .signal between bwLim and funcApply: the fused IQ chain must hand its
+    state to the stand-alone FM kernel and the results must still match."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("chain_fmtone_d34")
+    x, fs, f_off, bw = g["x"], int(g["fs"]), float(g["f_off"]), int(g["bw"])
+    ck = chunker.chunker(_Src(len(x)), 1111)
+    bh = filters.blackmanHarris(151)
+    fm = demod_fm.demod_fm()
+    out = comm.commSignal(1)
+    iq = []
+    for a, b in ck.getChunks:
+        s = comm.commSignal(fs, x[a:b], ck).offsetFreq(f_off).filter(bh).bwLim(bw, uniq="First")
+        iq.append(np.array(s.signal))
+        s.funcApply(fm.demod)
+        out.extend(s)
+    iq = np.concatenate(iq)
+    assert iq.dtype == np.complex128 and iq.shape == g["iq_c1111"].shape
+    assert O.rel_rms(iq, g["iq_c1111"]) <= TOL
+    assert wrap_rel_rms(out.signal, g["fm_c1111"]) <= TOL
+
+
+def test_fused_to_unfused_state_migration(golden):
+    """First chunks through the fused kernel, later chunks operator by operator (a plain
+    applyOn on the same filter object): the delay line and FM sample must carry over."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("chain_noise_d34")
+    x, fs, f_off, bw = g["x"], int(g["fs"]), float(g["f_off"]), int(g["bw"])
+    ck = chunker.chunker(_Src(len(x)), 2500)
+    bh = filters.blackmanHarris(151)
+    fm = demod_fm.demod_fm()
+    parts = []
+    for i, (a, b) in enumerate(ck.getChunks):
+        if i < 2:
+            s = comm.commSignal(fs, x[a:b], ck).offsetFreq(f_off).filter(bh).bwLim(bw, uniq="First")
+            s.funcApply(fm.demod)
+            parts.append(s.signal)
+        else:
+            s = comm.commSignal(fs, x[a:b], ck).offsetFreq(f_off)
+            y = bh.applyOn(s.signal)                       # stand-alone FIR, numpy in/out
+            s = comm.commSignal(fs, y, ck).bwLim(bw, uniq="First")
+            parts.append(fm.demod(s.signal))
+    got = np.concatenate(parts)
+    assert got.shape == g["fm_c2500"].shape
+    assert wrap_rel_rms(got, g["fm_c2500"]) <= TOL
+
+
+def test_mixer_at_huge_global_index(golden):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("mixer")
+    for tag in "abc":
+        fsx, f, n0 = g["p_" + tag]
+        ck = chunker.chunker(_Src(10), 10)
+        ck.set(constants.CHUNK_FREQOFFSET, int(n0))
+        s = comm.commSignal(int(fsx), g["x"], ck).offsetFreq(float(f))
+        assert ck.get(constants.CHUNK_FREQOFFSET) == int(n0) + len(g["x"])
+        assert O.rel_rms(s.signal, g["y_" + tag]) <= TOL, tag
+
+
+def test_mixer_per_sample_frequency_array():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(3)
+    n, fs = 5000, 2048000
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 30).astype(np.complex64)
+    f = 30000.0 + 500.0 * np.sin(np.arange(n) / 300.0)
+    ck = chunker.chunker(_Src(10), 10)
+    ck.set(constants.CHUNK_FREQOFFSET, 123456789)
+    got = comm.commSignal(fs, x, ck).offsetFreq(f).signal
+    want = x * np.exp(-1.0j * 2.0 * np.pi * f * np.arange(123456789, 123456789 + n) / fs)
+    assert O.rel_rms(got, want) <= TOL
+
+
+FILTERS = {
+    "bh151": lambda F, C: F.blackmanHarris(151),
+    "ham492": lambda F, C: F.hamming(492),
+    "gauss51": lambda F, C: F.gaussian(51, 5),
+    "roll7": lambda F, C: F.rollingAverage(7),
+    "remez255": lambda F, C: F.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=255),
+    "butlp8": lambda F, C: F.butter(2400000, 100000, n=8),
+    "butbp6": lambda F, C: F.butter(60235, 400, 4400, n=6, typeFlt=C.FLT_BP),
+    "buthp3": lambda F, C: F.butter(48000, 3000, n=3, typeFlt=C.FLT_HP),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FILTERS))
+def test_stateful_filters_match_reference(golden, name):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("filters")
+    cuts = g["cuts"].tolist()
+    for tag, x in (("c", g["xc"]), ("r", g["xr"])):
+        f = FILTERS[name](filters, constants)
+        np.testing.assert_allclose(np.asarray(f.getB, dtype=np.float64), g[name + "_b"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(np.asarray(f.getA, dtype=np.float64), g[name + "_a"], rtol=1e-12, atol=1e-15)
+        got = np.concatenate([f.applyOn(x[cuts[i]:cuts[i + 1]]) for i in range(len(cuts) - 1)])
+        want = g["%s_%s" % (name, tag)]
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert O.rel_rms(got, want) <= TOL, (name, tag, O.rel_rms(got, want))
+
+
+def test_iir_roundoff_floor_and_execution_modes(golden):
+    """scipy's float64 tf-form recursion has a filter-dependent roundoff floor; the library
+    measures it, replays the loop sequentially (bit-exact) when it would show at 1e-5, and its
+    segment-parallel mode agrees with scipy to that floor -- the same distance two scipy runs
+    started at different samples keep from each other."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("filters")
+    x = g["xr"].astype(np.float64)
+    f = filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP)
+    is_fir, warm, floor = f.info()
+    assert not is_fir and warm > 0 and 1e-5 < floor < 5e-3          # the NOAA band-pass: ~3e-4
+    exact = f.applyOn(x)                                           # AUTO -> sequential replay
+    import scipy.signal as sps
+    b, a = g["butbp6_b"], g["butbp6_a"]
+    ref, _ = sps.lfilter(b, a, x, zi=sps.lfilter_zi(b, a))
+    assert np.array_equal(exact.astype(np.float32), ref.astype(np.float32))   # bit-exact before narrowing
+    par = filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP).setIIRMode(1)
+    rng = np.random.default_rng(2)
+    xl = rng.standard_normal(400000).astype(np.float32).astype(np.float64)
+    refl, _ = sps.lfilter(b, a, xl, zi=sps.lfilter_zi(b, a))
+    err = O.rel_rms(par.applyOn(xl), refl)
+    assert err <= 10 * floor, (err, floor)
+    # a well-conditioned filter: parallel by default and within the plain tolerance
+    f8 = filters.butter(2400000, 100000, n=8)
+    assert f8.info()[2] < 1e-7
+    b8, a8 = O.taps_butter(2400000, 100000, n=8)
+    ref8, _ = sps.lfilter(b8, a8, xl, zi=sps.lfilter_zi(b8, a8))
+    assert O.rel_rms(f8.applyOn(xl), ref8) <= TOL
+
+
+def test_stateless_and_zero_phase_filters_match_reference(golden):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("filters")
+    xr, xc = g["xr"], g["xc"]
+    for k, cls, n in (("bh151", filters.blackmanHarris, 151), ("ham492", filters.hamming, 492)):
+        assert O.rel_rms(cls(n, zeroPhase=True).applyOn(xr), g[k + "_zp_r"]) <= TOL, k
+        assert O.rel_rms(cls(n, zeroPhase=True).applyOn(xc), g[k + "_zp_c"]) <= TOL, k
+        assert O.rel_rms(cls(n, storeState=False).applyOn(xr), g[k + "_sl_r"]) <= TOL, k
+    got = filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP, zeroPhase=True).applyOn(xr)
+    assert O.rel_rms(got, g["butbp6_zp_r"]) <= TOL
+    got = filters.butter(2400000, 100000, n=8, storeState=False).applyOn(xc)
+    assert O.rel_rms(got, g["butlp8_sl_c"]) <= TOL
+    with pytest.raises(ValueError):
+        filters.hamming(492, zeroPhase=True).applyOn(xr[:1000])       # scipy: len must exceed padlen
+
+
+def test_filter_constructor_errors_match_reference():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    with pytest.raises(ValueError):
+        filters.butter(48000, 1000, typeFlt=constants.FLT_BP)
+    with pytest.raises(ValueError):
+        filters.butter(48000, 1000, typeFlt=7)
+    with pytest.raises(ValueError):
+        filters.remez(48000, [], [])
+    with pytest.raises(ValueError):
+        filters.remez(48000, [[0, 1000], [2000, 24000]], [1, 0])
+    with pytest.raises(ValueError):
+        filters.remez(48000, [[0, 1000], [2000, 23000]], [1])
+
+
+def test_exp3_rolling_average_golden_vectors():
+    """Experiment 3 cells 9/11/19: storeState=True chunked == whole except the first sample,
+    which is 1.0 (unscaled lfilter_zi)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    x = np.arange(1, 20, dtype=np.float64)
+    whole = filters.rollingAverage(2, storeState=False).applyOn(x)
+    np.testing.assert_allclose(whole, np.arange(1, 20) - 0.5, atol=1e-6)
+    f = filters.rollingAverage(2)
+    got = np.concatenate([f.applyOn(x[:9]), f.applyOn(x[9:14]), f.applyOn(x[14:])])
+    want = np.arange(1, 20) - 0.5
+    want[0] = 1.0
+    np.testing.assert_allclose(got, want, atol=1e-6)
+
+
+def test_init_out_lfiltic_first_call():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(4000)
+    b, a = sps.butter(4, 0.2)
+    f = filters.filter(b, a, initOut=[0.3, -0.1, 0.2, 0.05])
+    got = np.concatenate([f.applyOn(x[:1500]), f.applyOn(x[1500:])])
+    want, _ = O.filt_initout(b, a, x, [0.3, -0.1, 0.2, 0.05])
+    assert O.rel_rms(got, want) <= TOL
+
+
+def test_fm_demod_golden_and_exp5_vectors(golden):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("demod")
+    x, cuts = g["x"], g["cuts"].tolist()
+    fm = demod_fm.demod_fm()
+    got = np.concatenate([fm.demod(x[cuts[i]:cuts[i + 1]]) for i in range(4)])
+    assert got.shape == g["fm_state"].shape and wrap_rel_rms(got, g["fm_state"]) <= TOL
+    got = demod_fm.demod_fm(storeState=False).demod(x)
+    assert got.shape == g["fm_whole"].shape and wrap_rel_rms(got, g["fm_whole"]) <= TOL
+    cuts2 = [0, 3, 700, 5000]
+    fmad = demod_fm.demod_fmAD()
+    got = np.concatenate([fmad.demod(x[cuts2[i]:cuts2[i + 1]]) for i in range(3)])
+    assert got.shape == g["fmad_state"].shape and wrap_rel_rms(got, g["fmad_state"]) <= TOL
+    # Experiment 5 cells 6/8/10
+    v = np.array([1 + 1j, 2 - 2j, 3 + 3j, 4 - 4j, 5 + 5j, 6 - 6j])
+    hp = np.pi / 2
+    np.testing.assert_allclose(demod_fm.demod_fm(storeState=False).demod(v), [-hp, hp, -hp, hp, -hp], atol=1e-6)
+    fm = demod_fm.demod_fm()
+    np.testing.assert_allclose(fm.demod(v[:3]), [-hp, hp], atol=1e-6)
+    np.testing.assert_allclose(fm.demod(v[3:]), [-hp, hp, -hp], atol=1e-6)
+
+
+def test_bwlim_decimation_with_chunker_carry(golden):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("bwlim")
+    x = g["x"]
+    ck = chunker.chunker(_Src(len(x)), 1000)
+    parts = []
+    for a0, b0 in ck.getChunks:
+        s = comm.commSignal(2048000, x[a0:b0], ck).bwLim(60000, uniq="q")
+        assert s.sampRate == 60235
+        parts.append(s.signal)
+    got = np.concatenate(parts)
+    assert np.array_equal(got.astype(np.float32), g["dec34"])
+    # Experiment 6 cells 5/7
+    sig = np.arange(100, dtype=np.float64)
+    ck = chunker.chunker(_Src(100), 10)
+    got = np.concatenate([comm.commSignal(40, sig[a:b], ck).bwLim(10).signal for a, b in ck.getChunks])
+    assert np.array_equal(got, np.arange(0, 100, 4))
+    assert np.array_equal(comm.commSignal(40, sig).bwLim(10).signal, np.arange(0, 100, 4))
+
+
+def test_commsignal_errors_and_bookkeeping():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    with pytest.raises(ValueError):
+        comm.commSignal(0, np.zeros(4))
+    with pytest.raises(TypeError):
+        comm.commSignal(10, np.zeros((4, 4)))
+    s = comm.commSignal(48000.7, np.zeros(10, dtype=np.complex64))
+    assert s.sampRate == 48000 and s.length == 10
+    with pytest.raises(ValueError):
+        s.bwLim(96000)
+    with pytest.raises(TypeError):
+        s.updateSignal(np.zeros((2, 2)))
+    a = comm.commSignal(100, np.arange(5.0))
+    b = comm.commSignal(200, np.arange(3.0))
+    with pytest.raises(TypeError):
+        a.extend(b)
+    e = comm.commSignal(1)
+    e.extend(b)
+    assert e.sampRate == 200 and e.length == 3
+    ck = chunker.chunker(_Src(25), 10)
+    assert ck.getChunks == [[0, 10], [10, 20], [20, 25]]
+    with pytest.raises(KeyError):
+        ck.get("nope")
+    assert ck.get("x", 5) == 5 and ck.get("x") == 5
+    # foreign callables and foreign filter objects still work (numpy in, numpy out)
+    s = comm.commSignal(100, np.arange(6.0)).funcApply(lambda v: v[::-1] * 2)
+    assert np.array_equal(s.signal, np.arange(6.0)[::-1] * 2)
+
+    class Twice:
+        def applyOn(self, v):
+            return np.asarray(v) * 2
+    assert np.array_equal(comm.commSignal(100, np.arange(4.0)).filter(Twice()).signal, np.arange(4.0) * 2)
+
+
+def test_blackman_harris_conv_same():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    rng = np.random.default_rng(5)
+    for n in (40, 151, 1000):
+        x = rng.standard_normal(n)
+        want = sps.convolve(x, sps.windows.blackmanharris(151), mode="same")
+        assert O.rel_rms(filters.blackmanHarrisConv(151).applyOn(x), want) <= TOL, n
+
+
+def test_long_fir_and_iir_large_chunks():
+    """C4-shaped operators at a size that crosses many FIR/IIR tiles: 1023-tap Remez and an
+    8th-order Butterworth on complex noise, chunked unevenly."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(17)
+    n = 300000
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    cuts = [0, 100001, 100002, 180000, n]
+    fr = filters.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023)
+    fb = filters.butter(2400000, 100000, n=8)
+    got_r = np.concatenate([fr.applyOn(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    got_b = np.concatenate([fb.applyOn(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    b, a = O.taps_remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], 1023)
+    want_r, _ = O.filt_stateful(b, a, x.astype(np.complex128), O.initial_zi(b, a))
+    b2, a2 = O.taps_butter(2400000, 100000, n=8)
+    want_b, _ = O.filt_stateful(b2, a2, x.astype(np.complex128), O.initial_zi(b2, a2))
+    assert O.rel_rms(got_r, want_r) <= TOL, O.rel_rms(got_r, want_r)
+    assert O.rel_rms(got_b, want_b) <= TOL, O.rel_rms(got_b, want_b)
+    # poles close to the unit circle on a real signal: warm-up lengths of ~1e5 samples
+    xr = rng.standard_normal(n)
+    for cutoff in (300.0, 100.0):
+        flp = filters.butter(2048000, cutoff, n=2)
+        got = np.concatenate([flp.applyOn(xr[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        b3, a3 = O.taps_butter(2048000, cutoff, n=2)
+        want, _ = O.filt_stateful(b3, a3, xr, O.initial_zi(b3, a3))
+        assert O.rel_rms(got, want) <= TOL, (cutoff, O.rel_rms(got, want))
