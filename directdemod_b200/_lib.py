@@ -60,6 +60,10 @@ SIGNATURES = {
     "ddm_filter_apply_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),
     "ddm_filter_filtfilt_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
     "ddm_lfilter_zi": (_int, [_pdbl, _int, _pdbl, _int, _pdbl]),
+    "ddm_fft_create": (_int, [_int, C.POINTER(_vp)]),
+    "ddm_fft_destroy": (_int, [_vp]),
+    "ddm_am_hilbert": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
+    "ddm_resample": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp]),
 }
 
 _lib = None

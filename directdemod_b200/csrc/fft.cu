@@ -1,0 +1,527 @@
+// FFT-defined operators of the hot path, float64 on the device:
+//
+//   ddm_am_hilbert   abs(scipy.signal.hilbert(x)) per chunk    demod_am.py:18-29,
+//                    chunked like decode_noaa.__getAM          decode_noaa.py:631-657
+//   ddm_resample     scipy.signal.resample(x, num)             comm.py:110-116 (strict bwLim),
+//                                                              decode_noaa.py:350-351
+//
+// Both are *circular*, length-dependent operations on lengths that are not powers of two
+// (240 000 = 2^7 3 5^4 for the AM chunks, arbitrary for resample), so the transform is a
+// Bluestein chirp-z: a length-n DFT as a circular convolution of length m = 2^k >= 2n-1,
+// evaluated with batched power-of-two Stockham radix-4 passes (twiddles from a float64 table,
+// chirp phases k^2 mod 2n in exact integer arithmetic).  Independent chunks are the batch
+// dimension: one launch per pass covers every chunk of a pass over a whole capture.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "ddm_common.cuh"
+
+namespace ddm {
+
+constexpr int kFftThreads = 256;
+
+__device__ __forceinline__ double2 cmuld(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ double2 conjd(double2 a) { return make_double2(a.x, -a.y); }
+
+// tw[t] = exp(-2 pi i t / m)
+__global__ void fft_twiddle_kernel(double2 *tw, int m) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    double s, c;
+    sincospi(-2.0 * static_cast<double>(t) / static_cast<double>(m), &s, &c);
+    tw[t] = make_double2(c, s);
+}
+
+// chirp w[k] = exp(-i pi k^2 / n), k < n;  b (length m) = conj chirp wrapped around
+__global__ void fft_chirp_kernel(double2 *w, double2 *b, long long n, int m) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= m) return;
+    if (k < n) {
+        const unsigned long long r = (static_cast<unsigned long long>(k) * static_cast<unsigned long long>(k)) %
+                                     static_cast<unsigned long long>(2 * n);
+        double s, c;
+        sincospi(-static_cast<double>(r) / static_cast<double>(n), &s, &c);
+        w[k] = make_double2(c, s);
+        b[k] = make_double2(c, -s);
+        if (k > 0) b[m - k] = make_double2(c, -s);
+    } else if (k <= m - n) {
+        b[k] = make_double2(0.0, 0.0);
+    }
+}
+
+// one Stockham radix-4 pass over `batch` rows of length m (grid.y = row)
+template <int DIR>
+__global__ void fft_pass_r4(const double2 *__restrict__ in, double2 *__restrict__ out,
+                            const double2 *__restrict__ tw, int m, int Ns) {
+    const int q = m >> 2;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= q) return;
+    const size_t row = static_cast<size_t>(blockIdx.y) * m;
+    in += row;
+    out += row;
+    const int k = j & (Ns - 1);
+    const int step = q / Ns;                 // m / (4 Ns)
+    double2 v0 = in[j], v1 = in[j + q], v2 = in[j + 2 * q], v3 = in[j + 3 * q];
+    if (k != 0) {
+        double2 t1 = tw[k * step], t2 = tw[2 * k * step], t3 = tw[3 * k * step];
+        if (DIR < 0) {
+            t1 = conjd(t1);
+            t2 = conjd(t2);
+            t3 = conjd(t3);
+        }
+        v1 = cmuld(v1, t1);
+        v2 = cmuld(v2, t2);
+        v3 = cmuld(v3, t3);
+    }
+    const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y);
+    const double2 a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
+    const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
+    const double2 d = make_double2(v1.x - v3.x, v1.y - v3.y);
+    // forward: a3 = -i d ; inverse: a3 = +i d
+    const double2 a3 = DIR > 0 ? make_double2(d.y, -d.x) : make_double2(-d.y, d.x);
+    const int j0 = ((j - k) << 2) + k;
+    out[j0] = make_double2(a0.x + a2.x, a0.y + a2.y);
+    out[j0 + Ns] = make_double2(a1.x + a3.x, a1.y + a3.y);
+    out[j0 + 2 * Ns] = make_double2(a0.x - a2.x, a0.y - a2.y);
+    out[j0 + 3 * Ns] = make_double2(a1.x - a3.x, a1.y - a3.y);
+}
+
+template <int DIR>
+__global__ void fft_pass_r2(const double2 *__restrict__ in, double2 *__restrict__ out,
+                            const double2 *__restrict__ tw, int m, int Ns) {
+    const int h = m >> 1;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= h) return;
+    const size_t row = static_cast<size_t>(blockIdx.y) * m;
+    in += row;
+    out += row;
+    const int k = j & (Ns - 1);
+    const int step = h / Ns;
+    double2 v0 = in[j], v1 = in[j + h];
+    if (k != 0) {
+        double2 t = tw[k * step];
+        if (DIR < 0) t = conjd(t);
+        v1 = cmuld(v1, t);
+    }
+    const int j0 = ((j - k) << 1) + k;
+    out[j0] = make_double2(v0.x + v1.x, v0.y + v1.y);
+    out[j0 + Ns] = make_double2(v0.x - v1.x, v0.y - v1.y);
+}
+
+// buf[row][k] *= bfft[k]
+__global__ void fft_pointwise_kernel(double2 *buf, const double2 *__restrict__ bfft, int m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    double2 *p = buf + static_cast<size_t>(blockIdx.y) * m + k;
+    *p = cmuld(*p, bfft[k]);
+}
+
+// ---- Bluestein stages ----------------------------------------------------------------
+// load:  a[row][k] = conj?(src[row][k]) * w[k]  (k < n), 0 (n <= k < m)
+// src kinds: 0 = f32 real rows, 1 = cf32 rows, 2 = double2 rows (row stride src_stride elements)
+template <int KIND, bool CONJ>
+__global__ void blu_load_kernel(const void *__restrict__ src, long long src_stride, long long n,
+                                const double2 *__restrict__ w, double2 *__restrict__ a, int m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const size_t row = blockIdx.y;
+    double2 v = make_double2(0.0, 0.0);
+    if (k < n) {
+        if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[row * src_stride + k]);
+        else if (KIND == 1) {
+            const float2 s = static_cast<const float2 *>(src)[row * src_stride + k];
+            v = make_double2(static_cast<double>(s.x), static_cast<double>(s.y));
+        } else v = static_cast<const double2 *>(src)[row * src_stride + k];
+        if (CONJ) v.y = -v.y;
+        v = cmuld(v, w[k]);
+    }
+    a[row * m + k] = v;
+}
+
+// finish: X[row][k] = w[k] * c[row][k] / m   (k < n) -> dst (double2 rows of stride dst_stride),
+// optionally conjugated and scaled (the inverse transform is conj(DFT(conj(.))) / n)
+template <bool CONJ>
+__global__ void blu_finish_kernel(const double2 *__restrict__ c, int m, long long n,
+                                  const double2 *__restrict__ w, double scale, double2 *__restrict__ dst,
+                                  long long dst_stride) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const size_t row = blockIdx.y;
+    double2 v = c[row * m + k];
+    if (w != nullptr) v = cmuld(v, w[k]);
+    v.x *= scale;
+    v.y *= scale;
+    if (CONJ) v.y = -v.y;
+    dst[row * dst_stride + k] = v;
+}
+
+// power-of-two direct path helpers
+template <int KIND>
+__global__ void fft_load_plain_kernel(const void *__restrict__ src, long long src_stride, long long n,
+                                      double2 *__restrict__ a) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const size_t row = blockIdx.y;
+    double2 v = make_double2(0.0, 0.0);
+    if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[row * src_stride + k]);
+    else if (KIND == 1) {
+        const float2 s = static_cast<const float2 *>(src)[row * src_stride + k];
+        v = make_double2(static_cast<double>(s.x), static_cast<double>(s.y));
+    } else v = static_cast<const double2 *>(src)[row * src_stride + k];
+    a[row * n + k] = v;
+}
+
+// ---- operator-specific spectrum edits --------------------------------------------------
+// hilbert mask (scipy.signal.hilbert): h[0] = 1, h[1..(n-1)/2] = 2, h[n/2] = 1 (n even), else 0
+__global__ void hilbert_mask_kernel(double2 *spec, long long n, long long stride) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    double2 *p = spec + static_cast<size_t>(blockIdx.y) * stride + k;
+    double h;
+    if (k == 0) h = 1.0;
+    else if ((n & 1) == 0 && k == n / 2) h = 1.0;
+    else if (k < (n + 1) / 2) h = 2.0;
+    else h = 0.0;
+    p->x *= h;
+    p->y *= h;
+}
+
+__global__ void abs_out_kernel(const double2 *__restrict__ z, long long n, long long stride,
+                               float *__restrict__ out, long long out_stride) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const double2 v = z[static_cast<size_t>(blockIdx.y) * stride + k];
+    out[static_cast<size_t>(blockIdx.y) * out_stride + k] = static_cast<float>(hypot(v.x, v.y));
+}
+
+// scipy.signal.resample spectrum placement, X (length n) -> Y (length num)
+//   real input:    Hermitian spectrum of irfft(rfft(x)[:N//2+1] ...) semantics
+//   complex input: the fft/ifft branch
+__global__ void resample_spec_kernel(const double2 *__restrict__ X, long long n, double2 *__restrict__ Y,
+                                     long long num, int is_real) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= num) return;
+    const long long N = n < num ? n : num;
+    const long long half = N / 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (is_real) {
+        // half spectrum Yh[0..num/2]; Yh[j] = X[j] for j < N/2+1; even N: Nyquist-of-N bin doubled
+        // (down) or halved (up); irfft ignores the imaginary part of DC and of the num/2 bin
+        const long long j = k <= num / 2 ? k : num - k;            // mirrored index
+        if (j <= half) {
+            v = X[j];
+            if ((N & 1) == 0 && j == half) {
+                if (num < n) { v.x *= 2.0; v.y *= 2.0; }
+                else if (num > n) { v.x *= 0.5; v.y *= 0.5; }
+            }
+            if (j == 0 || ((num & 1) == 0 && j == num / 2)) v.y = 0.0;
+            if (k > num / 2) v.y = -v.y;                              // Hermitian mirror
+        }
+    } else {
+        const long long nyq = half + 1;
+        if (k < nyq) {
+            v = X[k];
+        } else if (N > 2 && k >= num - (N - nyq)) {
+            v = X[n - (num - k)];
+        }
+        if ((N & 1) == 0) {
+            if (num < n) {
+                // downsampling: Y[-N/2] += X[-N/2]
+                if (k == num - half) {
+                    const double2 e = X[n - half];
+                    // when num - half == half (N == num) the slot already holds X[half]
+                    v = make_double2(v.x + e.x, v.y + e.y);
+                }
+            } else if (num > n) {
+                // upsampling: Y[N/2] *= 0.5 and mirrored into Y[num - N/2]
+                if (k == half) { v.x *= 0.5; v.y *= 0.5; }
+                else if (k == num - half) { const double2 e = X[half]; v = make_double2(0.5 * e.x, 0.5 * e.y); }
+            }
+        }
+    }
+    Y[k] = v;
+}
+
+__global__ void resample_out_kernel(const double2 *__restrict__ z, long long num, double scale, void *out,
+                                    int is_real) {
+    const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (k >= num) return;
+    const double2 v = z[k];
+    if (is_real) static_cast<float *>(out)[k] = static_cast<float>(v.x * scale);
+    else static_cast<float2 *>(out)[k] = make_float2(static_cast<float>(v.x * scale), static_cast<float>(v.y * scale));
+}
+
+}  // namespace ddm
+
+using namespace ddm;
+
+// =====================================================================================
+// host side: plans and context
+// =====================================================================================
+struct FftPlan {
+    long long n = 0;
+    int m = 0;              // transform size of the power-of-two engine
+    bool pow2 = false;      // n itself is a power of two: no chirp
+    double2 *d_tw = nullptr;
+    double2 *d_w = nullptr;
+    double2 *d_bfft = nullptr;
+};
+
+struct ddm_fft {
+    int device = 0;
+    std::map<long long, FftPlan> plans;
+    double2 *d_ws[2] = {nullptr, nullptr};
+    size_t ws_elems = 0;
+    double2 *d_spec[2] = {nullptr, nullptr};   // length-n spectra (rows)
+    size_t spec_elems = 0;
+};
+
+namespace {
+
+int ilog2(long long v) {
+    int l = 0;
+    while ((1LL << l) < v) ++l;
+    return l;
+}
+
+// batched power-of-two FFT, rows of length m in buf[cur]; returns the index of the buffer
+// holding the result
+template <int DIR>
+int pow2_fft(double2 *bufs[2], int cur, const double2 *tw, int m, int batch, cudaStream_t st) {
+    int Ns = 1;
+    const int lg = ilog2(m);
+    int left = lg;
+    while (left >= 2) {
+        const dim3 grid((m / 4 + kFftThreads - 1) / kFftThreads, batch);
+        fft_pass_r4<DIR><<<grid, kFftThreads, 0, st>>>(bufs[cur], bufs[cur ^ 1], tw, m, Ns);
+        count_launch();
+        cur ^= 1;
+        Ns <<= 2;
+        left -= 2;
+    }
+    if (left == 1) {
+        const dim3 grid((m / 2 + kFftThreads - 1) / kFftThreads, batch);
+        fft_pass_r2<DIR><<<grid, kFftThreads, 0, st>>>(bufs[cur], bufs[cur ^ 1], tw, m, Ns);
+        count_launch();
+        cur ^= 1;
+    }
+    return cur;
+}
+
+int ensure_ws(ddm_fft *c, size_t elems, cudaStream_t st) {
+    if (elems <= c->ws_elems) return DDM_OK;
+    DDM_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_ws[i]);
+        c->d_ws[i] = nullptr;
+    }
+    c->ws_elems = 0;
+    for (int i = 0; i < 2; ++i) DDM_CUDA(cudaMalloc(&c->d_ws[i], sizeof(double2) * elems));
+    c->ws_elems = elems;
+    return DDM_OK;
+}
+
+int ensure_spec(ddm_fft *c, size_t elems, cudaStream_t st) {
+    if (elems <= c->spec_elems) return DDM_OK;
+    DDM_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_spec[i]);
+        c->d_spec[i] = nullptr;
+    }
+    c->spec_elems = 0;
+    for (int i = 0; i < 2; ++i) DDM_CUDA(cudaMalloc(&c->d_spec[i], sizeof(double2) * elems));
+    c->spec_elems = elems;
+    return DDM_OK;
+}
+
+int get_plan(ddm_fft *c, long long n, cudaStream_t st, FftPlan **out) {
+    auto it = c->plans.find(n);
+    if (it != c->plans.end()) {
+        *out = &it->second;
+        return DDM_OK;
+    }
+    if (n > (1LL << 29)) {
+        set_error("FFT length %lld is above the supported maximum 2^29", n);
+        return DDM_ERR_UNSUPPORTED;
+    }
+    FftPlan p;
+    p.n = n;
+    p.pow2 = (n & (n - 1)) == 0;
+    p.m = p.pow2 ? static_cast<int>(n) : (1 << ilog2(2 * n - 1));
+    DDM_CUDA(cudaMalloc(&p.d_tw, sizeof(double2) * p.m));
+    fft_twiddle_kernel<<<(p.m + 255) / 256, 256, 0, st>>>(p.d_tw, p.m);
+    count_launch();
+    if (!p.pow2) {
+        DDM_CUDA(cudaMalloc(&p.d_w, sizeof(double2) * n));
+        DDM_CUDA(cudaMalloc(&p.d_bfft, sizeof(double2) * p.m));
+        int rc = ensure_ws(c, static_cast<size_t>(p.m), st);
+        if (rc != DDM_OK) return rc;
+        fft_chirp_kernel<<<(p.m + 255) / 256, 256, 0, st>>>(p.d_w, c->d_ws[0], n, p.m);
+        count_launch();
+        const int r = pow2_fft<1>(c->d_ws, 0, p.d_tw, p.m, 1, st);
+        DDM_CUDA(cudaMemcpyAsync(p.d_bfft, c->d_ws[r], sizeof(double2) * p.m, cudaMemcpyDeviceToDevice, st));
+    }
+    DDM_CUDA(cudaGetLastError());
+    auto ins = c->plans.emplace(n, p);
+    *out = &ins.first->second;
+    return DDM_OK;
+}
+
+// DFT of `batch` rows.  src: rows of kind KIND (0 f32, 1 cf32, 2 double2) with row stride
+// src_stride; dst: double2 rows of stride dst_stride.  INVERSE computes the unnormalised-by-caller
+// inverse as conj(DFT(conj(x))) * scale.
+template <int KIND, bool INVERSE>
+int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int batch, double scale,
+             double2 *dst, long long dst_stride, cudaStream_t st) {
+    const long long n = p->n;
+    const int m = p->m;
+    int rc = ensure_ws(c, static_cast<size_t>(m) * batch, st);
+    if (rc != DDM_OK) return rc;
+    if (p->pow2) {
+        const dim3 g((n + kFftThreads - 1) / kFftThreads, batch);
+        fft_load_plain_kernel<KIND><<<g, kFftThreads, 0, st>>>(src, src_stride, n, c->d_ws[0]);
+        count_launch();
+        const int r = INVERSE ? pow2_fft<-1>(c->d_ws, 0, p->d_tw, m, batch, st)
+                              : pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st);
+        // copy out with scale (no chirp on the power-of-two path)
+        blu_finish_kernel<false><<<g, kFftThreads, 0, st>>>(c->d_ws[r], m, n, nullptr, scale, dst, dst_stride);
+        count_launch();
+        DDM_CUDA(cudaGetLastError());
+        return DDM_OK;
+    }
+    const dim3 gm((m + kFftThreads - 1) / kFftThreads, batch);
+    const dim3 gn((n + kFftThreads - 1) / kFftThreads, batch);
+    blu_load_kernel<KIND, INVERSE><<<gm, kFftThreads, 0, st>>>(src, src_stride, n, p->d_w, c->d_ws[0], m);
+    count_launch();
+    int r = pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st);
+    fft_pointwise_kernel<<<gm, kFftThreads, 0, st>>>(c->d_ws[r], p->d_bfft, m);
+    count_launch();
+    r = pow2_fft<-1>(c->d_ws, r, p->d_tw, m, batch, st);
+    blu_finish_kernel<INVERSE><<<gn, kFftThreads, 0, st>>>(c->d_ws[r], m, n, p->d_w,
+                                                           scale / static_cast<double>(m), dst, dst_stride);
+    count_launch();
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddm_fft_create(int device, ddm_fft **out) {
+    DDM_REQUIRE(out != nullptr, "ddm_fft_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    DDM_CUDA(cudaGetDeviceCount(&ndev));
+    DDM_REQUIRE(device >= 0 && device < ndev, "ddm_fft_create: no such device %d", device);
+    ddm_fft *c = new (std::nothrow) ddm_fft();
+    if (!c) {
+        set_error("ddm_fft_create: out of host memory");
+        return DDM_ERR_NOMEM;
+    }
+    c->device = device;
+    *out = c;
+    return DDM_OK;
+}
+
+int ddm_fft_destroy(ddm_fft *c) {
+    if (!c) return DDM_OK;
+    DeviceGuard guard(c->device);
+    for (auto &kv : c->plans) {
+        cudaFree(kv.second.d_tw);
+        cudaFree(kv.second.d_w);
+        cudaFree(kv.second.d_bfft);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->d_ws[i]);
+        cudaFree(c->d_spec[i]);
+    }
+    delete c;
+    return DDM_OK;
+}
+
+int ddm_am_hilbert(ddm_fft *c, const void *x_dev, int64_t n, int64_t chunk, void *out_dev, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_am_hilbert: NULL context");
+    DDM_REQUIRE(n >= 0 && chunk >= 1, "ddm_am_hilbert: bad length/chunk");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_am_hilbert: NULL buffer");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float *x = static_cast<const float *>(x_dev);
+    float *out = static_cast<float *>(out_dev);
+    // chunk bounds like chunker.py:32-45: full chunks while start + chunk < n, then the rest
+    int64_t full = 0;
+    while ((full + 1) * chunk < n) ++full;
+    const int64_t tail = n - full * chunk;          // 1..chunk samples
+    struct Part { int64_t start, len, rows; };
+    Part parts[2] = {{0, chunk, full}, {full * chunk, tail, 1}};
+    if (tail == chunk) {                            // the last chunk is a full one too
+        parts[0].rows = full + 1;
+        parts[1].rows = 0;
+    }
+    for (const Part &pt : parts) {
+        if (pt.rows == 0) continue;
+        FftPlan *p = nullptr;
+        int rc = get_plan(c, pt.len, st, &p);
+        if (rc != DDM_OK) return rc;
+        // sub-batches keep the workspace below ~1 GiB
+        int64_t rows_per = std::max<int64_t>(1, (64LL << 20) / (2 * static_cast<int64_t>(p->m)));
+        rows_per = std::min<int64_t>(rows_per, 65535);
+        for (int64_t r0 = 0; r0 < pt.rows; r0 += rows_per) {
+            const int batch = static_cast<int>(std::min<int64_t>(rows_per, pt.rows - r0));
+            rc = ensure_spec(c, static_cast<size_t>(pt.len) * batch, st);
+            if (rc != DDM_OK) return rc;
+            const float *src = x + pt.start + r0 * pt.len;
+            rc = dft_rows<0, false>(c, p, src, pt.len, batch, 1.0, c->d_spec[0], pt.len, st);
+            if (rc != DDM_OK) return rc;
+            const dim3 gn((pt.len + kFftThreads - 1) / kFftThreads, batch);
+            hilbert_mask_kernel<<<gn, kFftThreads, 0, st>>>(c->d_spec[0], pt.len, pt.len);
+            count_launch();
+            rc = dft_rows<2, true>(c, p, c->d_spec[0], pt.len, batch, 1.0 / static_cast<double>(pt.len),
+                                   c->d_spec[1], pt.len, st);
+            if (rc != DDM_OK) return rc;
+            abs_out_kernel<<<gn, kFftThreads, 0, st>>>(c->d_spec[1], pt.len, pt.len,
+                                                       out + pt.start + r0 * pt.len, pt.len);
+            count_launch();
+        }
+    }
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
+int ddm_resample(ddm_fft *c, const void *x_dev, int64_t n, int is_complex, int64_t num, void *out_dev,
+                 void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_resample: NULL context");
+    DDM_REQUIRE(n >= 1 && num >= 0, "ddm_resample: bad lengths");
+    if (num == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_resample: NULL buffer");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FftPlan *pn = nullptr, *pm = nullptr;
+    int rc = get_plan(c, n, st, &pn);
+    if (rc != DDM_OK) return rc;
+    rc = get_plan(c, num, st, &pm);
+    if (rc != DDM_OK) return rc;
+    // std::map nodes are stable, pn stays valid after the second insertion
+    rc = ensure_spec(c, static_cast<size_t>(std::max<int64_t>(n, num)), st);
+    if (rc != DDM_OK) return rc;
+    if (is_complex) rc = dft_rows<1, false>(c, pn, x_dev, n, 1, 1.0, c->d_spec[0], n, st);
+    else rc = dft_rows<0, false>(c, pn, x_dev, n, 1, 1.0, c->d_spec[0], n, st);
+    if (rc != DDM_OK) return rc;
+    const unsigned g = static_cast<unsigned>((num + kFftThreads - 1) / kFftThreads);
+    resample_spec_kernel<<<g, kFftThreads, 0, st>>>(c->d_spec[0], n, c->d_spec[1], num, is_complex ? 0 : 1);
+    count_launch();
+    // y = ifft(Y) * num / n = conj(DFT(conj Y)) / n
+    rc = dft_rows<2, true>(c, pm, c->d_spec[1], num, 1, 1.0 / static_cast<double>(n), c->d_spec[0], num, st);
+    if (rc != DDM_OK) return rc;
+    resample_out_kernel<<<g, kFftThreads, 0, st>>>(c->d_spec[0], num, 1.0, out_dev, is_complex ? 0 : 1);
+    count_launch();
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
+}  // extern "C"

@@ -168,6 +168,21 @@ int ddm_filter_info(const ddm_filter *f, int *is_fir, int64_t *warmup, double *n
 /* scipy.signal.lfilter_zi restated; zi_out has max(na,nb)-1 entries */
 int ddm_lfilter_zi(const double *b, int nb, const double *a, int na, double *zi_out);
 
+/* ---- FFT-defined operators (float64 on the device) -------------------------------------
+ * A context owns the Bluestein/power-of-two plans (cached per length) and the workspace. */
+typedef struct ddm_fft ddm_fft;
+int ddm_fft_create(int device, ddm_fft **out);
+int ddm_fft_destroy(ddm_fft *c);
+/* demod_am.py:29 abs(hilbert(x)) applied per chunk exactly like decode_noaa.__getAM
+ * (decode_noaa.py:631-657; chunk bounds per chunker.py:32-45).  chunk >= n: one transform over
+ * the whole array (demod_am().demod).  x, out: f32 on the device; all chunks of equal length
+ * run as one batch. */
+int ddm_am_hilbert(ddm_fft *c, const void *x_dev, int64_t n, int64_t chunk, void *out_dev, void *stream);
+/* scipy.signal.resample(x, num) (comm.py:114 strict bwLim, decode_noaa.py:350-351): f32 -> f32
+ * (real branch: rfft/irfft semantics) or cf32 -> cf32 (complex branch) */
+int ddm_resample(ddm_fft *c, const void *x_dev, int64_t n, int is_complex, int64_t num, void *out_dev,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

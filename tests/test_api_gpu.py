@@ -343,3 +343,71 @@ def test_long_fir_and_iir_large_chunks():
         b3, a3 = O.taps_butter(2048000, cutoff, n=2)
         want, _ = O.filt_stateful(b3, a3, xr, O.initial_zi(b3, a3))
         assert O.rel_rms(got, want) <= TOL, (cutoff, O.rel_rms(got, want))
+
+
+# ---------------------------------------------------------------------------------------
+# FFT-defined operators: Hilbert envelope and strict (FFT) resampling
+# ---------------------------------------------------------------------------------------
+def test_am_demod_golden(golden):
+    from directdemod_b200 import demod_am
+    g = golden("demod")
+    a = g["am_x"]
+    am = demod_am.demod_am()
+    for got, want in ((am.demod(a), g["am_even"]), (am.demod(a[:2187]), g["am_odd"]),
+                      (am.demod(a[:30]), g["am_small"])):
+        assert got.dtype == np.float64 and got.shape == want.shape
+        assert O.rel_rms(got, want) <= TOL, O.rel_rms(got, want)
+    amf = demod_am.demod_amFLT(20800, 1200)
+    got = np.concatenate([amf.demod(a[:1000]), amf.demod(a[1000:])])
+    assert O.rel_rms(got, g["amflt"]) <= TOL
+
+
+def test_am_chunked_like_getAM_and_power_of_two():
+    """decode_noaa.__getAM: per-240 000-sample Hilbert, last chunk shorter; plus lengths that
+    take the direct power-of-two path."""
+    from directdemod_b200 import demod_am
+    rng = np.random.default_rng(21)
+    n = 2 * 240000 + 101234
+    t = np.arange(n) / 60235.0
+    x = ((1 + 0.4 * np.sin(2 * np.pi * 7 * t)) * np.sin(2 * np.pi * 2400 * t)
+         + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    got = demod_am.demod_am().demodChunked(x, O.AM_CHUNK)
+    want = O.am_envelope_chunked(x.astype(np.float64), O.AM_CHUNK)
+    assert got.shape == want.shape and O.rel_rms(got, want) <= TOL
+    # exact multiple: the reference's chunker still ends with a full-size chunk
+    x2 = x[:480000]
+    assert O.rel_rms(demod_am.demod_am().demodChunked(x2, O.AM_CHUNK),
+                     O.am_envelope_chunked(x2.astype(np.float64), O.AM_CHUNK)) <= TOL
+    for m in (1, 2, 64, 4096, 65536):
+        assert O.rel_rms(demod_am.demod_am().demod(x[:m]), O.am_envelope(x[:m].astype(np.float64))) <= TOL, m
+
+
+def test_strict_bwlim_golden(golden):
+    chunker, comm, constants, demod_fm, filters = _mods()
+    g = golden("bwlim")
+    x = g["x"]
+    s = comm.commSignal(60235, x).bwLim(20800, True)
+    assert s.sampRate == int(g["strict_rate"][0]) and s.length == len(g["strict_even"])
+    assert O.rel_rms(s.signal, g["strict_even"]) <= TOL
+    assert O.rel_rms(comm.commSignal(60235, x[:5800]).bwLim(40960, True).signal, g["strict_b"]) <= TOL
+    assert O.rel_rms(comm.commSignal(48000, x[:4801]).bwLim(12000, True).signal, g["strict_c"]) <= TOL
+
+
+def test_resample_all_branches_match_scipy():
+    """Down/up, even/odd lengths, real and complex: the spectrum bookkeeping of
+    scipy.signal.resample (Nyquist split/join) restated on the device."""
+    import scipy.signal as sps
+    from directdemod_b200 import _dev, fftops
+    rng = np.random.default_rng(33)
+    for n, num in ((1000, 400), (1000, 401), (1001, 400), (1001, 333), (400, 1000), (401, 1000),
+                   (400, 1001), (30117, 2080), (588235, 203127), (512, 512), (512, 128), (7, 3)):
+        xr = rng.standard_normal(n).astype(np.float32)
+        got = _dev.to_host(fftops.resample(_dev.to_device(xr), num))
+        want = sps.resample(xr.astype(np.float64), num)
+        assert got.shape == want.shape and O.rel_rms(got, want) <= TOL, ("real", n, num, O.rel_rms(got, want))
+        if n > 40000:
+            continue
+        xc = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        got = _dev.to_host(fftops.resample(_dev.to_device(xc), num))
+        want = sps.resample(xc.astype(np.complex128), num)
+        assert got.shape == want.shape and O.rel_rms(got, want) <= TOL, ("cplx", n, num, O.rel_rms(got, want))
