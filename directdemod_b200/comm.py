@@ -41,6 +41,7 @@ class commSignal:
         self._pending = []
         self._host = None
         self._dev = None
+        self._parts = []             # device pieces appended by extend(), joined on demand
         if _is_cuda_tensor(sig):
             if sig.dim() != 1:
                 raise TypeError("The signal array must be 1-D")
@@ -66,8 +67,8 @@ class commSignal:
     def signal(self):
         """The samples as a numpy array (float64 / complex128 once an operator has run)."""
         self._flush()
-        if self._host is None:
-            self._host = _dev.to_host(self._dev)
+        if self._host is None or self._parts:
+            self._host = _dev.to_host(self._device_array())
             self._dev = None          # the caller may now mutate the array it was given
         return self._host
 
@@ -78,7 +79,15 @@ class commSignal:
         return self._device_array()
 
     def _device_array(self):
-        if self._dev is None:
+        if self._parts:
+            t = _dev.torch()
+            parts = self._parts
+            self._parts = []
+            if any(p.is_complex() for p in parts):
+                parts = [p.to(t.complex64) for p in parts]
+            self._dev = parts[0] if len(parts) == 1 else t.cat(parts)
+            self._host = None
+        elif self._dev is None:
             self._dev = _dev.to_device(self._host)
             self._host = None
         return self._dev
@@ -143,6 +152,8 @@ class commSignal:
             offset = self._chunker.get(constants.CHUNK_BWLIM + uniq, 0)
             nxt = (jump - (self.length - offset) % jump) % jump
             self._chunker.set(constants.CHUNK_BWLIM + uniq, nxt)
+        if jump == 1 and offset == 0:
+            return self              # x[0::1]: nothing to move (decode_noaa.py:623, 60235 -> 40960)
         if not (self._pending and self._pending[-1][0] == "filter"):
             self._flush()
         self._pending.append(("decim", jump, int(offset)))
@@ -181,12 +192,31 @@ class commSignal:
             self._sampRate = sig.sampRate
         if not self._sampRate == sig.sampRate:
             raise TypeError("Signals must have same sampling rate to be extended")
-        self.updateSignal(np.concatenate([self.signal, sig.signal]))
+        if not isinstance(sig, commSignal):
+            self.updateSignal(np.concatenate([self.signal, sig.signal]))
+            return self
+        # the reference re-concatenates the whole accumulated array on every call (O(chunks^2)
+        # bytes); here the pieces stay on the device and are joined once, when first read
+        self._flush()
+        sig._flush()
+        piece = sig._device_array().clone()
+        if self._len == 0:
+            self._parts = [piece]
+            self._complex = bool(piece.is_complex())
+        else:
+            self._complex = self._complex or bool(piece.is_complex())
+            if not self._parts:
+                self._parts = [self._device_array()]
+            self._parts.append(piece)
+        self._dev = None
+        self._host = None
+        self._len += int(piece.numel())
         return self
 
     def updateSignal(self, sig):
         """Replace the samples (comm.py:166-181)."""
         self._pending = []
+        self._parts = []
         if _is_cuda_tensor(sig):
             if sig.dim() != 1:
                 raise TypeError("The signal array must be 1-D")
@@ -203,6 +233,7 @@ class commSignal:
 
     # ---- execution ------------------------------------------------------------------
     def _set_device(self, tensor):
+        self._parts = []
         self._dev = tensor
         self._host = None
         self._len = int(tensor.numel())

@@ -1,0 +1,562 @@
+// Sync-pattern correlation and peak picking: decode_noaa.__correlate /
+// __correlateAndFindPeaks (decode_noaa.py:659-767), and the AFSK mark/space correlator bank
+// (decode_afsk1200.py:106-142).
+//
+//   cor[i]  = sum_k h[i - M/2 + k] needle[k]                 signal.correlate(h, needle, 'same')
+//   sums[i] = sum_k h[i - M/2 + k]^2                         np.convolve(h*h, ones(M), 'same')
+//   ncc[i]  = cor[i] / sqrt(sums[i] * sum(needle^2))
+//
+// The APT sync needles are piecewise constant (40 bits x round(fs/4160) repeats), so cor is a
+// short weighted sum of range sums: two-level float64 prefix sums of h and h^2 (exclusive
+// prefix inside blocks of 2048 samples + block totals, so a range sum never subtracts two large
+// numbers) turn the 560- or 19 680-tap correlation into ~30 range queries per output --
+// HBM-bound instead of FP64-bound.  Arbitrary needles use the direct kernel.
+//
+// Peak picking: the scalar threshold of decode_noaa.py:714-723 needs the K largest and K
+// smallest values of 54 M correlations; a float64 radix select (8 histogram passes) finds them
+// on the device, an ordered compaction extracts the candidates above the threshold, and the
+// sequential group-maximum scan of :731-746 runs over that short list on the host, bit for bit.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ddm_common.cuh"
+
+namespace ddm {
+
+constexpr int kPfxBlock = 2048;      // samples per prefix block
+constexpr int kPfxThreads = 256;     // 8 samples per thread
+constexpr int kMaxRuns = 128;
+
+struct NeedleRuns {
+    int count;
+    int start[kMaxRuns];
+    int end[kMaxRuns];
+    double value[kMaxRuns];
+};
+
+template <typename T>
+__device__ __forceinline__ double to_double(T v) { return static_cast<double>(v); }
+
+// exclusive prefix inside each block of kPfxBlock samples, for h and h^2, plus block totals.
+// L has n + 1 entries (entry n lets a range end at the very end of the array).
+template <typename T>
+__global__ void __launch_bounds__(kPfxThreads)
+block_prefix_kernel(const T *__restrict__ h, long long n, double *__restrict__ L1, double *__restrict__ L2,
+                    double *__restrict__ T1, double *__restrict__ T2) {
+    __shared__ double s1[kPfxThreads], s2[kPfxThreads];
+    const long long base = static_cast<long long>(blockIdx.x) * kPfxBlock;
+    const int tid = threadIdx.x;
+    constexpr int PER = kPfxBlock / kPfxThreads;
+    double v[PER];
+    double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const long long j = base + tid * PER + i;
+        v[i] = j < n ? to_double(h[j]) : 0.0;
+        a1 += v[i];
+        a2 = fma(v[i], v[i], a2);
+    }
+    s1[tid] = a1;
+    s2[tid] = a2;
+    __syncthreads();
+    // Hillis-Steele over the 256 thread sums
+    for (int off = 1; off < kPfxThreads; off <<= 1) {
+        double b1 = 0.0, b2 = 0.0;
+        if (tid >= off) {
+            b1 = s1[tid - off];
+            b2 = s2[tid - off];
+        }
+        __syncthreads();
+        s1[tid] += b1;
+        s2[tid] += b2;
+        __syncthreads();
+    }
+    double p1 = tid > 0 ? s1[tid - 1] : 0.0;
+    double p2 = tid > 0 ? s2[tid - 1] : 0.0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const long long j = base + tid * PER + i;
+        if (j <= n) {
+            L1[j] = p1;
+            L2[j] = p2;
+        }
+        p1 += v[i];
+        p2 = fma(v[i], v[i], p2);
+    }
+    if (tid == kPfxThreads - 1) {
+        T1[blockIdx.x] = s1[tid];
+        T2[blockIdx.x] = s2[tid];
+    }
+}
+
+// sum over [a, b), 0 <= a <= b <= n
+__device__ __forceinline__ double range_sum(const double *__restrict__ L, const double *__restrict__ T,
+                                            long long a, long long b) {
+    const long long ba = a / kPfxBlock, bb = b / kPfxBlock;
+    if (ba == bb) return L[b] - L[a];
+    double s = T[ba] - L[a];
+    for (long long k = ba + 1; k < bb; ++k) s += T[k];
+    return s + L[b];
+}
+
+__global__ void ncc_runs_kernel(const double *__restrict__ L1, const double *__restrict__ L2,
+                                const double *__restrict__ T1, const double *__restrict__ T2, long long n,
+                                int M, double needle_energy, int normalised, const NeedleRuns runs,
+                                double *__restrict__ out) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long c = M / 2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const long long w0 = i - c;
+        double cor = 0.0;
+        for (int r = 0; r < runs.count; ++r) {
+            long long a = w0 + runs.start[r], b = w0 + runs.end[r];
+            a = a < 0 ? 0 : (a > n ? n : a);
+            b = b < 0 ? 0 : (b > n ? n : b);
+            if (b > a) cor = fma(runs.value[r], range_sum(L1, T1, a, b), cor);
+        }
+        if (normalised) {
+            long long a = w0, b = w0 + M;
+            a = a < 0 ? 0 : a;
+            b = b > n ? n : b;
+            const double sums = b > a ? range_sum(L2, T2, a, b) : 0.0;
+            out[i] = cor / sqrt(sums * needle_energy);
+        } else {
+            out[i] = cor;
+        }
+    }
+}
+
+// direct form for arbitrary needles: one output per thread, needle from global (L1-resident)
+template <typename T>
+__global__ void ncc_direct_kernel(const T *__restrict__ h, long long n, const double *__restrict__ needle,
+                                  int M, double needle_energy, int normalised, double *__restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    const long long w0 = i - M / 2;
+    int k0 = w0 < 0 ? static_cast<int>(-w0) : 0;
+    int k1 = w0 + M > n ? static_cast<int>(n - w0) : M;
+    double cor = 0.0, sums = 0.0;
+    for (int k = k0; k < k1; ++k) {
+        const double v = to_double(h[w0 + k]);
+        cor = fma(v, needle[k], cor);
+        sums = fma(v, v, sums);
+    }
+    out[i] = normalised ? cor / sqrt(sums * needle_energy) : cor;
+}
+
+// ---- radix select on float64 ------------------------------------------------------------
+// order-preserving key; NaNs sort above +inf like numpy's partition
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+    unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+
+// histogram of byte `shift/8` over the elements whose higher bytes equal `prefix`
+__global__ void select_hist_kernel(const double *__restrict__ x, long long n, unsigned long long prefix,
+                                   int shift, unsigned int *__restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const unsigned long long himask = shift >= 56 ? 0ULL : (~0ULL << (shift + 8));
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const unsigned long long k = f64_key(x[i]);
+        if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// per-block partial sums of the values strictly above / below a key, with their counts
+__global__ void select_sum_kernel(const double *__restrict__ x, long long n, unsigned long long key, int above,
+                                  double *__restrict__ part_sum, unsigned long long *__restrict__ part_cnt) {
+    __shared__ double ss[256];
+    __shared__ unsigned long long sc[256];
+    double s = 0.0;
+    unsigned long long c = 0;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        const unsigned long long k = f64_key(v);
+        if (above ? k > key : k < key) {
+            s += v;
+            ++c;
+        }
+    }
+    ss[threadIdx.x] = s;
+    sc[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            ss[threadIdx.x] += ss[threadIdx.x + off];
+            sc[threadIdx.x] += sc[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        part_sum[blockIdx.x] = ss[0];
+        part_cnt[blockIdx.x] = sc[0];
+    }
+}
+
+// ---- ordered compaction of the samples above a threshold --------------------------------
+constexpr int kCompactThreads = 256;
+constexpr int kCompactPer = 16;      // samples per thread, contiguous
+
+__global__ void compact_count_kernel(const double *__restrict__ x, long long n, double thr,
+                                     unsigned int *__restrict__ block_cnt) {
+    __shared__ unsigned int s[kCompactThreads];
+    const long long base = (static_cast<long long>(blockIdx.x) * kCompactThreads + threadIdx.x) * kCompactPer;
+    unsigned int c = 0;
+    for (int i = 0; i < kCompactPer; ++i) {
+        const long long j = base + i;
+        if (j < n && x[j] > thr) ++c;
+    }
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = kCompactThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = s[0];
+}
+
+__global__ void compact_write_kernel(const double *__restrict__ x, long long n, double thr,
+                                     const unsigned long long *__restrict__ block_off, long long cap,
+                                     long long *__restrict__ idx, double *__restrict__ val) {
+    __shared__ unsigned int s[kCompactThreads];
+    const long long base = (static_cast<long long>(blockIdx.x) * kCompactThreads + threadIdx.x) * kCompactPer;
+    unsigned int c = 0;
+    for (int i = 0; i < kCompactPer; ++i) {
+        const long long j = base + i;
+        if (j < n && x[j] > thr) ++c;
+    }
+    s[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = 1; off < kCompactThreads; off <<= 1) {
+        unsigned int b = threadIdx.x >= off ? s[threadIdx.x - off] : 0;
+        __syncthreads();
+        s[threadIdx.x] += b;
+        __syncthreads();
+    }
+    long long pos = static_cast<long long>(block_off[blockIdx.x]) + (s[threadIdx.x] - c);
+    for (int i = 0; i < kCompactPer; ++i) {
+        const long long j = base + i;
+        if (j < n && x[j] > thr) {
+            if (pos < cap) {
+                idx[pos] = j;
+                val[pos] = x[j];
+            }
+            ++pos;
+        }
+    }
+}
+
+// ---- AFSK correlator bank ---------------------------------------------------------------
+// out[s] = (sum x[s+k] t0[k])^2 + (sum x[s+k] t1[k])^2 - (sum x[s+k] t2[k])^2 - (sum x[s+k] t3[k])^2
+// for s < n - nbuf, 0 for the last nbuf outputs (loop bound of decode_afsk1200.py:129)
+template <typename T>
+__global__ void bank4_kernel(const T *__restrict__ x, long long n, const double *__restrict__ taps, int nbuf,
+                             float *__restrict__ out) {
+    extern __shared__ double s_taps[];
+    for (int i = threadIdx.x; i < 4 * nbuf; i += blockDim.x) s_taps[i] = taps[i];
+    __syncthreads();
+    const long long s = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (s >= n) return;
+    if (s >= n - nbuf) {
+        out[s] = 0.f;
+        return;
+    }
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int k = 0; k < nbuf; ++k) {
+        const double v = to_double(x[s + k]);
+        a0 = fma(v, s_taps[k], a0);
+        a1 = fma(v, s_taps[nbuf + k], a1);
+        a2 = fma(v, s_taps[2 * nbuf + k], a2);
+        a3 = fma(v, s_taps[3 * nbuf + k], a3);
+    }
+    out[s] = static_cast<float>(a0 * a0 + a1 * a1 - a2 * a2 - a3 * a3);
+}
+
+}  // namespace ddm
+
+using namespace ddm;
+
+namespace {
+
+int check_device(int device, const char *who) {
+    int ndev = 0;
+    DDM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) {
+        set_error("%s: no such device %d", who, device);
+        return DDM_ERR_INVALID;
+    }
+    return DDM_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int alloc(size_t bytes) {
+        DDM_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+        return DDM_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, const double *needle_host,
+                  int m, int normalised, void *out_f64_dev, void *stream) {
+    DDM_REQUIRE(n >= 0 && m >= 1, "ddm_correlate: bad lengths");
+    DDM_REQUIRE(needle_host != nullptr, "ddm_correlate: NULL needle");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(hay_dev != nullptr && out_f64_dev != nullptr, "ddm_correlate: NULL buffer");
+    int rc = check_device(device, "ddm_correlate");
+    if (rc != DDM_OK) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double energy = 0.0;
+    for (int k = 0; k < m; ++k) energy += needle_host[k] * needle_host[k];
+    // run-length form of the needle
+    NeedleRuns runs;
+    runs.count = 0;
+    bool compressible = true;
+    for (int k = 0; k < m;) {
+        int e = k + 1;
+        while (e < m && needle_host[e] == needle_host[k]) ++e;
+        if (needle_host[k] != 0.0) {
+            if (runs.count == kMaxRuns) {
+                compressible = false;
+                break;
+            }
+            runs.start[runs.count] = k;
+            runs.end[runs.count] = e;
+            runs.value[runs.count] = needle_host[k];
+            ++runs.count;
+        }
+        k = e;
+    }
+    double *out = static_cast<double *>(out_f64_dev);
+    if (compressible && runs.count * 8 <= m) {
+        const long long nblk = n / kPfxBlock + 1;
+        DevBuf L1, L2, T1, T2;
+        if ((rc = L1.alloc(sizeof(double) * (n + 1))) != DDM_OK) return rc;
+        if ((rc = L2.alloc(sizeof(double) * (n + 1))) != DDM_OK) return rc;
+        if ((rc = T1.alloc(sizeof(double) * nblk)) != DDM_OK) return rc;
+        if ((rc = T2.alloc(sizeof(double) * nblk)) != DDM_OK) return rc;
+        if (hay_is_f64)
+            block_prefix_kernel<double><<<static_cast<unsigned>(nblk), kPfxThreads, 0, st>>>(
+                static_cast<const double *>(hay_dev), n, static_cast<double *>(L1.p), static_cast<double *>(L2.p),
+                static_cast<double *>(T1.p), static_cast<double *>(T2.p));
+        else
+            block_prefix_kernel<float><<<static_cast<unsigned>(nblk), kPfxThreads, 0, st>>>(
+                static_cast<const float *>(hay_dev), n, static_cast<double *>(L1.p), static_cast<double *>(L2.p),
+                static_cast<double *>(T1.p), static_cast<double *>(T2.p));
+        const long long want = (n + 255) / 256;
+        const unsigned grid = static_cast<unsigned>(std::min<long long>(want, static_cast<long long>(sm_count(device)) * 16));
+        ncc_runs_kernel<<<grid, 256, 0, st>>>(static_cast<const double *>(L1.p), static_cast<const double *>(L2.p),
+                                             static_cast<const double *>(T1.p), static_cast<const double *>(T2.p),
+                                             n, m, energy, normalised, runs, out);
+        count_launch(2);
+        DDM_CUDA(cudaGetLastError());
+        DDM_CUDA(cudaStreamSynchronize(st));      // the scratch buffers die with this scope
+        return DDM_OK;
+    }
+    DevBuf nd;
+    if ((rc = nd.alloc(sizeof(double) * m)) != DDM_OK) return rc;
+    DDM_CUDA(cudaMemcpyAsync(nd.p, needle_host, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (hay_is_f64)
+        ncc_direct_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(hay_dev), n,
+                                                        static_cast<const double *>(nd.p), m, energy, normalised, out);
+    else
+        ncc_direct_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(hay_dev), n,
+                                                       static_cast<const double *>(nd.p), m, energy, normalised, out);
+    count_launch();
+    DDM_CUDA(cudaGetLastError());
+    DDM_CUDA(cudaStreamSynchronize(st));
+    return DDM_OK;
+}
+
+int ddm_topk_sums(int device, const void *x_f64_dev, int64_t n, int64_t k, double *sum_top, double *sum_bottom,
+                  void *stream) {
+    DDM_REQUIRE(n >= 1 && k >= 1 && k <= n, "ddm_topk_sums: need 1 <= k <= n (k = %lld, n = %lld)",
+                static_cast<long long>(k), static_cast<long long>(n));
+    DDM_REQUIRE(x_f64_dev != nullptr, "ddm_topk_sums: NULL buffer");
+    int rc = check_device(device, "ddm_topk_sums");
+    if (rc != DDM_OK) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double *x = static_cast<const double *>(x_f64_dev);
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, static_cast<long long>(sm_count(device)) * 8));
+    DevBuf hist, psum, pcnt;
+    if ((rc = hist.alloc(sizeof(unsigned int) * 256)) != DDM_OK) return rc;
+    if ((rc = psum.alloc(sizeof(double) * grid)) != DDM_OK) return rc;
+    if ((rc = pcnt.alloc(sizeof(unsigned long long) * grid)) != DDM_OK) return rc;
+    std::vector<unsigned int> h(256);
+    std::vector<double> hs(grid);
+    std::vector<unsigned long long> hc(grid);
+    for (int which = 0; which < 2; ++which) {
+        const bool top = which == 0;
+        double *result = top ? sum_top : sum_bottom;
+        if (!result) continue;
+        // find the key of the k-th largest (top) / k-th smallest (bottom) element
+        unsigned long long prefix = 0;
+        long long remaining = k;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            DDM_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned int) * 256, st));
+            select_hist_kernel<<<grid, 256, 0, st>>>(x, n, prefix, shift, static_cast<unsigned int *>(hist.p));
+            count_launch();
+            DDM_CUDA(cudaMemcpyAsync(h.data(), hist.p, sizeof(unsigned int) * 256, cudaMemcpyDeviceToHost, st));
+            DDM_CUDA(cudaStreamSynchronize(st));
+            int digit = top ? 255 : 0;
+            while (true) {
+                if (static_cast<long long>(h[digit]) >= remaining) break;
+                remaining -= h[digit];
+                digit += top ? -1 : 1;
+                if (digit < 0 || digit > 255) {
+                    set_error("ddm_topk_sums: internal selection error");
+                    return DDM_ERR_INVALID;
+                }
+            }
+            prefix |= static_cast<unsigned long long>(digit) << shift;
+        }
+        // `remaining` copies of the k-th value itself belong to the selection
+        select_sum_kernel<<<grid, 256, 0, st>>>(x, n, prefix, top ? 1 : 0, static_cast<double *>(psum.p),
+                                                static_cast<unsigned long long *>(pcnt.p));
+        count_launch();
+        DDM_CUDA(cudaMemcpyAsync(hs.data(), psum.p, sizeof(double) * grid, cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaMemcpyAsync(hc.data(), pcnt.p, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+        double s = 0.0;
+        unsigned long long c = 0;
+        for (unsigned i = 0; i < grid; ++i) {
+            s += hs[i];
+            c += hc[i];
+        }
+        // value of the k-th element from its key
+        unsigned long long u = (prefix >> 63) ? (prefix & 0x7FFFFFFFFFFFFFFFULL) : ~prefix;
+        double kth;
+        std::memcpy(&kth, &u, sizeof(kth));
+        *result = s + kth * static_cast<double>(static_cast<long long>(k) - static_cast<long long>(c));
+    }
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
+int ddm_compact_above(int device, const void *x_f64_dev, int64_t n, double threshold, void *idx_i64_dev,
+                      void *val_f64_dev, int64_t capacity, int64_t *count, void *stream) {
+    DDM_REQUIRE(n >= 0 && capacity >= 0 && count != nullptr, "ddm_compact_above: bad arguments");
+    *count = 0;
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_f64_dev != nullptr, "ddm_compact_above: NULL buffer");
+    int rc = check_device(device, "ddm_compact_above");
+    if (rc != DDM_OK) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double *x = static_cast<const double *>(x_f64_dev);
+    const long long per_block = static_cast<long long>(kCompactThreads) * kCompactPer;
+    const long long blocks = (n + per_block - 1) / per_block;
+    DevBuf cnt, off;
+    if ((rc = cnt.alloc(sizeof(unsigned int) * blocks)) != DDM_OK) return rc;
+    if ((rc = off.alloc(sizeof(unsigned long long) * blocks)) != DDM_OK) return rc;
+    compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(x, n, threshold,
+                                                                                    static_cast<unsigned int *>(cnt.p));
+    count_launch();
+    std::vector<unsigned int> hc(blocks);
+    DDM_CUDA(cudaMemcpyAsync(hc.data(), cnt.p, sizeof(unsigned int) * blocks, cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> ho(blocks);
+    unsigned long long total = 0;
+    for (long long b = 0; b < blocks; ++b) {
+        ho[b] = total;
+        total += hc[b];
+    }
+    *count = static_cast<int64_t>(total);
+    if (total == 0 || capacity == 0) return DDM_OK;
+    DDM_REQUIRE(idx_i64_dev != nullptr && val_f64_dev != nullptr, "ddm_compact_above: NULL output");
+    DDM_CUDA(cudaMemcpyAsync(off.p, ho.data(), sizeof(unsigned long long) * blocks, cudaMemcpyHostToDevice, st));
+    compact_write_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(
+        x, n, threshold, static_cast<const unsigned long long *>(off.p), capacity,
+        static_cast<long long *>(idx_i64_dev), static_cast<double *>(val_f64_dev));
+    count_launch();
+    DDM_CUDA(cudaGetLastError());
+    DDM_CUDA(cudaStreamSynchronize(st));
+    return DDM_OK;
+}
+
+int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double min_dist, int64_t *peaks,
+                    int64_t capacity, int64_t *n_peaks) {
+    DDM_REQUIRE(count >= 0 && n_peaks != nullptr, "ddm_group_peaks: bad arguments");
+    *n_peaks = 0;
+    if (count == 0) return DDM_OK;
+    DDM_REQUIRE(idx != nullptr && val != nullptr, "ddm_group_peaks: NULL input");
+    // decode_noaa.py:731-746: running maximum, closed when a candidate is >= min_dist beyond the
+    // CURRENT maximum; strict '<' so the first of equal maxima wins
+    bool have = false;
+    double cur_max = 0.0;
+    int64_t cur_idx = 0;
+    int64_t np = 0;
+    auto emit = [&](int64_t v) {
+        if (np < capacity && peaks) peaks[np] = v;
+        ++np;
+    };
+    for (int64_t i = 0; i < count; ++i) {
+        if (have && static_cast<double>(idx[i] - cur_idx) >= min_dist) {
+            emit(cur_idx);
+            have = false;
+        }
+        if (!have || cur_max < val[i]) {
+            cur_max = val[i];
+            cur_idx = idx[i];
+            have = true;
+        }
+    }
+    emit(cur_idx);
+    *n_peaks = np;
+    if (np > capacity) {
+        set_error("ddm_group_peaks: %lld peaks, capacity %lld", static_cast<long long>(np),
+                  static_cast<long long>(capacity));
+        return DDM_ERR_CAPACITY;
+    }
+    return DDM_OK;
+}
+
+int ddm_bank4(int device, const void *x_dev, int64_t n, int x_is_f64, const double *taps4_host, int nbuf,
+              void *out_f32_dev, void *stream) {
+    DDM_REQUIRE(n >= 0 && nbuf >= 1, "ddm_bank4: bad lengths");
+    DDM_REQUIRE(taps4_host != nullptr, "ddm_bank4: NULL taps");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_f32_dev != nullptr, "ddm_bank4: NULL buffer");
+    DDM_REQUIRE(nbuf <= 4096, "ddm_bank4: at most 4096 taps per correlator");
+    int rc = check_device(device, "ddm_bank4");
+    if (rc != DDM_OK) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevBuf t;
+    if ((rc = t.alloc(sizeof(double) * 4 * nbuf)) != DDM_OK) return rc;
+    DDM_CUDA(cudaMemcpyAsync(t.p, taps4_host, sizeof(double) * 4 * nbuf, cudaMemcpyHostToDevice, st));
+    const size_t smem = sizeof(double) * 4 * nbuf;
+    if (smem > 48 * 1024) {
+        DDM_CUDA(cudaFuncSetAttribute(bank4_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        DDM_CUDA(cudaFuncSetAttribute(bank4_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (x_is_f64)
+        bank4_kernel<double><<<grid, 256, smem, st>>>(static_cast<const double *>(x_dev), n,
+                                                      static_cast<const double *>(t.p), nbuf, static_cast<float *>(out_f32_dev));
+    else
+        bank4_kernel<float><<<grid, 256, smem, st>>>(static_cast<const float *>(x_dev), n,
+                                                     static_cast<const double *>(t.p), nbuf, static_cast<float *>(out_f32_dev));
+    count_launch();
+    DDM_CUDA(cudaGetLastError());
+    DDM_CUDA(cudaStreamSynchronize(st));
+    return DDM_OK;
+}
+
+}  // extern "C"

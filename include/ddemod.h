@@ -183,6 +183,30 @@ int ddm_am_hilbert(ddm_fft *c, const void *x_dev, int64_t n, int64_t chunk, void
 int ddm_resample(ddm_fft *c, const void *x_dev, int64_t n, int is_complex, int64_t num, void *out_dev,
                  void *stream);
 
+/* ---- sync correlation and peak picking (decode_noaa.py:659-767) -------------------------
+ * out[i] = sum_k hay[i - m/2 + k] needle[k]  (signal.correlate 'same'), divided by
+ * sqrt(sum_k hay[i - m/2 + k]^2 * sum(needle^2)) when normalised (decode_noaa.__correlate).
+ * hay: f32 or f64 on the device; needle: host f64; out: f64 on the device.  Piecewise-constant
+ * needles (the APT sync words) run on two-level prefix sums, others on the direct kernel. */
+int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, const double *needle_host,
+                  int m, int normalised, void *out_f64_dev, void *stream);
+/* sum of the k largest and of the k smallest values of a float64 device array -- what
+ * np.sum(cor[np.argpartition(cor, -k)[-k:]]) and its mirror compute (decode_noaa.py:714-720) */
+int ddm_topk_sums(int device, const void *x_f64_dev, int64_t n, int64_t k, double *sum_top,
+                  double *sum_bottom, void *stream);
+/* np.argwhere(x > threshold), ascending, with the values (decode_noaa.py:723); *count is the
+ * number found even when it exceeds capacity (call again with larger buffers) */
+int ddm_compact_above(int device, const void *x_f64_dev, int64_t n, double threshold, void *idx_i64_dev,
+                      void *val_f64_dev, int64_t capacity, int64_t *count, void *stream);
+/* host: the sequential group-maximum scan of decode_noaa.py:731-746 over (idx, val) candidates */
+int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double min_dist, int64_t *peaks,
+                    int64_t capacity, int64_t *n_peaks);
+/* decode_afsk1200.py:106-142: four nbuf-tap correlators over a real signal (taps4_host =
+ * [mark cos | mark sin | space cos | space sin], host f64); out[s] = mi^2 + mq^2 - si^2 - sq^2 for
+ * s < n - nbuf, 0 for the last nbuf samples; out f32 on the device */
+int ddm_bank4(int device, const void *x_dev, int64_t n, int x_is_f64, const double *taps4_host, int nbuf,
+              void *out_f32_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

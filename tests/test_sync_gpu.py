@@ -1,0 +1,148 @@
+"""GPU parity of the sync path: normalised correlation, threshold selection, peak picking,
+decode_noaa.getCrudeSync / getAccurateSync (positions bit-exact), and the AFSK correlator bank."""
+
+import numpy as np
+import pytest
+
+from oracle import ddoracle as O
+from tests.util import TOL, ArraySource, apt_iq
+
+pytestmark = pytest.mark.gpu
+
+
+def test_correlate_matches_oracle_runs_and_direct_paths():
+    from directdemod_b200 import sync
+    rng = np.random.default_rng(1)
+    n = 200000
+    hay = np.abs(rng.standard_normal(n)) + 0.1
+    for needle in (sync.sync_needle(O.NOAA_SYNCA, 60235), sync.sync_needle(O.NOAA_SYNCB, 60235, False),
+                   rng.standard_normal(561), rng.standard_normal(64), np.ones(7)):
+        for normalised in (True, False):
+            got = sync.correlate(hay, needle, normalised).cpu().numpy()
+            want = O.ncc(hay, needle) if normalised else __import__("scipy.signal").signal.correlate(hay, needle, "same")
+            assert got.shape == want.shape
+            assert O.rel_rms(got, want) <= 1e-9, (len(needle), normalised, O.rel_rms(got, want))
+    # float32 device input (what the AM kernel hands over)
+    import torch
+    h32 = torch.from_numpy(hay.astype(np.float32)).cuda()
+    needle = sync.sync_needle(O.NOAA_SYNCA, 60235)
+    got = sync.correlate(h32, needle).cpu().numpy()
+    assert O.rel_rms(got, O.ncc(hay.astype(np.float32).astype(np.float64), needle)) <= 1e-9
+    assert np.array_equal(sync.sync_needle(O.NOAA_SYNCA, 60235), O.sync_needle(O.NOAA_SYNCA, 60235))
+
+
+def test_topk_sums_compaction_and_group_scan():
+    import ctypes as C
+    import torch
+    from directdemod_b200 import _dev, _lib
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(1000003)
+    x[1234] = x[99999] = 7.5            # ties at the top
+    x[5] = -9.0
+    xd = torch.from_numpy(x).cuda()
+    for k in (1, 2, 17, 4000, len(x)):
+        top, bot = C.c_double(), C.c_double()
+        _lib.check(_lib.lib().ddm_topk_sums(0, _dev.ptr(xd), len(x), k, C.byref(top), C.byref(bot), _dev.stream_ptr(0)), "topk")
+        s = np.sort(x)
+        assert abs(top.value - s[-k:].sum()) <= 1e-9 * max(1.0, abs(s[-k:].sum())), k
+        assert abs(bot.value - s[:k].sum()) <= 1e-9 * max(1.0, abs(s[:k].sum())), k
+    thr = 2.5
+    want = np.argwhere(x > thr).ravel()
+    idx = torch.empty(len(want) + 10, dtype=torch.int64, device="cuda")
+    val = torch.empty(len(want) + 10, dtype=torch.float64, device="cuda")
+    cnt = C.c_int64()
+    _lib.check(_lib.lib().ddm_compact_above(0, _dev.ptr(xd), len(x), thr, _dev.ptr(idx), _dev.ptr(val), idx.numel(),
+                                            C.byref(cnt), _dev.stream_ptr(0)), "compact")
+    assert cnt.value == len(want)
+    assert np.array_equal(idx[:cnt.value].cpu().numpy(), want)
+    assert np.array_equal(val[:cnt.value].cpu().numpy(), x[want])
+
+
+def test_pick_peaks_matches_reference_logic_including_ties():
+    import torch
+    from directdemod_b200 import sync
+    rng = np.random.default_rng(3)
+    fs = 1000
+    n = 20000
+    cor = 0.05 * rng.standard_normal(n)
+    for p in range(250, n, 500):
+        cor[p - 3:p + 4] += np.array([0.2, 0.5, 0.8, 1.0, 0.8, 0.5, 0.2])
+    cor[2750] = cor[2751] = 1.5         # exact tie: the first one must win (strict '<')
+    got, _ = sync.pick_peaks(torch.from_numpy(cor).cuda(), fs, 40)
+    want = O.pick_sync_peaks(cor, fs, 40)
+    assert np.array_equal(got, want)
+
+
+@pytest.fixture(scope="module")
+def apt_pass():
+    fs = 2048000
+    x = apt_iq(7, 11.0, fs=fs)          # 22.5 M samples -> two PROC_CHUNKSIZE chunks
+    return x, fs
+
+
+def test_crude_sync_positions_bit_exact(apt_pass):
+    from directdemod_b200 import decode_noaa
+    x, fs = apt_pass
+    dec = decode_noaa.decode_noaa(ArraySource(x, fs), 30000.0)
+    syncA, syncB = dec.getCrudeSync()
+    assert dec.useful == 1
+    # oracle: the reference's algorithm on the same input (float64 scipy path)
+    taps = O.taps_blackman_harris(151)[0]
+    audio, rate = O.chain_stream(x, fs, 30000.0, taps, 60000)
+    assert rate == 60235
+    am = O.am_envelope_chunked(audio)
+    wantA, _ = O.find_syncs(am, rate, O.NOAA_SYNCA)
+    wantB, _ = O.find_syncs(am, rate, O.NOAA_SYNCB)
+    assert np.array_equal(np.asarray(syncA), wantA)
+    assert np.array_equal(np.asarray(syncB), wantB)
+    assert len(wantA) >= 20 and np.all(np.abs(np.diff(wantA)[:-1] - rate / 2) <= 2)   # last one: cut-off line
+    # intermediate signals within the stated tolerance
+    from tests.util import wrap_rel_rms
+    assert wrap_rel_rms(dec._audOut.signal, audio) <= TOL
+
+
+def test_accurate_sync_positions_bit_exact(apt_pass):
+    from directdemod_b200 import decode_noaa
+    x, fs = apt_pass
+    n_use = int(6.2 * fs)               # >= 11 syncs, or the usefulness test has nothing to look at
+    xs = x[:n_use]
+    dec = decode_noaa.decode_noaa(ArraySource(xs, fs), 30000.0)
+    res = dec.getAccurateSync()
+    asyncA, asyncB = res[0], res[4]
+    # oracle windows (decode_noaa.py:826-856 restated with the oracle primitives)
+    taps = O.taps_blackman_harris(151)[0]
+    audio, rate = O.chain_stream(xs, fs, 30000.0, taps, 60000)
+    am = O.am_envelope_chunked(audio)
+    width = int(3 * O.NOAA_T * 40 * fs)
+    ham = O.taps_hamming(492)[0]
+    for bits, got in ((O.NOAA_SYNCA, asyncA), (O.NOAA_SYNCB, asyncB)):
+        crude, _ = O.find_syncs(am, rate, bits)
+        want = []
+        for c in crude / rate * fs:
+            a, b = int(c) - width, int(c) + width
+            if a < 0 or b > len(xs):
+                continue
+            if len(want) == 4:          # a handful of windows keeps the CPU oracle in seconds
+                break
+            w, _ = O.mix(xs[a:b], 30000.0, fs, 0)
+            w = O.filt_zero_phase(taps, [1], w)
+            w, _ = O.fm_discriminator(w, None, store_state=True)
+            w = O.am_envelope(w)
+            pk, _ = O.find_syncs(w, fs, bits, prefilter_taps=ham)
+            want.append(pk[0] + a)
+        assert len(want) >= 3
+        assert list(map(int, got[:len(want)])) == list(map(int, want))
+
+
+def test_afsk_bank_matches_oracle():
+    from directdemod_b200 import afsk
+    rng = np.random.default_rng(5)
+    for bw, n in ((48000, 30000), (22050, 5000), (48000, 30)):
+        t = np.arange(n) / bw
+        x = np.sin(2 * np.pi * np.where((t * 1200).astype(int) % 2 == 0, 1200, 2200) * t) + 0.1 * rng.standard_normal(n)
+        got = afsk.mark_space_bank(x, bw)
+        want = O.afsk_bank(x, bw)
+        assert got.shape == want.shape
+        nbuf = int(np.round(bw / 1200))
+        assert np.all(got[max(0, n - nbuf):] == 0)
+        assert O.rel_rms(got, want) <= TOL
