@@ -1,0 +1,109 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed).
+
+Two seams, both taken from the reference's own structure:
+
+* independent units -- separate captures, separate channels of one recording, the
+  accurate-sync windows (decode_noaa.py:844,865): ``unit_range`` deals them out, no
+  communication.
+* one long stream in time -- the chunker's seam (chunker.py): rank g owns a contiguous slab
+  of the stream.  The only data that crosses a slab boundary is what the reference carries
+  from chunk to chunk, expressed as raw input history: the last ``halo_len`` samples of the
+  previous slab (FIR delay line + previous decimated sample for the FM discriminator; for the
+  segment-parallel IIR the same halo is its warm-up).  ``exchange_halo`` moves it with ONE
+  neighbour send/recv per rank (NCCL point-to-point over NVLink; a few KB, latency bound).
+  The mixer phase and the decimation phase need no exchange: both are functions of the
+  global sample index.
+
+The sequential (bit-exact replay) IIR mode cannot be time-sharded -- its state is a serial
+dependency by construction; such filters shard by independent units only.
+"""
+
+from __future__ import annotations
+
+
+def unit_range(n_units, world, rank):
+    """[first, last) of the units rank ``rank`` of ``world`` processes (contiguous blocks,
+    sizes differing by at most one)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank %r/%r" % (world, rank))
+    base, extra = divmod(int(n_units), world)
+    first = rank * base + min(rank, extra)
+    return first, first + base + (1 if rank < extra else 0)
+
+
+def slab_bounds(n_samples, world, decim=1):
+    """Time slabs [start, end) per rank, starts aligned to the decimation factor so every
+    slab begins on a kept sample (comm.py:124: kept samples are those with global index
+    == offset (mod j); offset is 0 at the start of a stream)."""
+    n_samples, decim = int(n_samples), int(decim)
+    if world < 1 or decim < 1:
+        raise ValueError("bad world/decimation")
+    starts = [(g * n_samples // world) // decim * decim for g in range(world)]
+    ends = starts[1:] + [n_samples]
+    return [(s, e) for s, e in zip(starts, ends)]
+
+
+def decim_offset_at(start, decim, stream_offset=0):
+    """Chunker variable "bwlim" a chunk starting at global index ``start`` would see."""
+    return (stream_offset - start) % decim
+
+
+def exchange_halo(tail, rank, world, group=None):
+    """Ring shift g -> g+1 of the slab tails.  ``tail``: this rank's last halo_len input
+    samples (tensor on the device of the process group's backend).  Returns the tensor received
+    from rank-1, or None on rank 0 (which starts from the reference's initial condition)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return None
+    ops = []
+    recv = torch.empty_like(tail) if rank > 0 else None
+    if rank + 1 < world:
+        ops.append(dist.P2POp(dist.isend, tail.contiguous(), rank + 1, group))
+    if rank > 0:
+        ops.append(dist.P2POp(dist.irecv, recv, rank - 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    return recv
+
+
+class TimeShardedChain:
+    """The fused chain over one slab of a time-sharded stream.
+
+    Every rank builds the same chain (taps, decimation, mixer); ``run`` receives the slab's
+    raw cf32 samples (cuda tensor), exchanges halos with the neighbours and returns this rank's
+    part of the output.  Concatenating the parts of ranks 0..world-1 gives exactly what one
+    GPU (and the reference) produces for the whole stream."""
+
+    def __init__(self, taps, decim, freq_offset, samp_rate, n_samples, rank, world, demod=True,
+                 device=None, group=None):
+        from .fused import FusedChain
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.decim = int(decim)
+        self.bounds = slab_bounds(n_samples, world, decim)
+        self.start, self.end = self.bounds[rank]
+        self.chain = FusedChain(taps, decim, freq_offset, samp_rate, demod=demod, device=device)
+        self.halo_len = self.chain.halo_len
+        for s, e in self.bounds[:-1]:
+            if e - s < self.halo_len:
+                raise ValueError("slab of %d samples is shorter than the %d-sample halo" % (e - s, self.halo_len))
+
+    def run(self, x_slab):
+        if x_slab.numel() != self.end - self.start:
+            raise ValueError("slab has %d samples, expected %d" % (x_slab.numel(), self.end - self.start))
+        tail = x_slab[-self.halo_len:] if self.rank + 1 < self.world else x_slab[:0]
+        if self.rank + 1 < self.world and tail.numel() != self.halo_len:
+            raise ValueError("slab shorter than the halo")
+        if self.world > 1:
+            import torch
+            send = tail if self.rank + 1 < self.world else torch.empty(self.halo_len, dtype=x_slab.dtype,
+                                                                        device=x_slab.device)
+            halo = exchange_halo(send, self.rank, self.world, self.group)
+        else:
+            halo = None
+        off = decim_offset_at(self.start, self.decim)
+        if self.rank == 0:
+            self.chain.set_position(0, off, False)
+        else:
+            self.chain.set_position(self.start, off, True, halo)
+        return self.chain.apply(x_slab)

@@ -1,0 +1,152 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the public
+header declares, the ctypes table mirrors the header, and the pure host logic of the drop-in
+API (chunker, constants, argument validation) behaves like the reference."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ddemod.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_a_sane_api():
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    for must in ("ddm_chain_apply_dev", "ddm_chain_apply_host", "ddm_filter_apply_dev", "ddm_am_hilbert",
+                 "ddm_resample", "ddm_correlate", "ddm_fm_demod", "ddm_mix_cf32", "ddm_last_error"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from directdemod_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(handle, s)]
+    assert not missing, missing
+
+
+def test_ctypes_table_mirrors_the_header():
+    from directdemod_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.lib()                      # binds restype/argtypes of every entry
+    assert lib.ddm_version() >= 100
+    n = ctypes.c_int(-1)
+    assert lib.ddm_device_count(ctypes.byref(n)) == 0 and n.value >= 0
+
+
+def test_lfilter_zi_restatement_matches_scipy():
+    import scipy.signal as sps
+    from directdemod_b200 import _lib
+    lib = _lib.lib()
+    # (the 12th-order band-pass is left out: its zi is a catastrophic cancellation, scipy's own
+    # float64 solve is only good to ~3e-4 there, and the Python layer hands scipy's very bits to
+    # the library through ddm_filter_set_zi_base for exactly that reason)
+    for b, a in (sps.butter(8, 0.0833), sps.butter(4, 0.2),
+                 (sps.windows.hamming(492), [1.0]), ([0.5, 0.5], [1.0]), sps.butter(3, 0.125, btype="highpass")):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        zi = np.zeros(max(len(a), len(b)) - 1)
+        rc = lib.ddm_lfilter_zi(b.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(b),
+                                a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(a),
+                                zi.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert rc == 0
+        np.testing.assert_allclose(zi, sps.lfilter_zi(b, a), rtol=1e-9, atol=1e-12)
+
+
+def test_group_peaks_host_logic_matches_reference_scan():
+    from directdemod_b200 import _lib
+    from oracle import ddoracle as O
+    rng = np.random.default_rng(4)
+    fs, n = 1000, 30000
+    cor = 0.05 * rng.standard_normal(n)
+    for p in range(250, n, 500):
+        cor[p - 2:p + 3] += np.array([0.4, 0.8, 1.0, 0.8, 0.4])
+    cor[5250] = cor[5251] = 2.0
+    want = O.pick_sync_peaks(cor, fs, 0)
+    expected = int(2 * (n / fs)) + 2
+    s = np.sort(cor)
+    thr = s[-expected:].sum() / expected
+    thr -= O.NOAA_PEAKHEIGHTWIGGLE * (thr - s[:expected].sum() / expected)
+    idx = np.ascontiguousarray(np.argwhere(cor > thr).ravel().astype(np.int64))
+    val = np.ascontiguousarray(cor[idx])
+    out = np.zeros(len(idx), dtype=np.int64)
+    cnt = ctypes.c_int64()
+    rc = _lib.lib().ddm_group_peaks(idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                    val.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(idx),
+                                    O.NOAA_MINPEAKDIST * fs, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                    len(out), ctypes.byref(cnt))
+    assert rc == 0
+    assert np.array_equal(np.sort(out[:cnt.value]), want)
+
+
+def test_chunker_matches_reference_golden(golden):
+    from directdemod_b200 import chunker
+
+    class Src:
+        def __init__(self, n):
+            self.length = n
+    g = golden("chunker")
+    for key in g.files:
+        ln, sz = (int(v[1:]) for v in key.split("_"))
+        assert np.array_equal(np.array(chunker.chunker(Src(ln), sz).getChunks, dtype=np.int64), g[key]), key
+    ck = chunker.chunker(Src(25), 10)
+    with pytest.raises(KeyError):
+        ck.get("missing")
+    assert ck.get("v", 3) == 3
+    ck.set("v", 9)
+    assert ck.get("v", 3) == 9 and ck.get("v") == 9
+
+
+def test_constants_match_reference_values():
+    from directdemod_b200 import constants as c
+    from oracle import ddoracle as O
+    assert c.PROC_CHUNKSIZE == O.PROC_CHUNKSIZE == 20000000
+    assert c.NOAA_SYNCA == O.NOAA_SYNCA and c.NOAA_SYNCB == O.NOAA_SYNCB
+    assert c.NOAA_T == O.NOAA_T and c.NOAA_MINPEAKDIST == O.NOAA_MINPEAKDIST
+    assert c.NOAA_PEAKHEIGHTWIGGLE == O.NOAA_PEAKHEIGHTWIGGLE
+    assert (c.FLT_LP, c.FLT_HP, c.FLT_BP, c.FLT_BS) == (0, 1, 2, 3)
+    assert c.CHUNK_FREQOFFSET == "freqoffset" and c.CHUNK_BWLIM == "bwlim"
+    assert c.IQ_FREQOFFSET == 30000 and c.NOAA_FMBW == 60000 and c.NOAA_CRUDESYNCSAMPRATE == 40960
+
+
+def test_argument_validation_needs_no_gpu():
+    """Errors are raised by the Python layer before anything touches the device."""
+    from directdemod_b200 import comm, constants, filters
+    with pytest.raises(ValueError):
+        comm.commSignal(-5, np.zeros(3))
+    with pytest.raises(TypeError):
+        comm.commSignal(10, np.zeros((2, 3)))
+    s = comm.commSignal(1000, np.zeros(8, dtype=np.complex64))
+    with pytest.raises(ValueError):
+        s.bwLim(2000)
+    with pytest.raises(TypeError):
+        comm.commSignal(1000, np.zeros(8)).offsetFreq(10.0)        # real signal, complex rotator
+    with pytest.raises(ValueError):
+        filters.butter(48000, 1000, typeFlt=constants.FLT_BS)
+    with pytest.raises(ValueError):
+        filters.remez(48000, [[0, 1000], [2000, 30000]], [1, 0])
+    f = filters.blackmanHarris(151)
+    assert f.isFIR and len(f.getB) == 151 and list(f.getA) == [1]
+    assert not filters.butter(48000, 1000).isFIR
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from directdemod_b200 import filters
+    from directdemod_b200.fused import FusedChain
+    with pytest.raises(RuntimeError):
+        FusedChain(np.ones(4), 2, 0.0, 1000.0)
+    with pytest.raises(RuntimeError):
+        filters.rollingAverage(3).applyOn(np.arange(10.0))
