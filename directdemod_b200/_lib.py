@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libddemod.so")
+LIB_PATH = os.environ.get("DDEMOD_LIB") or os.path.join(_HERE, "csrc", "libddemod.so")
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_UNSUPPORTED = -1, -2, -3, -4, -5

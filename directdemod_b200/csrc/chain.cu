@@ -33,7 +33,17 @@ namespace ddm {
 constexpr int kChainThreads = 128;   // blocks (threads) per tile
 constexpr int kChainMaxQ = 8;
 constexpr int kChainCtasPerSm = 2;
-constexpr int kChainStages = 2;      // TMA stages per CTA (3 stages drop occupancy to 1 CTA/SM: measured slower)
+#ifndef DDM_CHAIN_STAGES
+#define DDM_CHAIN_STAGES 2
+#endif
+#ifndef DDM_CHAIN_FFMA2
+#define DDM_CHAIN_FFMA2 1
+#endif
+constexpr int kChainStages = DDM_CHAIN_STAGES;   // TMA ring depth per CTA
+// with a 2-deep ring there is shared memory to double-buffer the partial-sum exchange (one
+// barrier per tile); the 3-deep ring single-buffers it (two barriers per tile)
+constexpr int kChainEBufs = kChainStages >= 3 ? 1 : 2;
+constexpr bool kChainPacked = DDM_CHAIN_FFMA2 != 0;
 
 struct ChainParams {
     const float2 *x;       // chunk, n samples
@@ -65,19 +75,27 @@ chain_fused_kernel(const ChainParams P) {
     // ---- shared memory carve-up ----
     constexpr int S = kChainStages;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);                 // S barriers (<= 4)
-    float *s_taps = reinterpret_cast<float *>(smem_raw + 32);                // Q*DP floats
-    float2 *s_rot = reinterpret_cast<float2 *>(s_taps + Q * DP);             // DP float2
-    float2 *s_e = s_rot + DP;                                                // 2*Q*NT float2
+    float *s_taps = reinterpret_cast<float *>(smem_raw + 32);                // Q*DP taps
+    float *s_rx = s_taps + Q * DP;                                           // DP: cos
+    float2 *s_ry = reinterpret_cast<float2 *>(s_rx + DP);                    // DP: (sin, -sin) = (-ry, ry)
+    float2 *s_e = s_ry + DP;                                                 // kChainEBufs*Q*NT float2
     const size_t stage_bytes = static_cast<size_t>(NT) * D * sizeof(float2);
-    unsigned char *s_stage0 = reinterpret_cast<unsigned char *>(
-        (reinterpret_cast<uintptr_t>(s_e + 2 * Q * NT) + 127) & ~static_cast<uintptr_t>(127));
+    // plain offset arithmetic from the (128-byte aligned) dynamic shared base keeps the pointer in
+    // the shared address space: the tile reads must be LDS, not generic loads
+    const unsigned fixed_bytes =
+        (32u + 4u * (Q * DP + DP) + 8u * (DP + kChainEBufs * Q * NT) + 127u) & ~127u;
+    unsigned char *s_stage0 = smem_raw + fixed_bytes;
 
     if (tid == 0) {
         for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
         fence_mbar_init();
     }
     for (int i = tid; i < Q * DP; i += NT) s_taps[i] = P.taps[i];
-    for (int i = tid; i < DP; i += NT) s_rot[i] = P.rot[i];
+    for (int i = tid; i < DP; i += NT) {
+        const float2 r = P.rot[i];          // (cos, -sin) = exp(-j 2 pi r a)
+        s_rx[i] = r.x;
+        s_ry[i] = make_float2(-r.y, r.y);
+    }
     __syncthreads();
 
     const long long n_even = P.n & ~1LL;
@@ -117,7 +135,6 @@ chain_fused_kernel(const ChainParams P) {
         }
     }
 
-    const int D4 = D & ~3;
     for (int it = 0; tile < P.num_tiles; tile += gridDim.x, ++it) {
         const int stage = it % S;
         const long long nxt = tile + static_cast<long long>(S - 1) * gridDim.x;
@@ -130,74 +147,77 @@ chain_fused_kernel(const ChainParams P) {
         mbar_wait(&mbar[stage], (it / S) & 1);
 
         const long long jblk = tile * J - Q + tid;          // this thread's block index
-        float2 *e_buf = s_e + (it & 1) * (Q * NT);
+        float2 *e_buf = s_e + (kChainEBufs == 2 ? (it & 1) * (Q * NT) : 0);
         if (jblk < P.M) {
             const unsigned char *sp = s_stage0 + stage * stage_bytes +
                                       static_cast<size_t>(tid) * D * sizeof(float2);
             const float4 *sp4 = reinterpret_cast<const float4 *>(sp);
-            const float4 *rot4 = reinterpret_cast<const float4 *>(s_rot);
-            float2 acc[Q];
+            // Packed single precision (FFMA2): accumulators are (re, im) pairs, a tap is a
+            // broadcast scalar operand, and the complex rotation is
+            //   m = x * cos + swap(x) * (sin, -sin)        (swap = the LO_HI operand selector)
+            // so a sample costs 2 + Q issue slots instead of 4 + 2Q.
+            unsigned long long acc[Q];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) acc[q] = make_float2(0.f, 0.f);
+            for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
 
+            auto rotate = [&](float xr, float xi, float rx, float2 ry) -> unsigned long long {
+                if (!MIX) return pack_f32x2(xr, xi);
+                const unsigned long long m = fmul2(pack_f32x2(xr, xi), pack_f32x2(rx, rx));
+                return ffma2(pack_f32x2(xi, xr), pack_f32x2(ry.x, ry.y), m);
+            };
+            const int D4 = D & ~3;
             int a = 0;
-#pragma unroll 2
+#pragma unroll 1
             for (; a < D4; a += 4) {
-                const float4 v0 = sp4[(a >> 1)], v1 = sp4[(a >> 1) + 1];
-                float2 m0, m1, m2, m3;
+                const float4 v0 = sp4[a >> 1], v1 = sp4[(a >> 1) + 1];
+                float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
+                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0;
                 if (MIX) {
-                    const float4 r0 = rot4[(a >> 1)], r1 = rot4[(a >> 1) + 1];
-                    m0 = cmul(make_float2(v0.x, v0.y), make_float2(r0.x, r0.y));
-                    m1 = cmul(make_float2(v0.z, v0.w), make_float2(r0.z, r0.w));
-                    m2 = cmul(make_float2(v1.x, v1.y), make_float2(r1.x, r1.y));
-                    m3 = cmul(make_float2(v1.z, v1.w), make_float2(r1.z, r1.w));
-                } else {
-                    m0 = make_float2(v0.x, v0.y);
-                    m1 = make_float2(v0.z, v0.w);
-                    m2 = make_float2(v1.x, v1.y);
-                    m3 = make_float2(v1.z, v1.w);
+                    rx = *reinterpret_cast<const float4 *>(s_rx + a);
+                    ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                    ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
                 }
+                const unsigned long long M0 = rotate(v0.x, v0.y, rx.x, make_float2(ry0.x, ry0.y));
+                const unsigned long long M1 = rotate(v0.z, v0.w, rx.y, make_float2(ry0.z, ry0.w));
+                const unsigned long long M2 = rotate(v1.x, v1.y, rx.z, make_float2(ry1.x, ry1.y));
+                const unsigned long long M3 = rotate(v1.z, v1.w, rx.w, make_float2(ry1.z, ry1.w));
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
-                    acc[q].x = fmaf(t.x, m0.x, acc[q].x);
-                    acc[q].y = fmaf(t.x, m0.y, acc[q].y);
-                    acc[q].x = fmaf(t.y, m1.x, acc[q].x);
-                    acc[q].y = fmaf(t.y, m1.y, acc[q].y);
-                    acc[q].x = fmaf(t.z, m2.x, acc[q].x);
-                    acc[q].y = fmaf(t.z, m2.y, acc[q].y);
-                    acc[q].x = fmaf(t.w, m3.x, acc[q].x);
-                    acc[q].y = fmaf(t.w, m3.y, acc[q].y);
+                    acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                    acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                    acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
+                    acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
                 }
             }
-            if (a < D) {                                    // D % 4 == 2
-                const float4 v0 = sp4[(a >> 1)];
-                float2 m0, m1;
+            if (a < D) {                                    // D % 4 == 2 (D is even on this path)
+                const float4 v0 = sp4[a >> 1];
+                float2 rx = make_float2(1.f, 1.f);
+                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (MIX) {
-                    const float4 r0 = rot4[(a >> 1)];
-                    m0 = cmul(make_float2(v0.x, v0.y), make_float2(r0.x, r0.y));
-                    m1 = cmul(make_float2(v0.z, v0.w), make_float2(r0.z, r0.w));
-                } else {
-                    m0 = make_float2(v0.x, v0.y);
-                    m1 = make_float2(v0.z, v0.w);
+                    rx = *reinterpret_cast<const float2 *>(s_rx + a);
+                    ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
                 }
+                const unsigned long long M0 = rotate(v0.x, v0.y, rx.x, make_float2(ry0.x, ry0.y));
+                const unsigned long long M1 = rotate(v0.z, v0.w, rx.y, make_float2(ry0.z, ry0.w));
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
-                    acc[q].x = fmaf(t.x, m0.x, acc[q].x);
-                    acc[q].y = fmaf(t.x, m0.y, acc[q].y);
-                    acc[q].x = fmaf(t.y, m1.x, acc[q].x);
-                    acc[q].y = fmaf(t.y, m1.y, acc[q].y);
+                    acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                    acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
                 }
             }
+            float2 w0 = make_float2(1.f, 0.f);
             if (MIX) {
                 const long long g = P.n0 + P.b0 + jblk * D;  // global index of the block start
-                const float2 w0 = phase_rotator(P.r_hi, P.r_lo, g);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) acc[q] = cmul(acc[q], w0);
+                w0 = phase_rotator(P.r_hi, P.r_lo, g);
             }
 #pragma unroll
-            for (int q = 0; q < Q; ++q) e_buf[q * NT + tid] = acc[q];
+            for (int q = 0; q < Q; ++q) {
+                float2 p = unpack_f32x2(acc[q]);
+                if (MIX) p = cmul(p, w0);
+                e_buf[q * NT + tid] = p;
+            }
         }
         __syncthreads();
 
@@ -226,6 +246,7 @@ chain_fused_kernel(const ChainParams P) {
                 reinterpret_cast<float *>(P.out)[m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
             }
         }
+        if (kChainEBufs == 1) __syncthreads();        // e_buf is reused by the next tile
     }
 }
 
@@ -314,10 +335,10 @@ namespace {
 using namespace ddm;
 
 size_t chain_smem_bytes(int Q, int D, int DP) {
-    size_t fixed = 32 + sizeof(float) * Q * DP + sizeof(float2) * DP +
-                   sizeof(float2) * 2 * Q * kChainThreads;
+    size_t fixed = 32 + sizeof(float) * (Q * DP + DP) + sizeof(float2) * DP +
+                   sizeof(float2) * kChainEBufs * Q * kChainThreads;
     fixed = (fixed + 127) & ~static_cast<size_t>(127);
-    return fixed + 128 + kChainStages * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
+    return fixed + kChainStages * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
 }
 
 template <int Q, bool MIX, int OUT>
