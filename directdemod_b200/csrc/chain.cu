@@ -21,9 +21,11 @@
 // into a shared-memory ring of kChainStages stages by the TMA engine with 1-D bulk copies
 // (cp.async.bulk, SASS UBLKCP) that signal an mbarrier; the first tile's copy is split
 // between the carried halo buffer and the chunk.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "ddm_common.cuh"
@@ -44,6 +46,10 @@ constexpr int kChainStages = DDM_CHAIN_STAGES;   // TMA ring depth per CTA
 // barrier per tile); the 3-deep ring single-buffers it (two barriers per tile)
 constexpr int kChainEBufs = kChainStages >= 3 ? 1 : 2;
 constexpr bool kChainPacked = DDM_CHAIN_FFMA2 != 0;
+#ifndef DDM_CHAIN_UNROLL
+#define DDM_CHAIN_UNROLL 4
+#endif
+constexpr int kChainUnroll = DDM_CHAIN_UNROLL;   // 4-sample bodies per loop trip
 
 struct ChainParams {
     const float2 *x;       // chunk, n samples
@@ -58,6 +64,7 @@ struct ChainParams {
     long long num_tiles;
     double r_hi, r_lo;
     int D, DP, H, s, has_prev;
+    int a_lastq;           // taps of the last partial sum are zero for a < a_lastq (multiple of 4)
 };
 
 // ------------------------------------------------------------------------------------
@@ -167,8 +174,9 @@ chain_fused_kernel(const ChainParams P) {
             };
             const int D4 = D & ~3;
             int a = 0;
-#pragma unroll 1
-            for (; a < D4; a += 4) {
+            // four samples against the first NQ partial sums
+            auto body4 = [&](auto nq_tag) {
+                constexpr int NQ = decltype(nq_tag)::value;
                 const float4 v0 = sp4[a >> 1], v1 = sp4[(a >> 1) + 1];
                 float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
                 float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0;
@@ -182,14 +190,21 @@ chain_fused_kernel(const ChainParams P) {
                 const unsigned long long M2 = rotate(v1.x, v1.y, rx.z, make_float2(ry1.x, ry1.y));
                 const unsigned long long M3 = rotate(v1.z, v1.w, rx.w, make_float2(ry1.z, ry1.w));
 #pragma unroll
-                for (int q = 0; q < Q; ++q) {
+                for (int q = 0; q < NQ; ++q) {
                     const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
                     acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
                     acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
                     acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
                     acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
                 }
+            };
+            // the last partial sum only sees the filter's tail: its taps are zero up to a_lastq
+            if (Q > 1) {
+#pragma unroll(kChainUnroll)
+                for (; a < P.a_lastq; a += 4) body4(std::integral_constant<int, (Q > 1 ? Q - 1 : 1)>());
             }
+#pragma unroll(kChainUnroll)
+            for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
             if (a < D) {                                    // D % 4 == 2 (D is even on this path)
                 const float4 v0 = sp4[a >> 1];
                 float2 rx = make_float2(1.f, 1.f);
@@ -315,6 +330,7 @@ struct ddm_chain {
     int has_prev = 0;
     int H = 0, DP = 0;
     int Q[2] = {0, 0};
+    int a_lastq[2] = {0, 0};
     int per_sm[2] = {0, 0};                  // resident CTAs per SM of the fused kernel, per s
     float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
     double *d_taps_lin = nullptr;            // K
@@ -507,6 +523,14 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
                     const int k = q * D + D - 1 - a - s;
                     if (k >= 0 && k < K) t[static_cast<size_t>(q) * c->DP + a] = static_cast<float>(taps[k]);
                 }
+            // first tap position (rounded down to the 4-sample body) the last partial sum needs
+            int first = D;
+            for (int a = 0; a < D; ++a)
+                if (t[static_cast<size_t>(Q - 1) * c->DP + a] != 0.f) {
+                    first = a;
+                    break;
+                }
+            c->a_lastq[s] = Q > 1 ? std::min(first & ~3, D & ~3) : 0;
             e = cudaMalloc(&c->d_taps[s], sizeof(float) * t.size());
             if (e == cudaSuccess)
                 e = cudaMemcpy(c->d_taps[s], t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice);
@@ -715,6 +739,7 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
             p.H = c->H;
             p.s = s;
             p.has_prev = c->has_prev;
+            p.a_lastq = c->a_lastq[s];
             int rc = launch_fused(c, Q, p, st);
             if (rc != DDM_OK) return rc;
         } else {
