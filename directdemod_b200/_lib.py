@@ -29,6 +29,7 @@ SIGNATURES = {
     "ddm_last_error": (C.c_char_p, []),
     "ddm_launch_count": (_i64, []),
     "ddm_device_count": (_int, [_pint]),
+    "ddm_release_scratch": (_int, [_int]),
     "ddm_chain_create": (_int, [_int, _pdbl, _int, _int, _dbl, _dbl, _int, _int,
                                 C.POINTER(_vp)]),
     "ddm_chain_destroy": (_int, [_vp]),

@@ -20,6 +20,50 @@ void set_error(const char *fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Per-device scratch pool for the operators that need temporary device memory (correlation
+// prefix sums, selection histograms, compaction offsets).  Slots grow on demand and are kept, so
+// steady-state calls do no cudaMalloc/cudaFree.  Calls that use the pool must be serialised per
+// device by the caller (the same rule as for handles).
+namespace {
+constexpr int kScratchSlots = 8;
+constexpr int kScratchDevices = 64;
+struct ScratchSlot {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+ScratchSlot g_scratch[kScratchDevices][kScratchSlots];
+std::mutex g_scratch_mu;
+}  // namespace
+
+void *scratch_get(int device, int slot, size_t bytes) {
+    if (device < 0 || device >= kScratchDevices || slot < 0 || slot >= kScratchSlots) return nullptr;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    ScratchSlot &s = g_scratch[device][slot];
+    if (bytes <= s.cap && s.p) return s.p;
+    if (s.p) cudaFree(s.p);           // implicit device synchronisation
+    s.p = nullptr;
+    s.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&s.p, want) != cudaSuccess) {
+        cudaGetLastError();
+        s.p = nullptr;
+        set_error("scratch allocation of %zu bytes failed on device %d", want, device);
+        return nullptr;
+    }
+    s.cap = want;
+    return s.p;
+}
+
+void scratch_release(int device) {
+    if (device < 0 || device >= kScratchDevices) return;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (ScratchSlot &s : g_scratch[device]) {
+        if (s.p) cudaFree(s.p);
+        s.p = nullptr;
+        s.cap = 0;
+    }
+}
+
 int sm_count(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
@@ -36,6 +80,15 @@ int ddm_version(void) { return 100; }   // 0.1.0
 const char *ddm_last_error(void) { return ddm::g_last_error.c_str(); }
 
 int64_t ddm_launch_count(void) { return ddm::g_launches.load(std::memory_order_relaxed); }
+
+int ddm_release_scratch(int device) {
+    int ndev = 0;
+    DDM_CUDA(cudaGetDeviceCount(&ndev));
+    DDM_REQUIRE(device >= 0 && device < ndev, "ddm_release_scratch: no such device %d", device);
+    ddm::DeviceGuard guard(device);
+    ddm::scratch_release(device);
+    return DDM_OK;
+}
 
 int ddm_device_count(int *count) {
     DDM_REQUIRE(count != nullptr, "ddm_device_count: NULL argument");

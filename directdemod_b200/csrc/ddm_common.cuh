@@ -47,6 +47,8 @@ struct DeviceGuard {
 };
 
 int sm_count(int device);
+void *scratch_get(int device, int slot, size_t bytes);   // nullptr (+ error message) on failure
+void scratch_release(int device);
 
 // ---- device-side primitives ------------------------------------------------------------
 #ifdef __CUDACC__

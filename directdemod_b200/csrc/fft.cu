@@ -5,12 +5,13 @@
 //   ddm_resample     scipy.signal.resample(x, num)             comm.py:110-116 (strict bwLim),
 //                                                              decode_noaa.py:350-351
 //
-// Both are *circular*, length-dependent operations on lengths that are not powers of two
-// (240 000 = 2^7 3 5^4 for the AM chunks, arbitrary for resample), so the transform is a
-// Bluestein chirp-z: a length-n DFT as a circular convolution of length m = 2^k >= 2n-1,
-// evaluated with batched power-of-two Stockham radix-4 passes (twiddles from a float64 table,
-// chirp phases k^2 mod 2n in exact integer arithmetic).  Independent chunks are the batch
-// dimension: one launch per pass covers every chunk of a pass over a whole capture.
+// Both are *circular*, length-dependent operations on lengths that are not powers of two.
+// 2-3-5 smooth lengths (240 000 = 2^7 3 5^4, the AM chunk of decode_noaa.py:647) are transformed
+// directly by batched mixed-radix Stockham passes (radix 16/8/4/2, 25/5, 3 butterflies in
+// registers, float64, twiddles from a float64 table); any other length (resample: 588 235 =
+// 5 71 1657) is a Bluestein chirp-z over a power-of-two engine of the same passes (chirp phases
+// k^2 mod 2n in exact integer arithmetic).  Independent chunks are the batch dimension: one
+// launch per pass covers every chunk of a pass over a whole capture.
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -53,63 +54,164 @@ __global__ void fft_chirp_kernel(double2 *w, double2 *b, long long n, int m) {
     }
 }
 
-// one Stockham radix-4 pass over `batch` rows of length m (grid.y = row)
+// ---- small DFTs in registers -------------------------------------------------------------
+// DIR = +1: forward (exp(-i...)), DIR = -1: inverse (exp(+i...)), unnormalised.
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
 template <int DIR>
-__global__ void fft_pass_r4(const double2 *__restrict__ in, double2 *__restrict__ out,
-                            const double2 *__restrict__ tw, int m, int Ns) {
-    const int q = m >> 2;
+__device__ __forceinline__ double2 mul_mi(double2 a) {
+    return DIR > 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+// w = (c, s) with s the FORWARD sine; conjugated for the inverse
+template <int DIR>
+__device__ __forceinline__ double2 cmul_w(double2 a, double c, double s) {
+    const double ss = DIR > 0 ? s : -s;
+    return make_double2(fma(a.x, c, -a.y * ss), fma(a.x, ss, a.y * c));
+}
+
+template <int R, int DIR>
+struct SmallDft;
+
+template <int DIR>
+struct SmallDft<2, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[2]) {
+        const double2 a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <int DIR>
+struct SmallDft<3, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[3]) {
+        const double s3 = 0.86602540378443864676;    // sin(2 pi / 3)
+        const double2 t = cadd(v[1], v[2]);
+        const double2 d = mul_mi<DIR>(csub(v[1], v[2]));       // -i (v1 - v2) forward
+        const double2 m = make_double2(v[0].x - 0.5 * t.x, v[0].y - 0.5 * t.y);
+        v[0] = cadd(v[0], t);
+        v[1] = make_double2(m.x + s3 * d.x, m.y + s3 * d.y);
+        v[2] = make_double2(m.x - s3 * d.x, m.y - s3 * d.y);
+    }
+};
+
+template <int DIR>
+struct SmallDft<4, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[4]) {
+        const double2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+        const double2 a2 = cadd(v[1], v[3]), a3 = mul_mi<DIR>(csub(v[1], v[3]));
+        v[0] = cadd(a0, a2);
+        v[1] = cadd(a1, a3);
+        v[2] = csub(a0, a2);
+        v[3] = csub(a1, a3);
+    }
+};
+
+template <int DIR>
+struct SmallDft<5, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[5]) {
+        const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;   // cos(2pi/5), cos(4pi/5)
+        const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;    // sin(2pi/5), sin(4pi/5)
+        const double2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        const double2 d1 = mul_mi<DIR>(csub(v[1], v[4])), d2 = mul_mi<DIR>(csub(v[2], v[3]));
+        const double2 x0 = v[0];
+        v[0] = make_double2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+        const double2 m1 = make_double2(x0.x + c1 * t1.x + c2 * t2.x, x0.y + c1 * t1.y + c2 * t2.y);
+        const double2 m2 = make_double2(x0.x + c2 * t1.x + c1 * t2.x, x0.y + c2 * t1.y + c1 * t2.y);
+        const double2 n1 = make_double2(s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y);
+        const double2 n2 = make_double2(s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y);
+        v[1] = cadd(m1, n1);
+        v[4] = csub(m1, n1);
+        v[2] = cadd(m2, n2);
+        v[3] = csub(m2, n2);
+    }
+};
+
+// composite sizes by one Cooley-Tukey step in registers: R = R1 * R2, input n = R2 n1 + n2,
+// output k = k1 + R1 k2; inner twiddles exp(-2 pi i n2 k1 / R) from a constant table
+__constant__ double2 c_tw8[8], c_tw16[16], c_tw25[25];
+
+template <int R>
+__device__ __forceinline__ double2 small_tw(int idx);
+template <>
+__device__ __forceinline__ double2 small_tw<8>(int idx) { return c_tw8[idx]; }
+template <>
+__device__ __forceinline__ double2 small_tw<16>(int idx) { return c_tw16[idx]; }
+template <>
+__device__ __forceinline__ double2 small_tw<25>(int idx) { return c_tw25[idx]; }
+
+template <int R, int R1, int R2, int DIR>
+__device__ __forceinline__ void composite_dft(double2 (&v)[R]) {
+    double2 a[R1][R2];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+        double2 col[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) col[n1] = v[R2 * n1 + n2];
+        SmallDft<R1, DIR>::run(col);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            double2 x = col[k1];
+            if (n2 * k1 != 0) {
+                const double2 w = small_tw<R>((n2 * k1) % R);
+                x = cmul_w<DIR>(x, w.x, w.y);
+            }
+            a[k1][n2] = x;
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+        double2 row[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) row[n2] = a[k1][n2];
+        SmallDft<R2, DIR>::run(row);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = row[k2];
+    }
+}
+
+template <int DIR>
+struct SmallDft<8, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[8]) { composite_dft<8, 2, 4, DIR>(v); }
+};
+template <int DIR>
+struct SmallDft<16, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[16]) { composite_dft<16, 4, 4, DIR>(v); }
+};
+template <int DIR>
+struct SmallDft<25, DIR> {
+    __device__ static __forceinline__ void run(double2 (&v)[25]) { composite_dft<25, 5, 5, DIR>(v); }
+};
+
+// one Stockham radix-R pass over `batch` rows of length m (grid.y = row):
+//   v[r] = in[j + r m/R] * w^(r k),  k = j mod Ns,  w = exp(-+2 pi i / (Ns R));  DFT_R;
+//   out[(j - k) R + k + r Ns] = v[r]
+template <int R, int DIR>
+__global__ void __launch_bounds__(R >= 16 ? 128 : 256)
+fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw, int m,
+         int Ns) {
+    const int q = m / R;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= q) return;
     const size_t row = static_cast<size_t>(blockIdx.y) * m;
     in += row;
     out += row;
-    const int k = j & (Ns - 1);
-    const int step = q / Ns;                 // m / (4 Ns)
-    double2 v0 = in[j], v1 = in[j + q], v2 = in[j + 2 * q], v3 = in[j + 3 * q];
+    const int k = j % Ns;
+    const int step = q / Ns;                 // m / (R Ns)
+    double2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in[j + r * q];
     if (k != 0) {
-        double2 t1 = tw[k * step], t2 = tw[2 * k * step], t3 = tw[3 * k * step];
-        if (DIR < 0) {
-            t1 = conjd(t1);
-            t2 = conjd(t2);
-            t3 = conjd(t3);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const double2 t = tw[static_cast<size_t>(k) * step * r];
+            v[r] = cmul_w<DIR>(v[r], t.x, t.y);
         }
-        v1 = cmuld(v1, t1);
-        v2 = cmuld(v2, t2);
-        v3 = cmuld(v3, t3);
     }
-    const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y);
-    const double2 a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
-    const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
-    const double2 d = make_double2(v1.x - v3.x, v1.y - v3.y);
-    // forward: a3 = -i d ; inverse: a3 = +i d
-    const double2 a3 = DIR > 0 ? make_double2(d.y, -d.x) : make_double2(-d.y, d.x);
-    const int j0 = ((j - k) << 2) + k;
-    out[j0] = make_double2(a0.x + a2.x, a0.y + a2.y);
-    out[j0 + Ns] = make_double2(a1.x + a3.x, a1.y + a3.y);
-    out[j0 + 2 * Ns] = make_double2(a0.x - a2.x, a0.y - a2.y);
-    out[j0 + 3 * Ns] = make_double2(a1.x - a3.x, a1.y - a3.y);
-}
-
-template <int DIR>
-__global__ void fft_pass_r2(const double2 *__restrict__ in, double2 *__restrict__ out,
-                            const double2 *__restrict__ tw, int m, int Ns) {
-    const int h = m >> 1;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= h) return;
-    const size_t row = static_cast<size_t>(blockIdx.y) * m;
-    in += row;
-    out += row;
-    const int k = j & (Ns - 1);
-    const int step = h / Ns;
-    double2 v0 = in[j], v1 = in[j + h];
-    if (k != 0) {
-        double2 t = tw[k * step];
-        if (DIR < 0) t = conjd(t);
-        v1 = cmuld(v1, t);
-    }
-    const int j0 = ((j - k) << 1) + k;
-    out[j0] = make_double2(v0.x + v1.x, v0.y + v1.y);
-    out[j0 + Ns] = make_double2(v0.x - v1.x, v0.y - v1.y);
+    SmallDft<R, DIR>::run(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) out[j0 + r * Ns] = v[r];
 }
 
 // buf[row][k] *= bfft[k]
@@ -265,7 +367,8 @@ using namespace ddm;
 struct FftPlan {
     long long n = 0;
     int m = 0;              // transform size of the power-of-two engine
-    bool pow2 = false;      // n itself is a power of two: no chirp
+    bool pow2 = false;      // n itself is 2-3-5 smooth: transformed directly, no chirp
+    std::vector<int> radices;   // Stockham pass radices of the size-m engine
     double2 *d_tw = nullptr;
     double2 *d_w = nullptr;
     double2 *d_bfft = nullptr;
@@ -288,28 +391,69 @@ int ilog2(long long v) {
     return l;
 }
 
-// batched power-of-two FFT, rows of length m in buf[cur]; returns the index of the buffer
-// holding the result
+// radices of a 2-3-5 smooth length (largest butterflies first); empty if n is not smooth
+std::vector<int> smooth_radices(long long n) {
+    std::vector<int> r;
+    int e2 = 0, e3 = 0, e5 = 0;
+    while (n % 2 == 0) { n /= 2; ++e2; }
+    while (n % 3 == 0) { n /= 3; ++e3; }
+    while (n % 5 == 0) { n /= 5; ++e5; }
+    if (n != 1) return r;
+    while (e2 >= 4) { r.push_back(16); e2 -= 4; }
+    if (e2 == 3) r.push_back(8);
+    if (e2 == 2) r.push_back(4);
+    if (e2 == 1) r.push_back(2);
+    while (e5 >= 2) { r.push_back(25); e5 -= 2; }
+    if (e5 == 1) r.push_back(5);
+    while (e3 >= 1) { r.push_back(3); --e3; }
+    return r;
+}
+
+template <int R, int DIR>
+void launch_pass(double2 *in, double2 *out, const double2 *tw, int m, int Ns, int batch, cudaStream_t st) {
+    const int threads = R >= 16 ? 128 : 256;
+    const dim3 grid((m / R + threads - 1) / threads, batch);
+    fft_pass<R, DIR><<<grid, threads, 0, st>>>(in, out, tw, m, Ns);
+    count_launch();
+}
+
+// batched FFT of a 2-3-5 smooth size m, rows in bufs[cur]; returns the index of the buffer holding
+// the result
 template <int DIR>
-int pow2_fft(double2 *bufs[2], int cur, const double2 *tw, int m, int batch, cudaStream_t st) {
+int pow2_fft(double2 *bufs[2], int cur, const double2 *tw, int m, int batch, cudaStream_t st,
+             const std::vector<int> &radices) {
     int Ns = 1;
-    const int lg = ilog2(m);
-    int left = lg;
-    while (left >= 2) {
-        const dim3 grid((m / 4 + kFftThreads - 1) / kFftThreads, batch);
-        fft_pass_r4<DIR><<<grid, kFftThreads, 0, st>>>(bufs[cur], bufs[cur ^ 1], tw, m, Ns);
-        count_launch();
+    for (int R : radices) {
+        double2 *in = bufs[cur], *out = bufs[cur ^ 1];
+        switch (R) {
+            case 2: launch_pass<2, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 3: launch_pass<3, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 4: launch_pass<4, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 5: launch_pass<5, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 8: launch_pass<8, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 16: launch_pass<16, DIR>(in, out, tw, m, Ns, batch, st); break;
+            case 25: launch_pass<25, DIR>(in, out, tw, m, Ns, batch, st); break;
+        }
         cur ^= 1;
-        Ns <<= 2;
-        left -= 2;
-    }
-    if (left == 1) {
-        const dim3 grid((m / 2 + kFftThreads - 1) / kFftThreads, batch);
-        fft_pass_r2<DIR><<<grid, kFftThreads, 0, st>>>(bufs[cur], bufs[cur ^ 1], tw, m, Ns);
-        count_launch();
-        cur ^= 1;
+        Ns *= R;
     }
     return cur;
+}
+
+int upload_small_twiddles() {
+    static bool done[64] = {false};
+    int dev = 0;
+    DDM_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return DDM_OK;
+    double2 t8[8], t16[16], t25[25];
+    for (int i = 0; i < 8; ++i) t8[i] = make_double2(std::cos(2.0 * M_PI * i / 8), -std::sin(2.0 * M_PI * i / 8));
+    for (int i = 0; i < 16; ++i) t16[i] = make_double2(std::cos(2.0 * M_PI * i / 16), -std::sin(2.0 * M_PI * i / 16));
+    for (int i = 0; i < 25; ++i) t25[i] = make_double2(std::cos(2.0 * M_PI * i / 25), -std::sin(2.0 * M_PI * i / 25));
+    DDM_CUDA(cudaMemcpyToSymbol(c_tw8, t8, sizeof(t8)));
+    DDM_CUDA(cudaMemcpyToSymbol(c_tw16, t16, sizeof(t16)));
+    DDM_CUDA(cudaMemcpyToSymbol(c_tw25, t25, sizeof(t25)));
+    if (dev < 64) done[dev] = true;
+    return DDM_OK;
 }
 
 int ensure_ws(ddm_fft *c, size_t elems, cudaStream_t st) {
@@ -350,8 +494,12 @@ int get_plan(ddm_fft *c, long long n, cudaStream_t st, FftPlan **out) {
     }
     FftPlan p;
     p.n = n;
-    p.pow2 = (n & (n - 1)) == 0;
+    int rc0 = upload_small_twiddles();
+    if (rc0 != DDM_OK) return rc0;
+    p.radices = smooth_radices(n);
+    p.pow2 = !p.radices.empty() || n == 1;
     p.m = p.pow2 ? static_cast<int>(n) : (1 << ilog2(2 * n - 1));
+    if (!p.pow2) p.radices = smooth_radices(p.m);
     DDM_CUDA(cudaMalloc(&p.d_tw, sizeof(double2) * p.m));
     fft_twiddle_kernel<<<(p.m + 255) / 256, 256, 0, st>>>(p.d_tw, p.m);
     count_launch();
@@ -362,7 +510,7 @@ int get_plan(ddm_fft *c, long long n, cudaStream_t st, FftPlan **out) {
         if (rc != DDM_OK) return rc;
         fft_chirp_kernel<<<(p.m + 255) / 256, 256, 0, st>>>(p.d_w, c->d_ws[0], n, p.m);
         count_launch();
-        const int r = pow2_fft<1>(c->d_ws, 0, p.d_tw, p.m, 1, st);
+        const int r = pow2_fft<1>(c->d_ws, 0, p.d_tw, p.m, 1, st, p.radices);
         DDM_CUDA(cudaMemcpyAsync(p.d_bfft, c->d_ws[r], sizeof(double2) * p.m, cudaMemcpyDeviceToDevice, st));
     }
     DDM_CUDA(cudaGetLastError());
@@ -385,8 +533,8 @@ int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int 
         const dim3 g((n + kFftThreads - 1) / kFftThreads, batch);
         fft_load_plain_kernel<KIND><<<g, kFftThreads, 0, st>>>(src, src_stride, n, c->d_ws[0]);
         count_launch();
-        const int r = INVERSE ? pow2_fft<-1>(c->d_ws, 0, p->d_tw, m, batch, st)
-                              : pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st);
+        const int r = INVERSE ? pow2_fft<-1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices)
+                              : pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices);
         // copy out with scale (no chirp on the power-of-two path)
         blu_finish_kernel<false><<<g, kFftThreads, 0, st>>>(c->d_ws[r], m, n, nullptr, scale, dst, dst_stride);
         count_launch();
@@ -397,10 +545,10 @@ int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int 
     const dim3 gn((n + kFftThreads - 1) / kFftThreads, batch);
     blu_load_kernel<KIND, INVERSE><<<gm, kFftThreads, 0, st>>>(src, src_stride, n, p->d_w, c->d_ws[0], m);
     count_launch();
-    int r = pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st);
+    int r = pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices);
     fft_pointwise_kernel<<<gm, kFftThreads, 0, st>>>(c->d_ws[r], p->d_bfft, m);
     count_launch();
-    r = pow2_fft<-1>(c->d_ws, r, p->d_tw, m, batch, st);
+    r = pow2_fft<-1>(c->d_ws, r, p->d_tw, m, batch, st, p->radices);
     blu_finish_kernel<INVERSE><<<gn, kFftThreads, 0, st>>>(c->d_ws[r], m, n, p->d_w,
                                                            scale / static_cast<double>(m), dst, dst_stride);
     count_launch();

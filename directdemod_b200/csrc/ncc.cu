@@ -128,6 +128,81 @@ __global__ void ncc_runs_kernel(const double *__restrict__ L1, const double *__r
     }
 }
 
+// Short needles (M <= kNccTileMaxM): everything in one kernel, no global prefix arrays.  A CTA
+// stages the window its `tile` outputs look at, turns it into exclusive prefix sums of h and h^2
+// in shared memory (window-local, so a range sum is ONE subtraction of small numbers), and
+// evaluates the run-length correlation from shared memory.  HBM traffic: ~(1 + M/tile) x 4 B read
+// + 8 B written per output.
+constexpr int kNccTileThreads = 256;
+constexpr int kNccTile = 2048;
+constexpr int kNccTileMaxM = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(kNccTileThreads)
+ncc_tile_kernel(const T *__restrict__ h, long long n, int M, double needle_energy, int normalised,
+                const NeedleRuns runs, double *__restrict__ out) {
+    extern __shared__ double ncc_sm[];
+    const int win = kNccTile + M;
+    double *P1 = ncc_sm;                       // win + 1
+    double *P2 = P1 + (win + 1);               // win + 1
+    double *S1 = P2 + (win + 1);               // kNccTileThreads
+    double *S2 = S1 + kNccTileThreads;         // kNccTileThreads
+    const int tid = threadIdx.x;
+    const long long i0 = static_cast<long long>(blockIdx.x) * kNccTile;
+    const long long base = i0 - M / 2;         // global index of window position 0
+    for (int j = tid; j < win; j += kNccTileThreads) {
+        const long long g = base + j;
+        P1[j] = (g >= 0 && g < n) ? to_double(h[g]) : 0.0;
+    }
+    __syncthreads();
+    const int per = (win + kNccTileThreads - 1) / kNccTileThreads;
+    const int j0 = tid * per;
+    const int j1 = min(j0 + per, win);
+    double a1 = 0.0, a2 = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const double v = P1[j];
+        a1 += v;
+        a2 = fma(v, v, a2);
+    }
+    S1[tid] = a1;
+    S2[tid] = a2;
+    __syncthreads();
+    for (int off = 1; off < kNccTileThreads; off <<= 1) {
+        double b1 = 0.0, b2 = 0.0;
+        if (tid >= off) {
+            b1 = S1[tid - off];
+            b2 = S2[tid - off];
+        }
+        __syncthreads();
+        S1[tid] += b1;
+        S2[tid] += b2;
+        __syncthreads();
+    }
+    double p1 = tid > 0 ? S1[tid - 1] : 0.0;
+    double p2 = tid > 0 ? S2[tid - 1] : 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const double v = P1[j];
+        P1[j] = p1;
+        P2[j] = p2;
+        p1 += v;
+        p2 = fma(v, v, p2);
+    }
+    if (j1 == win && j0 < win) {
+        P1[win] = p1;
+        P2[win] = p2;
+    }
+    __syncthreads();
+    for (int t = tid; t < kNccTile; t += kNccTileThreads) {
+        const long long i = i0 + t;
+        if (i >= n) break;
+        double cor = 0.0;
+        for (int r = 0; r < runs.count; ++r)
+            cor = fma(runs.value[r], P1[t + runs.end[r]] - P1[t + runs.start[r]], cor);
+        if (normalised) out[i] = cor / sqrt((P2[t + M] - P2[t]) * needle_energy);
+        else out[i] = cor;
+    }
+}
+
 // direct form for arbitrary needles: one output per thread, needle from global (L1-resident)
 template <typename T>
 __global__ void ncc_direct_kernel(const T *__restrict__ h, long long n, const double *__restrict__ needle,
@@ -153,52 +228,68 @@ __device__ __forceinline__ unsigned long long f64_key(double v) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
 }
 
-// histogram of byte `shift/8` over the elements whose higher bytes equal `prefix`
-__global__ void select_hist_kernel(const double *__restrict__ x, long long n, unsigned long long prefix,
-                                   int shift, unsigned int *__restrict__ hist) {
-    __shared__ unsigned int sh[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+// histograms of byte `shift/8` over the elements whose higher bytes equal the given prefixes:
+// one read of the array serves the search for the k-th largest (hist[0..255], prefix_top) and
+// the k-th smallest (hist[256..511], prefix_bot)
+__global__ void select_hist2_kernel(const double *__restrict__ x, long long n, unsigned long long prefix_top,
+                                    unsigned long long prefix_bot, int shift, unsigned int *__restrict__ hist) {
+    __shared__ unsigned int sh[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const unsigned long long himask = shift >= 56 ? 0ULL : (~0ULL << (shift + 8));
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
         const unsigned long long k = f64_key(x[i]);
-        if ((k & himask) == prefix) atomicAdd(&sh[(k >> shift) & 255], 1u);
+        const unsigned long long hi = k & himask;
+        const unsigned int d = static_cast<unsigned int>((k >> shift) & 255);
+        if (hi == prefix_top) atomicAdd(&sh[d], 1u);
+        if (hi == prefix_bot) atomicAdd(&sh[256 + d], 1u);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    for (int i = threadIdx.x; i < 512; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-// per-block partial sums of the values strictly above / below a key, with their counts
-__global__ void select_sum_kernel(const double *__restrict__ x, long long n, unsigned long long key, int above,
-                                  double *__restrict__ part_sum, unsigned long long *__restrict__ part_cnt) {
-    __shared__ double ss[256];
-    __shared__ unsigned long long sc[256];
-    double s = 0.0;
-    unsigned long long c = 0;
+// per-block partial sums (and counts) of the values strictly above key_top and strictly below key_bot
+__global__ void select_sum2_kernel(const double *__restrict__ x, long long n, unsigned long long key_top,
+                                   unsigned long long key_bot, double *__restrict__ part_sum,
+                                   unsigned long long *__restrict__ part_cnt) {
+    __shared__ double ss[2][256];
+    __shared__ unsigned long long sc[2][256];
+    double s0 = 0.0, s1 = 0.0;
+    unsigned long long c0 = 0, c1 = 0;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
         const double v = x[i];
         const unsigned long long k = f64_key(v);
-        if (above ? k > key : k < key) {
-            s += v;
-            ++c;
+        if (k > key_top) {
+            s0 += v;
+            ++c0;
+        }
+        if (k < key_bot) {
+            s1 += v;
+            ++c1;
         }
     }
-    ss[threadIdx.x] = s;
-    sc[threadIdx.x] = c;
+    ss[0][threadIdx.x] = s0;
+    ss[1][threadIdx.x] = s1;
+    sc[0][threadIdx.x] = c0;
+    sc[1][threadIdx.x] = c1;
     __syncthreads();
     for (int off = blockDim.x / 2; off > 0; off >>= 1) {
         if (threadIdx.x < off) {
-            ss[threadIdx.x] += ss[threadIdx.x + off];
-            sc[threadIdx.x] += sc[threadIdx.x + off];
+            ss[0][threadIdx.x] += ss[0][threadIdx.x + off];
+            ss[1][threadIdx.x] += ss[1][threadIdx.x + off];
+            sc[0][threadIdx.x] += sc[0][threadIdx.x + off];
+            sc[1][threadIdx.x] += sc[1][threadIdx.x + off];
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        part_sum[blockIdx.x] = ss[0];
-        part_cnt[blockIdx.x] = sc[0];
+        part_sum[2 * blockIdx.x] = ss[0][0];
+        part_sum[2 * blockIdx.x + 1] = ss[1][0];
+        part_cnt[2 * blockIdx.x] = sc[0][0];
+        part_cnt[2 * blockIdx.x + 1] = sc[1][0];
     }
 }
 
@@ -297,12 +388,12 @@ int check_device(int device, const char *who) {
     return DDM_OK;
 }
 
+// a slot of the per-device scratch pool (capi.cu); nothing to free
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    int alloc(size_t bytes) {
-        DDM_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
-        return DDM_OK;
+    int alloc(int device, int slot, size_t bytes) {
+        p = scratch_get(device, slot, bytes ? bytes : 1);
+        return p ? DDM_OK : DDM_ERR_NOMEM;
     }
 };
 
@@ -342,13 +433,29 @@ int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, co
         k = e;
     }
     double *out = static_cast<double *>(out_f64_dev);
+    if (compressible && runs.count * 8 <= m && m <= kNccTileMaxM) {
+        const size_t smem = sizeof(double) * (2 * (static_cast<size_t>(kNccTile) + m + 1) + 2 * kNccTileThreads);
+        const unsigned grid = static_cast<unsigned>((n + kNccTile - 1) / kNccTile);
+        if (hay_is_f64) {
+            DDM_CUDA(cudaFuncSetAttribute(ncc_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            ncc_tile_kernel<double><<<grid, kNccTileThreads, smem, st>>>(static_cast<const double *>(hay_dev), n, m, energy,
+                                                                         normalised, runs, out);
+        } else {
+            DDM_CUDA(cudaFuncSetAttribute(ncc_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            ncc_tile_kernel<float><<<grid, kNccTileThreads, smem, st>>>(static_cast<const float *>(hay_dev), n, m, energy,
+                                                                        normalised, runs, out);
+        }
+        count_launch();
+        DDM_CUDA(cudaGetLastError());
+        return DDM_OK;
+    }
     if (compressible && runs.count * 8 <= m) {
         const long long nblk = n / kPfxBlock + 1;
         DevBuf L1, L2, T1, T2;
-        if ((rc = L1.alloc(sizeof(double) * (n + 1))) != DDM_OK) return rc;
-        if ((rc = L2.alloc(sizeof(double) * (n + 1))) != DDM_OK) return rc;
-        if ((rc = T1.alloc(sizeof(double) * nblk)) != DDM_OK) return rc;
-        if ((rc = T2.alloc(sizeof(double) * nblk)) != DDM_OK) return rc;
+        if ((rc = L1.alloc(device, 0, sizeof(double) * (n + 1))) != DDM_OK) return rc;
+        if ((rc = L2.alloc(device, 1, sizeof(double) * (n + 1))) != DDM_OK) return rc;
+        if ((rc = T1.alloc(device, 2, sizeof(double) * nblk)) != DDM_OK) return rc;
+        if ((rc = T2.alloc(device, 3, sizeof(double) * nblk)) != DDM_OK) return rc;
         if (hay_is_f64)
             block_prefix_kernel<double><<<static_cast<unsigned>(nblk), kPfxThreads, 0, st>>>(
                 static_cast<const double *>(hay_dev), n, static_cast<double *>(L1.p), static_cast<double *>(L2.p),
@@ -364,12 +471,12 @@ int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, co
                                              n, m, energy, normalised, runs, out);
         count_launch(2);
         DDM_CUDA(cudaGetLastError());
-        DDM_CUDA(cudaStreamSynchronize(st));      // the scratch buffers die with this scope
         return DDM_OK;
     }
     DevBuf nd;
-    if ((rc = nd.alloc(sizeof(double) * m)) != DDM_OK) return rc;
+    if ((rc = nd.alloc(device, 0, sizeof(double) * m)) != DDM_OK) return rc;
     DDM_CUDA(cudaMemcpyAsync(nd.p, needle_host, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    DDM_CUDA(cudaStreamSynchronize(st));          // needle_host may be reused by the caller
     const unsigned grid = static_cast<unsigned>((n + 255) / 256);
     if (hay_is_f64)
         ncc_direct_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(hay_dev), n,
@@ -379,7 +486,6 @@ int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, co
                                                        static_cast<const double *>(nd.p), m, energy, normalised, out);
     count_launch();
     DDM_CUDA(cudaGetLastError());
-    DDM_CUDA(cudaStreamSynchronize(st));
     return DDM_OK;
 }
 
@@ -395,55 +501,58 @@ int ddm_topk_sums(int device, const void *x_f64_dev, int64_t n, int64_t k, doubl
     const double *x = static_cast<const double *>(x_f64_dev);
     const unsigned grid = static_cast<unsigned>(std::min<long long>((n + 255) / 256, static_cast<long long>(sm_count(device)) * 8));
     DevBuf hist, psum, pcnt;
-    if ((rc = hist.alloc(sizeof(unsigned int) * 256)) != DDM_OK) return rc;
-    if ((rc = psum.alloc(sizeof(double) * grid)) != DDM_OK) return rc;
-    if ((rc = pcnt.alloc(sizeof(unsigned long long) * grid)) != DDM_OK) return rc;
-    std::vector<unsigned int> h(256);
-    std::vector<double> hs(grid);
-    std::vector<unsigned long long> hc(grid);
-    for (int which = 0; which < 2; ++which) {
-        const bool top = which == 0;
-        double *result = top ? sum_top : sum_bottom;
-        if (!result) continue;
-        // find the key of the k-th largest (top) / k-th smallest (bottom) element
-        unsigned long long prefix = 0;
-        long long remaining = k;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            DDM_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned int) * 256, st));
-            select_hist_kernel<<<grid, 256, 0, st>>>(x, n, prefix, shift, static_cast<unsigned int *>(hist.p));
-            count_launch();
-            DDM_CUDA(cudaMemcpyAsync(h.data(), hist.p, sizeof(unsigned int) * 256, cudaMemcpyDeviceToHost, st));
-            DDM_CUDA(cudaStreamSynchronize(st));
+    if ((rc = hist.alloc(device, 4, sizeof(unsigned int) * 512)) != DDM_OK) return rc;
+    if ((rc = psum.alloc(device, 5, sizeof(double) * 2 * grid)) != DDM_OK) return rc;
+    if ((rc = pcnt.alloc(device, 6, sizeof(unsigned long long) * 2 * grid)) != DDM_OK) return rc;
+    std::vector<unsigned int> h(512);
+    // keys of the k-th largest and the k-th smallest element, one digit (byte) per pass, both
+    // searches served by the same read of the array
+    unsigned long long prefix[2] = {0, 0};
+    long long remaining[2] = {static_cast<long long>(k), static_cast<long long>(k)};
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        DDM_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned int) * 512, st));
+        select_hist2_kernel<<<grid, 256, 0, st>>>(x, n, prefix[0], prefix[1], shift, static_cast<unsigned int *>(hist.p));
+        count_launch();
+        DDM_CUDA(cudaMemcpyAsync(h.data(), hist.p, sizeof(unsigned int) * 512, cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+        for (int which = 0; which < 2; ++which) {
+            const bool top = which == 0;
+            const unsigned int *hh = h.data() + 256 * which;
             int digit = top ? 255 : 0;
-            while (true) {
-                if (static_cast<long long>(h[digit]) >= remaining) break;
-                remaining -= h[digit];
+            while (static_cast<long long>(hh[digit]) < remaining[which]) {
+                remaining[which] -= hh[digit];
                 digit += top ? -1 : 1;
                 if (digit < 0 || digit > 255) {
                     set_error("ddm_topk_sums: internal selection error");
                     return DDM_ERR_INVALID;
                 }
             }
-            prefix |= static_cast<unsigned long long>(digit) << shift;
+            prefix[which] |= static_cast<unsigned long long>(digit) << shift;
         }
-        // `remaining` copies of the k-th value itself belong to the selection
-        select_sum_kernel<<<grid, 256, 0, st>>>(x, n, prefix, top ? 1 : 0, static_cast<double *>(psum.p),
-                                                static_cast<unsigned long long *>(pcnt.p));
-        count_launch();
-        DDM_CUDA(cudaMemcpyAsync(hs.data(), psum.p, sizeof(double) * grid, cudaMemcpyDeviceToHost, st));
-        DDM_CUDA(cudaMemcpyAsync(hc.data(), pcnt.p, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost, st));
-        DDM_CUDA(cudaStreamSynchronize(st));
-        double s = 0.0;
+    }
+    select_sum2_kernel<<<grid, 256, 0, st>>>(x, n, prefix[0], prefix[1], static_cast<double *>(psum.p),
+                                             static_cast<unsigned long long *>(pcnt.p));
+    count_launch();
+    std::vector<double> hs(2 * grid);
+    std::vector<unsigned long long> hc(2 * grid);
+    DDM_CUDA(cudaMemcpyAsync(hs.data(), psum.p, sizeof(double) * 2 * grid, cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaMemcpyAsync(hc.data(), pcnt.p, sizeof(unsigned long long) * 2 * grid, cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaStreamSynchronize(st));
+    for (int which = 0; which < 2; ++which) {
+        double *result = which == 0 ? sum_top : sum_bottom;
+        if (!result) continue;
+        double sum = 0.0;
         unsigned long long c = 0;
         for (unsigned i = 0; i < grid; ++i) {
-            s += hs[i];
-            c += hc[i];
+            sum += hs[2 * i + which];
+            c += hc[2 * i + which];
         }
-        // value of the k-th element from its key
-        unsigned long long u = (prefix >> 63) ? (prefix & 0x7FFFFFFFFFFFFFFFULL) : ~prefix;
+        // value of the k-th element from its key; (k - c) copies of it complete the selection
+        const unsigned long long key = prefix[which];
+        unsigned long long u = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFULL) : ~key;
         double kth;
         std::memcpy(&kth, &u, sizeof(kth));
-        *result = s + kth * static_cast<double>(static_cast<long long>(k) - static_cast<long long>(c));
+        *result = sum + kth * static_cast<double>(static_cast<long long>(k) - static_cast<long long>(c));
     }
     DDM_CUDA(cudaGetLastError());
     return DDM_OK;
@@ -463,8 +572,8 @@ int ddm_compact_above(int device, const void *x_f64_dev, int64_t n, double thres
     const long long per_block = static_cast<long long>(kCompactThreads) * kCompactPer;
     const long long blocks = (n + per_block - 1) / per_block;
     DevBuf cnt, off;
-    if ((rc = cnt.alloc(sizeof(unsigned int) * blocks)) != DDM_OK) return rc;
-    if ((rc = off.alloc(sizeof(unsigned long long) * blocks)) != DDM_OK) return rc;
+    if ((rc = cnt.alloc(device, 4, sizeof(unsigned int) * blocks)) != DDM_OK) return rc;
+    if ((rc = off.alloc(device, 5, sizeof(unsigned long long) * blocks)) != DDM_OK) return rc;
     compact_count_kernel<<<static_cast<unsigned>(blocks), kCompactThreads, 0, st>>>(x, n, threshold,
                                                                                     static_cast<unsigned int *>(cnt.p));
     count_launch();
@@ -539,7 +648,7 @@ int ddm_bank4(int device, const void *x_dev, int64_t n, int x_is_f64, const doub
     DeviceGuard guard(device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DevBuf t;
-    if ((rc = t.alloc(sizeof(double) * 4 * nbuf)) != DDM_OK) return rc;
+    if ((rc = t.alloc(device, 0, sizeof(double) * 4 * nbuf)) != DDM_OK) return rc;
     DDM_CUDA(cudaMemcpyAsync(t.p, taps4_host, sizeof(double) * 4 * nbuf, cudaMemcpyHostToDevice, st));
     const size_t smem = sizeof(double) * 4 * nbuf;
     if (smem > 48 * 1024) {

@@ -47,6 +47,8 @@ const char *ddm_last_error(void);
 /* number of kernels this library has launched in the calling process (all handles) */
 int64_t ddm_launch_count(void);
 int ddm_device_count(int *count);
+/* free the per-device scratch pool kept by ddm_correlate / ddm_topk_sums / ddm_compact_above / ddm_bank4 */
+int ddm_release_scratch(int device);
 
 /* ---- fused chain ---------------------------------------------------------------------
  * offsetFreq -> real-tap FIR with carried state -> integer decimation -> FM discriminator

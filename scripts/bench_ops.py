@@ -86,7 +86,7 @@ def main():
                             ("FIR remez1023 cf32 (C4)", filters.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023), 4 * 1023),
                             ("IIR butter8 LP cf32 parallel (C4)", filters.butter(2400000, 100000, n=8), 2 * 34 * 2),
                             ("IIR butter6 LP f32 parallel", filters.butter(20800, 1200), 2 * 26)):
-        xin = xf if "f32 " not in tag else noise(nf, False)
+        xin = xf if " cf32" in tag else noise(nf, False)
         flt._apply_dev(xin[:1000000])
         report(tag, nf, *timeit(lambda: flt._apply_dev(xin), reps=3, warm=1), bytes_per_sample=16 if xin.is_complex() else 8,
                flops_per_sample=flops, note=str(flt.info()))
