@@ -48,9 +48,11 @@ struct FirTraits<false> {
     static constexpr int kRowStride = 12;              // floats per padded row (48 B)
 };
 
+// complex sample x real tap as ONE packed FFMA2 (broadcast-scalar tap operand): same FMA-pipe
+// time as two FFMAs but half the issue slots, which is what the LDS traffic competes for
 __device__ __forceinline__ void fir_mac(float2 &acc, float t, float2 v) {
-    acc.x = fmaf(t, v.x, acc.x);
-    acc.y = fmaf(t, v.y, acc.y);
+    const unsigned long long r = ffma2(pack_f32x2(t, t), pack_f32x2(v.x, v.y), pack_f32x2(acc.x, acc.y));
+    acc = unpack_f32x2(r);
 }
 __device__ __forceinline__ void fir_mac(float &acc, float t, float v) { acc = fmaf(t, v, acc); }
 __device__ __forceinline__ void fir_add(float2 &a, const float2 b) {
