@@ -48,6 +48,7 @@ SIGNATURES = {
     "ddm_fm_angle_diff": (_int, [_int, _vp, _i64, _vp, _vp, _vp, _pi64, _vp]),
     "ddm_abs": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
     "ddm_stride_copy": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _pi64, _vp]),
+    "ddm_medfilt": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
     "ddm_cu8_to_cf32": (_int, [_int, _vp, _i64, _vp, _vp]),
     "ddm_filter_create": (_int, [_int, _pdbl, _int, _pdbl, _int, C.POINTER(_vp)]),
     "ddm_filter_destroy": (_int, [_vp]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "ddm_filter_info": (_int, [_vp, _pint, _pi64, _pdbl]),
     "ddm_filter_apply_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),
     "ddm_filter_filtfilt_dev": (_int, [_vp, _vp, _i64, _int, _vp, _vp]),
+    "ddm_iir_analyse": (_int, [_pdbl, _int, _pdbl, _int, _pi64, _pdbl]),
     "ddm_lfilter_zi": (_int, [_pdbl, _int, _pdbl, _int, _pdbl]),
     "ddm_fft_create": (_int, [_int, C.POINTER(_vp)]),
     "ddm_fft_destroy": (_int, [_vp]),

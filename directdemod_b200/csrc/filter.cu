@@ -572,26 +572,18 @@ int setup_fir(ddm_filter *f) {
     return dev_alloc_copy(&f->d_b, f->b.data(), static_cast<size_t>(K));
 }
 
-int setup_iir(ddm_filter *f) {
-    const int P = pick_P(f->order);
-    if (P < 0) {
-        set_error("ddm_filter_create: IIR order %d is above the supported maximum %d", f->order, kIirMaxOrder);
-        return DDM_ERR_UNSUPPORTED;
-    }
-    f->P = P;
-    std::memset(&f->coef, 0, sizeof(f->coef));
-    for (int i = 0; i <= f->order; ++i) {
-        f->coef.b[i] = f->b[i];
-        f->coef.a[i] = f->a[i];
-    }
+// Host-side analysis of an IIR (order >= 1, coefficients normalised by a[0], padded to order+1):
+// warm-up length of the segment-parallel run and the float64 roundoff floor of the recursion.
+void analyse_iir(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
+                 double *noise_floor) {
     // Warm-up length of the segment-parallel run: the zero-input response of the recursion,
     // started from each unit state vector, simulated in long double until every state has
     // fallen below 1e-30 (a zero-input run has no roundoff floor, it decays geometrically all
     // the way).  Matrix powers of the companion form are useless here: for the reference's
     // clustered Butterworth poles they carry 1e20 transients and cancel catastrophically.
-    f->warmup = -1;
+    *warmup = -1;
     {
-        const int p = f->order;
+        const int p = order;
         const long long cap = 1LL << 22;
         long long worst = 0;
         bool ok = true;
@@ -603,7 +595,7 @@ int setup_iir(ddm_filter *f) {
                 const ld y = z[0];
                 ld m = 0;
                 for (int i = 0; i < p; ++i) {
-                    z[i] = z[i + 1] - static_cast<ld>(f->a[i + 1]) * y;
+                    z[i] = z[i + 1] - static_cast<ld>(a[i + 1]) * y;
                     m = std::max(m, std::fabs(z[i]));
                 }
                 ++k;
@@ -617,15 +609,15 @@ int setup_iir(ddm_filter *f) {
             if (k >= cap) ok = false;
             worst = std::max(worst, k);
         }
-        if (ok) f->warmup = worst + kIirBlock;
+        if (ok) *warmup = worst + kIirBlock;
     }
     // Roundoff noise floor of scipy's float64 recursion for THIS filter: run it on white noise
     // in double and in long double and compare.  Two float64 runs whose states ever differ by
     // one ulp stay this far apart for good (the rounding errors are re-amplified by 1/A(z)), so
     // a segment-parallel run can match the reference's own sequential run no better than this.
     {
-        const int p = f->order;
-        const long long nt = std::min<long long>(std::max<long long>(f->warmup > 0 ? 2 * f->warmup : 65536, 8192), 65536);
+        const int p = order;
+        const long long nt = std::min<long long>(std::max<long long>(*warmup > 0 ? 2 * *warmup : 65536, 8192), 65536);
         std::vector<double> zd(p + 1, 0.0);
         std::vector<ld> zl(p + 1, 0.0L);
         unsigned long long lcg = 0x9E3779B97F4A7C15ULL;
@@ -633,14 +625,14 @@ int setup_iir(ddm_filter *f) {
         for (long long i = 0; i < nt; ++i) {
             lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
             const double xv = static_cast<double>(static_cast<float>((static_cast<double>(lcg >> 11) / 9007199254740992.0) - 0.5));
-            volatile double yd = zd[0] + f->b[0] * xv;
-            const ld yl = zl[0] + static_cast<ld>(f->b[0]) * xv;
+            volatile double yd = zd[0] + b[0] * xv;
+            const ld yl = zl[0] + static_cast<ld>(b[0]) * xv;
             for (int k = 0; k < p; ++k) {
-                volatile double t1 = xv * f->b[k + 1];
+                volatile double t1 = xv * b[k + 1];
                 volatile double t2 = zd[k + 1] + t1;
-                volatile double t3 = yd * f->a[k + 1];
+                volatile double t3 = yd * a[k + 1];
                 zd[k] = t2 - t3;
-                zl[k] = zl[k + 1] + static_cast<ld>(f->b[k + 1]) * xv - static_cast<ld>(f->a[k + 1]) * yl;
+                zl[k] = zl[k + 1] + static_cast<ld>(b[k + 1]) * xv - static_cast<ld>(a[k + 1]) * yl;
             }
             if (i >= nt / 2) {
                 const long double d = static_cast<ld>(yd) - yl;
@@ -648,9 +640,24 @@ int setup_iir(ddm_filter *f) {
                 den += yl * yl;
             }
         }
-        f->noise_floor = den > 0 ? static_cast<double>(std::sqrt(num / den)) : 0.0;
-        if (!(f->noise_floor == f->noise_floor)) f->noise_floor = 1.0;
+        *noise_floor = den > 0 ? static_cast<double>(std::sqrt(num / den)) : 0.0;
+        if (!(*noise_floor == *noise_floor)) *noise_floor = 1.0;
     }
+}
+
+int setup_iir(ddm_filter *f) {
+    const int P = pick_P(f->order);
+    if (P < 0) {
+        set_error("ddm_filter_create: IIR order %d is above the supported maximum %d", f->order, kIirMaxOrder);
+        return DDM_ERR_UNSUPPORTED;
+    }
+    f->P = P;
+    std::memset(&f->coef, 0, sizeof(f->coef));
+    for (int i = 0; i <= f->order; ++i) {
+        f->coef.b[i] = f->b[i];
+        f->coef.a[i] = f->a[i];
+    }
+    analyse_iir(f->order, f->b, f->a, &f->warmup, &f->noise_floor);
     return DDM_OK;
 }
 
@@ -884,6 +891,24 @@ int ddm_filter_info(const ddm_filter *f, int *is_fir, int64_t *warmup, double *n
     if (is_fir) *is_fir = f->fir ? 1 : 0;
     if (warmup) *warmup = f->fir ? 0 : f->warmup;
     if (noise_floor) *noise_floor = f->fir ? 0.0 : f->noise_floor;
+    return DDM_OK;
+}
+
+int ddm_iir_analyse(const double *b, int nb, const double *a, int na, int64_t *warmup, double *noise_floor) {
+    DDM_REQUIRE(b && a && nb >= 1 && na >= 1, "ddm_iir_analyse: bad arguments");
+    DDM_REQUIRE(a[0] != 0.0, "ddm_iir_analyse: a[0] must be non-zero");
+    const int order = std::max(na, nb) - 1;
+    std::vector<double> bb(order + 1, 0.0), aa(order + 1, 0.0);
+    for (int i = 0; i < nb; ++i) bb[i] = b[i] / a[0];
+    for (int i = 0; i < na; ++i) aa[i] = a[i] / a[0];
+    long long w = 0;
+    double nf = 0.0;
+    bool fir = true;
+    for (int i = 1; i <= order; ++i)
+        if (aa[i] != 0.0) fir = false;
+    if (!fir) analyse_iir(order, bb, aa, &w, &nf);
+    if (warmup) *warmup = w;
+    if (noise_floor) *noise_floor = nf;
     return DDM_OK;
 }
 

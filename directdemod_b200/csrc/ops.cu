@@ -157,6 +157,28 @@ __global__ void cu8_kernel_scalar(const unsigned char *in, float2 *out, long lon
                              static_cast<float>(in[2 * i + 1]) - 127.5f);
 }
 
+// scipy.signal.medfilt(x, k): median of the k-sample window centred on each sample, zeros
+// outside the array (filters.py:322-326).  One thread per output; the window is kept sorted by
+// insertion in local memory (k is small: the reference's default is 5).
+constexpr int kMedMaxK = 255;
+__global__ void medfilt_kernel(const float *__restrict__ x, long long n, int k, float *__restrict__ out) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float w[kMedMaxK];
+    const int half = k / 2;
+    for (int j = 0; j < k; ++j) {
+        const long long g = i - half + j;
+        const float v = (g >= 0 && g < n) ? x[g] : 0.f;
+        int p = j;
+        while (p > 0 && w[p - 1] > v) {
+            w[p] = w[p - 1];
+            --p;
+        }
+        w[p] = v;
+    }
+    out[i] = w[half];
+}
+
 }  // namespace ddm
 
 using namespace ddm;
@@ -299,6 +321,21 @@ int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, in
     else
         stride_copy_kernel<double2><<<grid, kOpsThreads, 0, st>>>(
             static_cast<const double2 *>(x_dev), static_cast<double2 *>(out_dev), m, offset, step);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_medfilt(int device, const void *x_dev, int64_t n, int kernel_size, void *out_dev, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_medfilt: negative length");
+    DDM_REQUIRE(kernel_size >= 1 && (kernel_size & 1) == 1, "ddm_medfilt: Each element of kernel_size should be odd.");
+    DDM_REQUIRE(kernel_size <= kMedMaxK, "ddm_medfilt: kernel sizes above %d are not supported", kMedMaxK);
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_medfilt: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_medfilt");
+    DeviceGuard guard(device);
+    medfilt_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float *>(x_dev), n, kernel_size, static_cast<float *>(out_dev));
     DDM_CUDA(cudaGetLastError());
     count_launch();
     return DDM_OK;

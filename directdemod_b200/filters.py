@@ -73,6 +73,28 @@ class filter:
         _lib.check(_lib.lib().ddm_filter_set_iir_mode(self._handle(), int(mode)), "ddm_filter_set_iir_mode")
         return self
 
+    def analysis(self):
+        """(warm-up length of the segment-parallel IIR, measured roundoff floor) -- host only,
+        needs no device; (0, 0.0) for a FIR."""
+        w, nf = C.c_int64(), C.c_double()
+        _lib.check(_lib.lib().ddm_iir_analyse(
+            self._bd.ctypes.data_as(C.POINTER(C.c_double)), self._bd.size,
+            self._ad.ctypes.data_as(C.POINTER(C.c_double)), self._ad.size, C.byref(w), C.byref(nf)),
+            "ddm_iir_analyse")
+        return int(w.value), float(nf.value)
+
+    def lookback(self):
+        """Input history (samples) a time slab needs from its predecessor for this filter:
+        ntaps-1 for a FIR, the warm-up length for a segment-parallel IIR.  Raises for filters
+        that only run as a sequential replay (their state is a serial dependency)."""
+        if self.isFIR:
+            return max(self._bd.size, self._ad.size) - 1
+        w, nf = self.analysis()
+        if w < 0 or nf > 1e-7:
+            raise ValueError("this IIR runs as a sequential bit-exact replay (roundoff floor %.1e) and cannot "
+                             "be time-sharded; shard it by independent units" % nf)
+        return w
+
     def info(self):
         """(is_fir, parallel warm-up length, measured float64 roundoff floor of the recursion)."""
         fir, w, nf = C.c_int(), C.c_int64(), C.c_double()
@@ -274,13 +296,22 @@ class blackmanHarrisConv:
 
 
 class medianFilter:
-    """scipy medfilt wrapper (filters.py:322-326).  Not on the hot path: no decoder calls it
-    and the reference marks it 'to be implemented later'; it stays a host call."""
+    """scipy.signal.medfilt(sig, n) (filters.py:322-326) on the GPU: window median with zero
+    padding at the ends; real signals, odd n."""
+
+    _ddm_native = True
 
     def __init__(self, n=5):
         self._n = n
 
     def applyOn(self, sig):
-        if _dev.is_tensor(sig):
-            sig = _dev.to_host(sig)
-        return signal.medfilt(sig, self._n)
+        if self._n % 2 != 1:
+            raise ValueError("Each element of kernel_size should be odd.")
+        dev_in = _dev.is_tensor(sig) and sig.is_cuda
+        xd = _dev.to_device(sig)
+        if xd.is_complex():
+            raise TypeError("medianFilter works on real signals")
+        y = _dev.empty_like_kind(xd.numel(), False, xd.device.index)
+        _lib.check(_lib.lib().ddm_medfilt(xd.device.index, _dev.ptr(xd), xd.numel(), int(self._n), _dev.ptr(y),
+                                          _dev.stream_ptr(xd.device.index)), "ddm_medfilt")
+        return y if dev_in else _dev.to_host(y)

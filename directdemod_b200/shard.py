@@ -107,3 +107,53 @@ class TimeShardedChain:
         else:
             self.chain.set_position(self.start, off, True, halo)
         return self.chain.apply(x_slab)
+
+
+class TimeShardedFilters:
+    """A cascade of filters.filter objects (BASELINE config 4: 1023-tap Remez, then an 8th-order
+    Butterworth) over one slab of a time-sharded stream.
+
+    Each filter needs ``filter.lookback()`` samples of history: ntaps-1 inputs for a FIR, the
+    warm-up length W for the segment-parallel IIR.  The histories add up along the cascade, and
+    all of it is RAW input of the previous slab, so ONE neighbour exchange of
+    ``halo_len = sum(lookbacks)`` samples (NCCL point-to-point) serves the whole cascade and does
+    not wait for the neighbour's compute.  Rank 0 runs the filters statefully from the reference's
+    initial conditions (lfilter_zi); ranks > 0 run them from zero state over [halo ++ slab] and
+    drop the first halo_len outputs -- by then the zero-input response of every stage has decayed
+    below one ulp.  A filter that only runs as a sequential replay raises at construction."""
+
+    def __init__(self, filts, n_samples, rank, world, group=None):
+        self.filts = list(filts)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.halo_len = int(sum(f.lookback() for f in self.filts)) if world > 1 else 0
+        self.bounds = slab_bounds(n_samples, world, 1)
+        self.start, self.end = self.bounds[rank]
+        for s, e in self.bounds[:-1]:
+            if world > 1 and e - s < self.halo_len:
+                raise ValueError("slab of %d samples is shorter than the %d-sample halo" % (e - s, self.halo_len))
+
+    def run(self, x_slab):
+        import ctypes as C
+        import torch
+        from . import _dev, _lib
+        if x_slab.numel() != self.end - self.start:
+            raise ValueError("slab has %d samples, expected %d" % (x_slab.numel(), self.end - self.start))
+        halo = None
+        if self.world > 1:
+            send = x_slab[-self.halo_len:] if self.rank + 1 < self.world else \
+                torch.empty(self.halo_len, dtype=x_slab.dtype, device=x_slab.device)
+            halo = exchange_halo(send.contiguous(), self.rank, self.world, self.group)
+        if self.rank == 0 or self.world == 1:
+            y = x_slab
+            for f in self.filts:
+                y = f._apply_dev(y)
+            return y
+        y = torch.cat([halo, x_slab])
+        l = _lib.lib()
+        for f in self.filts:
+            out = torch.empty_like(y)
+            _lib.check(l.ddm_filter_apply_dev(f._handle(), _dev.ptr(y), y.numel(), int(y.is_complex()),
+                                              _dev.ptr(out), 0, _dev.stream_ptr(y.device.index)),
+                       "ddm_filter_apply_dev")
+            y = out
+        return y[self.halo_len:]

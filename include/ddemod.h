@@ -128,6 +128,8 @@ int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_
 /* comm.py:127  out = x[offset::step]; elem_bytes 4 (f32), 8 (cf32) or 16 (c128) */
 int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, int64_t offset,
                     int64_t step, void *out_dev, int64_t *n_out, void *stream);
+/* filters.py:322-326  scipy.signal.medfilt(x, kernel_size) on f32 (odd kernel_size <= 255, zero padded) */
+int ddm_medfilt(int device, const void *x_dev, int64_t n, int kernel_size, void *out_dev, void *stream);
 /* source.py:117-118 / :209-210  interleaved u8 IQ -> cf32 minus (127.5 + 127.5j) */
 int ddm_cu8_to_cf32(int device, const void *iq_u8_dev, int64_t n, void *out_dev, void *stream);
 
@@ -167,6 +169,9 @@ int ddm_filter_set_zi_base(ddm_filter *f, const double *zi_host);
 int ddm_filter_set_iir_mode(ddm_filter *f, int mode);
 /* is_fir, warm-up length of the segment-parallel IIR (-1: never decays), measured noise floor */
 int ddm_filter_info(const ddm_filter *f, int *is_fir, int64_t *warmup, double *noise_floor);
+/* host only (no device needed): warm-up length of the segment-parallel IIR (-1: the zero-input
+ * response never decays) and the measured float64 roundoff floor; 0 / 0.0 for a FIR */
+int ddm_iir_analyse(const double *b, int nb, const double *a, int na, int64_t *warmup, double *noise_floor);
 /* scipy.signal.lfilter_zi restated; zi_out has max(na,nb)-1 entries */
 int ddm_lfilter_zi(const double *b, int nb, const double *a, int na, double *zi_out);
 

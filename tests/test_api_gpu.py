@@ -317,6 +317,18 @@ def test_blackman_harris_conv_same():
         assert O.rel_rms(filters.blackmanHarrisConv(151).applyOn(x), want) <= TOL, n
 
 
+def test_median_filter_matches_scipy():
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(10007).astype(np.float32)
+    for k in (1, 3, 5, 21):
+        got = filters.medianFilter(k).applyOn(x)
+        assert np.array_equal(got.astype(np.float32), sps.medfilt(x, k).astype(np.float32)), k
+    with pytest.raises(ValueError):
+        filters.medianFilter(4).applyOn(x)
+
+
 def test_long_fir_and_iir_large_chunks():
     """C4-shaped operators at a size that crosses many FIR/IIR tiles: 1023-tap Remez and an
     8th-order Butterworth on complex noise, chunked unevenly."""
