@@ -67,6 +67,8 @@ SIGNATURES = {
     "ddm_fft_destroy": (_int, [_vp]),
     "ddm_am_hilbert": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ddm_resample": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp]),
+    "ddm_resample_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "ddm_row_medians": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ddm_correlate": (_int, [_int, _vp, _i64, _int, _pdbl, _int, _int, _vp, _vp]),
     "ddm_topk_sums": (_int, [_int, _vp, _i64, _i64, _pdbl, _pdbl, _vp]),
     "ddm_compact_above": (_int, [_int, _vp, _i64, _dbl, _vp, _vp, _i64, _pi64, _vp]),

@@ -227,17 +227,19 @@ __global__ void fft_pointwise_kernel(double2 *buf, const double2 *__restrict__ b
 // src kinds: 0 = f32 real rows, 1 = cf32 rows, 2 = double2 rows (row stride src_stride elements)
 template <int KIND, bool CONJ>
 __global__ void blu_load_kernel(const void *__restrict__ src, long long src_stride, long long n,
-                                const double2 *__restrict__ w, double2 *__restrict__ a, int m) {
+                                const double2 *__restrict__ w, double2 *__restrict__ a, int m,
+                                const long long *__restrict__ row_off) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= m) return;
     const size_t row = blockIdx.y;
+    const size_t r0 = row_off ? static_cast<size_t>(row_off[row]) : row * src_stride;
     double2 v = make_double2(0.0, 0.0);
     if (k < n) {
-        if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[row * src_stride + k]);
+        if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[r0 + k]);
         else if (KIND == 1) {
-            const float2 s = static_cast<const float2 *>(src)[row * src_stride + k];
+            const float2 s = static_cast<const float2 *>(src)[r0 + k];
             v = make_double2(static_cast<double>(s.x), static_cast<double>(s.y));
-        } else v = static_cast<const double2 *>(src)[row * src_stride + k];
+        } else v = static_cast<const double2 *>(src)[r0 + k];
         if (CONJ) v.y = -v.y;
         v = cmuld(v, w[k]);
     }
@@ -264,16 +266,17 @@ __global__ void blu_finish_kernel(const double2 *__restrict__ c, int m, long lon
 // power-of-two direct path helpers
 template <int KIND>
 __global__ void fft_load_plain_kernel(const void *__restrict__ src, long long src_stride, long long n,
-                                      double2 *__restrict__ a) {
+                                      double2 *__restrict__ a, const long long *__restrict__ row_off) {
     const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (k >= n) return;
     const size_t row = blockIdx.y;
+    const size_t r0 = row_off ? static_cast<size_t>(row_off[row]) : row * src_stride;
     double2 v = make_double2(0.0, 0.0);
-    if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[row * src_stride + k]);
+    if (KIND == 0) v.x = static_cast<double>(static_cast<const float *>(src)[r0 + k]);
     else if (KIND == 1) {
-        const float2 s = static_cast<const float2 *>(src)[row * src_stride + k];
+        const float2 s = static_cast<const float2 *>(src)[r0 + k];
         v = make_double2(static_cast<double>(s.x), static_cast<double>(s.y));
-    } else v = static_cast<const double2 *>(src)[row * src_stride + k];
+    } else v = static_cast<const double2 *>(src)[r0 + k];
     a[row * n + k] = v;
 }
 
@@ -307,6 +310,8 @@ __global__ void resample_spec_kernel(const double2 *__restrict__ X, long long n,
                                      long long num, int is_real) {
     const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (k >= num) return;
+    X += static_cast<size_t>(blockIdx.y) * n;          // one spectrum per row
+    Y += static_cast<size_t>(blockIdx.y) * num;
     const long long N = n < num ? n : num;
     const long long half = N / 2;
     double2 v = make_double2(0.0, 0.0);
@@ -352,9 +357,10 @@ __global__ void resample_out_kernel(const double2 *__restrict__ z, long long num
                                     int is_real) {
     const long long k = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (k >= num) return;
-    const double2 v = z[k];
-    if (is_real) static_cast<float *>(out)[k] = static_cast<float>(v.x * scale);
-    else static_cast<float2 *>(out)[k] = make_float2(static_cast<float>(v.x * scale), static_cast<float>(v.y * scale));
+    const size_t r0 = static_cast<size_t>(blockIdx.y) * num;
+    const double2 v = z[r0 + k];
+    if (is_real) static_cast<float *>(out)[r0 + k] = static_cast<float>(v.x * scale);
+    else static_cast<float2 *>(out)[r0 + k] = make_float2(static_cast<float>(v.x * scale), static_cast<float>(v.y * scale));
 }
 
 }  // namespace ddm
@@ -524,14 +530,14 @@ int get_plan(ddm_fft *c, long long n, cudaStream_t st, FftPlan **out) {
 // inverse as conj(DFT(conj(x))) * scale.
 template <int KIND, bool INVERSE>
 int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int batch, double scale,
-             double2 *dst, long long dst_stride, cudaStream_t st) {
+             double2 *dst, long long dst_stride, cudaStream_t st, const long long *row_off = nullptr) {
     const long long n = p->n;
     const int m = p->m;
     int rc = ensure_ws(c, static_cast<size_t>(m) * batch, st);
     if (rc != DDM_OK) return rc;
     if (p->pow2) {
         const dim3 g((n + kFftThreads - 1) / kFftThreads, batch);
-        fft_load_plain_kernel<KIND><<<g, kFftThreads, 0, st>>>(src, src_stride, n, c->d_ws[0]);
+        fft_load_plain_kernel<KIND><<<g, kFftThreads, 0, st>>>(src, src_stride, n, c->d_ws[0], row_off);
         count_launch();
         const int r = INVERSE ? pow2_fft<-1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices)
                               : pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices);
@@ -543,7 +549,7 @@ int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int 
     }
     const dim3 gm((m + kFftThreads - 1) / kFftThreads, batch);
     const dim3 gn((n + kFftThreads - 1) / kFftThreads, batch);
-    blu_load_kernel<KIND, INVERSE><<<gm, kFftThreads, 0, st>>>(src, src_stride, n, p->d_w, c->d_ws[0], m);
+    blu_load_kernel<KIND, INVERSE><<<gm, kFftThreads, 0, st>>>(src, src_stride, n, p->d_w, c->d_ws[0], m, row_off);
     count_launch();
     int r = pow2_fft<1>(c->d_ws, 0, p->d_tw, m, batch, st, p->radices);
     fft_pointwise_kernel<<<gm, kFftThreads, 0, st>>>(c->d_ws[r], p->d_bfft, m);
@@ -668,6 +674,43 @@ int ddm_resample(ddm_fft *c, const void *x_dev, int64_t n, int is_complex, int64
     if (rc != DDM_OK) return rc;
     resample_out_kernel<<<g, kFftThreads, 0, st>>>(c->d_spec[0], num, 1.0, out_dev, is_complex ? 0 : 1);
     count_launch();
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
+int ddm_resample_rows(ddm_fft *c, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t n,
+                      int64_t num, void *out_dev, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_resample_rows: NULL context");
+    DDM_REQUIRE(rows >= 0 && n >= 1 && num >= 0, "ddm_resample_rows: bad sizes");
+    if (rows == 0 || num == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && row_start_dev != nullptr && out_dev != nullptr, "ddm_resample_rows: NULL buffer");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FftPlan *pn = nullptr, *pm = nullptr;
+    int rc = get_plan(c, n, st, &pn);
+    if (rc != DDM_OK) return rc;
+    rc = get_plan(c, num, st, &pm);
+    if (rc != DDM_OK) return rc;
+    const int64_t mmax = std::max<int64_t>(pn->m, pm->m);
+    int64_t rows_per = std::max<int64_t>(1, (32LL << 20) / mmax);       // workspace <= ~1 GiB
+    rows_per = std::min<int64_t>(rows_per, 65535);
+    const int64_t big = std::max<int64_t>(n, num);
+    float *out = static_cast<float *>(out_dev);
+    for (int64_t r0 = 0; r0 < rows; r0 += rows_per) {
+        const int batch = static_cast<int>(std::min<int64_t>(rows_per, rows - r0));
+        rc = ensure_spec(c, static_cast<size_t>(big) * batch, st);
+        if (rc != DDM_OK) return rc;
+        rc = dft_rows<0, false>(c, pn, x_dev, 0, batch, 1.0, c->d_spec[0], n, st,
+                                reinterpret_cast<const long long *>(row_start_dev + r0));
+        if (rc != DDM_OK) return rc;
+        const dim3 g(static_cast<unsigned>((num + kFftThreads - 1) / kFftThreads), batch);
+        resample_spec_kernel<<<g, kFftThreads, 0, st>>>(c->d_spec[0], n, c->d_spec[1], num, 1);
+        count_launch();
+        rc = dft_rows<2, true>(c, pm, c->d_spec[1], num, batch, 1.0 / static_cast<double>(n), c->d_spec[0], num, st);
+        if (rc != DDM_OK) return rc;
+        resample_out_kernel<<<g, kFftThreads, 0, st>>>(c->d_spec[0], num, 1.0, out + r0 * num, 1);
+        count_launch();
+    }
     DDM_CUDA(cudaGetLastError());
     return DDM_OK;
 }

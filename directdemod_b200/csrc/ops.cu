@@ -179,6 +179,79 @@ __global__ void medfilt_kernel(const float *__restrict__ x, long long n, int k, 
     out[i] = w[half];
 }
 
+// np.median of many rows of one array: out[r] = median(x[start[r] : start[r] + len]).
+// Short rows (<= 64): one thread per row, insertion sort in local memory.
+constexpr int kRowMedSmall = 64;
+__global__ void row_median_small_kernel(const float *__restrict__ x, const long long *__restrict__ start,
+                                        long long rows, long long stride, int len, double *__restrict__ out) {
+    const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (r >= rows) return;
+    const float *p = x + (start ? start[r] : r * stride);
+    float w[kRowMedSmall];
+    for (int j = 0; j < len; ++j) {
+        const float v = p[j];
+        int q = j;
+        while (q > 0 && w[q - 1] > v) {
+            w[q] = w[q - 1];
+            --q;
+        }
+        w[q] = v;
+    }
+    out[r] = (len & 1) ? static_cast<double>(w[len / 2])
+                       : 0.5 * (static_cast<double>(w[len / 2 - 1]) + static_cast<double>(w[len / 2]));
+}
+
+// Long rows: one CTA per row, 4-pass radix select on order-preserving float keys (shared-memory
+// histograms); for an even length both middle elements are found and averaged like numpy.
+__device__ __forceinline__ unsigned int f32_key(float v) {
+    const unsigned int u = __float_as_uint(v);
+    return (u >> 31) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_key(unsigned int k) {
+    return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void __launch_bounds__(256)
+row_median_select_kernel(const float *__restrict__ x, const long long *__restrict__ start, long long stride,
+                         long long len, double *__restrict__ out) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_prefix, s_rank;
+    const float *p = x + (start ? start[blockIdx.x] : blockIdx.x * stride);
+    double acc = 0.0;
+    const int picks = (len & 1) ? 1 : 2;
+    for (int pick = 0; pick < picks; ++pick) {
+        // rank (0-based, ascending) of the element wanted
+        long long want = (len & 1) ? len / 2 : len / 2 - 1 + pick;
+        unsigned int prefix = 0;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+            __syncthreads();
+            const unsigned int himask = shift >= 24 ? 0u : (~0u << (shift + 8));
+            for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+                const unsigned int k = f32_key(p[i]);
+                if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long rem = want;
+                int d = 0;
+                while (static_cast<long long>(hist[d]) <= rem) {
+                    rem -= hist[d];
+                    ++d;
+                }
+                s_prefix = prefix | (static_cast<unsigned int>(d) << shift);
+                s_rank = static_cast<unsigned int>(rem);
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            want = s_rank;
+            __syncthreads();
+        }
+        acc += static_cast<double>(f32_from_key(prefix));
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = acc / picks;
+}
+
 }  // namespace ddm
 
 using namespace ddm;
@@ -336,6 +409,29 @@ int ddm_medfilt(int device, const void *x_dev, int64_t n, int kernel_size, void 
     DeviceGuard guard(device);
     medfilt_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float *>(x_dev), n, kernel_size, static_cast<float *>(out_dev));
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_row_medians(int device, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t row_stride,
+                    int64_t row_len, void *out_f64_dev, void *stream) {
+    DDM_REQUIRE(rows >= 0 && row_len >= 1, "ddm_row_medians: bad sizes");
+    if (rows == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_f64_dev != nullptr, "ddm_row_medians: NULL buffer");
+    DDM_CHECK_DEVICE(device, "ddm_row_medians");
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long *start = reinterpret_cast<const long long *>(row_start_dev);
+    if (row_len <= kRowMedSmall) {
+        row_median_small_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, st>>>(
+            static_cast<const float *>(x_dev), start, rows, row_stride, static_cast<int>(row_len),
+            static_cast<double *>(out_f64_dev));
+    } else {
+        DDM_REQUIRE(rows <= 2147483647LL, "ddm_row_medians: too many rows");
+        row_median_select_kernel<<<static_cast<unsigned>(rows), 256, 0, st>>>(
+            static_cast<const float *>(x_dev), start, row_stride, row_len, static_cast<double *>(out_f64_dev));
+    }
     DDM_CUDA(cudaGetLastError());
     count_launch();
     return DDM_OK;

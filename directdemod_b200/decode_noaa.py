@@ -2,9 +2,12 @@
 (__audio), chunked Hilbert AM (__getAM), normalised sync correlation with peak picking
 (__correlate / __correlateAndFindPeaks), getCrudeSync, getAccurateSync and the usefulness test.
 
-Same class name, constructor and method/property names as the reference.  The image
-assembly (getImage and what hangs off it: channelID, getColor, getMapImage) is the consumer
-of this path and is not part of it; those members raise NotImplementedError.
+Same class name, constructor and method/property names as the reference.  ``getImage``
+(decode_noaa.py:255-465), the consumer that defines the pixel-level acceptance, is assembled
+here too: the whole-stream band-pass filtfilt, the Hilbert AM, every line's FFT resample (all
+lines of equal length in one batch) and all medians run on the GPU; the colour-calibration
+state machine stays on the host.  False colour and map overlay (getColor, getMapImage) are
+cosmetic post-processing and out of scope.
 """
 
 from __future__ import annotations
@@ -13,7 +16,35 @@ import logging
 
 import numpy as np
 
-from . import chunker, comm, constants, demod_am, demod_fm, filters, sync
+import ctypes as C
+
+from . import _dev, _lib, chunker, comm, constants, demod_am, demod_fm, fftops, filters, sync
+
+
+def _row_medians(x, starts=None, rows=None, stride=0, length=1):
+    """np.median over rows of the cuda float32 tensor ``x`` (ddm_row_medians) -> float64 numpy."""
+    t = _dev.torch()
+    if starts is not None:
+        sd = t.as_tensor(np.ascontiguousarray(starts, dtype=np.int64), device=x.device)
+        rows = sd.numel()
+        sp = _dev.ptr(sd)
+    else:
+        sp = C.c_void_p(0)
+    out = t.empty(int(rows), dtype=t.float64, device=x.device)
+    _lib.check(_lib.lib().ddm_row_medians(x.device.index, _dev.ptr(x), sp, int(rows), int(stride), int(length),
+                                          _dev.ptr(out), _dev.stream_ptr(x.device.index)), "ddm_row_medians")
+    return out.cpu().numpy()
+
+
+def _resample_rows(x, starts, n, num):
+    """signal.resample of the rows x[s:s+n] -> [rows][num] cuda float32 (ddm_resample_rows)."""
+    t = _dev.torch()
+    sd = t.as_tensor(np.ascontiguousarray(starts, dtype=np.int64), device=x.device)
+    out = t.empty((sd.numel(), int(num)), dtype=t.float32, device=x.device)
+    _lib.check(_lib.lib().ddm_resample_rows(fftops._context(x.device.index), _dev.ptr(x), _dev.ptr(sd),
+                                            sd.numel(), int(n), int(num), _dev.ptr(out),
+                                            _dev.stream_ptr(x.device.index)), "ddm_resample_rows")
+    return out
 
 
 class decode_noaa:
@@ -36,15 +67,228 @@ class decode_noaa:
         self._useNormCorrelate = None
         self._useful = 0
         self._syncCrudeSampRate = None
+        self._image = None
+        self._chIDA = None
+        self._chIDB = None
+        self._low = self._high = self._slope = self._intercept = None
 
-    # ---- not on the hot path ----------------------------------------------------------
+    # ---- image assembly ---------------------------------------------------------------
     @property
     def channelID(self):
-        raise NotImplementedError("image assembly (decode_noaa.getImage) is outside the accelerated path")
+        """[channel id A, channel id B] from the telemetry wedges (decode_noaa.py:53-66)."""
+        if self._image is None:
+            self.getImage
+        return [self._chIDA, self._chIDB]
+
+    @staticmethod
+    def _fillSync(csync, maxLen):
+        """decode_noaa.py:467-508: keep the syncs spaced by the modal distance (+-200), then
+        extrapolate backwards to the start and fill every gap forwards up to maxLen."""
+        spacing = np.diff(csync)
+        counts = list(spacing)
+        mode = max(set(spacing), key=counts.count)
+        wiggle = 200
+        valid = []
+        for i in range(len(csync) - 1):
+            if abs(csync[i + 1] - csync[i] - mode) < wiggle:
+                for v in (csync[i], csync[i + 1]):
+                    if v not in valid:
+                        valid.append(v)
+        filled = valid[:]
+        c = valid[0] - mode
+        while c > wiggle:
+            filled.append(c)
+            c -= mode
+        anchor = 0
+        c = mode
+        while valid[anchor] + c < maxLen:
+            if (anchor + 1) < len(valid) and (abs(valid[anchor + 1] - c - valid[anchor]) < wiggle
+                                              or c + valid[anchor] > valid[anchor + 1]):
+                anchor += 1
+                c = mode
+            else:
+                filled.append(valid[anchor] + c)
+                c += mode
+        return list(np.sort(filled))
 
     @property
     def getImage(self):
-        raise NotImplementedError("image assembly (decode_noaa.getImage) is outside the accelerated path")
+        """Matrix of uint8 pixel values, one row per APT line (decode_noaa.py:255-465)."""
+        if self._image is not None:
+            return self._image
+        if self._audOut is None or self._syncA is None or self._syncB is None:
+            self.getCrudeSync()
+        logging.info('Beginning image extraction')
+        t = _dev.torch()
+        aud = self._audOut
+        fs = aud.sampRate
+        # :274 whole-stream zero-phase band-pass.  Its float64 tf-form recursion has a 3e-4 roundoff
+        # floor (DESIGN.md 3.3) and its input already differs from the reference's by the fp32
+        # rounding of the FM stage, so the sequential bit-replay buys nothing here: run parallel.
+        bp = filters.butter(fs, 400, 4400, typeFlt=constants.FLT_BP, zeroPhase=True)
+        bp.setIIRMode(1)
+        aud.filter(bp)
+        am = self._getAM(aud)
+        sig = am.deviceSignal                       # cuda float32, stays on the device
+        n = am.length
+        csyncA = self._syncA / self._syncCrudeSampRate * fs
+        csyncB = self._syncB / self._syncCrudeSampRate * fs
+        ucsync = csyncA[:]
+        csyncA = self._fillSync(csyncA, n)
+        csyncB = self._fillSync(csyncB, n)
+        if csyncB[0] < csyncA[0]:
+            csyncB.pop(0)
+        if csyncB[-1] < csyncA[-1]:
+            csyncA.pop(-1)
+        if not len(csyncA) == len(csyncB):
+            logging.error("Number of syncA and syncB unequal")
+            csyncB = np.array(csyncA) + int(0.25 * fs)
+
+        numPixels = int(0.5 / constants.NOAA_T)      # 2080
+        half = numPixels // 2
+        # :317-320 first guess of the black / white levels from the whole pass
+        seg = n // numPixels
+        (self._low, self._high) = np.percentile(_row_medians(sig, rows=numPixels, stride=seg, length=seg),
+                                                (0.5, 99.5))
+
+        # ---- geometry of every line, then all GPU work in batches --------------------
+        lines = []
+        for k in range(len(csyncA)):
+            sA, sB = int(csyncA[k]), int(csyncB[k])
+            eA = sB
+            eB = sB + int(0.25 * fs)
+            if 1 + k < len(csyncA):
+                eB = int(csyncA[k + 1])
+            if eB > n or eA > n or sA < 0 or sB < 0:
+                continue
+            lines.append((k, sA, eA, sB, eB))
+        # per-pixel medians of the resampled half lines, grouped by (length, target) so that each
+        # group is one batched FFT resample; plus the raw samples of the 40 sync pixels of side A
+        pix = {}
+        sync_px = {}
+        groups = {}
+        for li, (k, sA, eA, sB, eB) in enumerate(lines):
+            for side, (s0, e0) in (("A", (sA, eA)), ("B", (sB, eB))):
+                ln = e0 - s0
+                num = int(int(ln / (numPixels * 0.5)) * (numPixels * 0.5))
+                groups.setdefault((ln, num), []).append((li, side, s0))
+        nsync = len(constants.NOAA_SYNCA)
+        for (ln, num), members in groups.items():
+            if ln < 1 or num < half:
+                for li, side, s0 in members:
+                    pix[(li, side)] = None
+                continue
+            rows = _resample_rows(sig, [m[2] for m in members], ln, num)        # [rows][num]
+            per = num // half
+            med = _row_medians(rows.reshape(-1), rows=rows.shape[0] * half, stride=per, length=per)
+            med = med.reshape(rows.shape[0], half)
+            head = rows[:, :nsync * per].cpu().numpy().astype(np.float64)
+            for r, (li, side, s0) in enumerate(members):
+                pix[(li, side)] = med[r]
+                if side == "A":
+                    sync_px[li] = head[r].reshape(nsync, per)
+        # calibration strips in front of each sync (:370-378)
+        lenStrip = int((len(constants.NOAA_SYNCA) * constants.NOAA_T) * fs)
+        lenStrip2 = int((len(constants.NOAA_SYNCB) * constants.NOAA_T) * fs)
+
+        def strip_medians(starts, ln):
+            vals = np.full(len(starts), np.nan)
+            ok = [i for i, s0 in enumerate(starts) if s0 - ln >= 0]
+            if ok and ln > 0:
+                vals[ok] = _row_medians(sig, starts=[starts[i] - ln for i in ok], length=ln)
+            for i, s0 in enumerate(starts):
+                if i not in ok:                 # negative start: numpy slice semantics (usually empty -> nan)
+                    piece = sig[s0 - ln:s0].cpu().numpy()
+                    vals[i] = np.median(piece) if piece.size else np.nan
+            return vals
+        stripA = strip_medians([l[1] for l in lines], lenStrip)
+        stripB = strip_medians([l[3] for l in lines], lenStrip2)
+
+        # ---- host: colour-calibration state machine over the precomputed lines -------
+        image, imageBuffer, backupImage = [], [], []
+        lowFifo, highFifo = [], []
+        corrfifo, corrfifosig, corrfifosig2 = [], [], []
+        ncorrfifo = 3
+        lcorr = lcorrsig = None
+        statecorr = 0
+        valuesPixCorr, valuesSigCorr = [], []
+        chidFifo1, chidFifo2 = [], []
+        fifoLen = constants.NOAA_COLORCORRECT_FIFOLEN
+
+        def quantise(v):
+            v = np.round(v)
+            v[v < 0] = 0
+            v[v > 255] = 255
+            return v.astype(np.uint8)
+
+        for li, (k, sA, eA, sB, eB) in enumerate(lines):
+            if pix.get((li, "A")) is None or pix.get((li, "B")) is None:
+                raise ValueError("cannot reshape array of size 0 into shape (%d,0)" % half)
+            if csyncA[k] in ucsync:
+                pxA = sync_px[li]
+                for j in range(nsync):
+                    if constants.NOAA_SYNCA[j] == 0:
+                        lowFifo.extend(pxA[j])
+                    else:
+                        highFifo.extend(pxA[j])
+                    lowFifo = lowFifo[-fifoLen:]
+                    highFifo = highFifo[-fifoLen:]
+                val11, val244 = np.median(lowFifo), np.median(highFifo)
+                self._low = val11 - (val244 - val11) * (11 - 0) / (244 - 11)
+                self._high = val11 - (val244 - val11) * (11 - 255) / (244 - 11)
+            stripVal = stripA[li]
+            corrfifo = (corrfifo + [255 * (stripVal - self._low) / (self._high - self._low)])[-ncorrfifo:]
+            outcorr = np.median(corrfifo)
+            corrfifosig = (corrfifosig + [stripVal])[-ncorrfifo:]
+            outcorrsig = np.median(corrfifosig)
+            corrfifosig2 = (corrfifosig2 + [stripB[li]])[-ncorrfifo:]
+            outcorrsig2 = np.median(corrfifosig2)
+            chidFifo1 = (chidFifo1 + [outcorrsig2])[-100:]
+            chidFifo2 = (chidFifo2 + [outcorrsig])[-100:]
+            # telemetry wedge tracker (:386-425): eight rising steps then a big drop = one frame
+            if lcorr is None or abs(outcorr - lcorr) > 255.0 / 16:
+                if statecorr == 0 and lcorrsig is not None:
+                    valuesPixCorr = [lcorr, outcorr]
+                    valuesSigCorr = [lcorrsig, outcorrsig]
+                    statecorr = 1
+                elif 1 <= statecorr <= 6:
+                    if outcorr - valuesPixCorr[-1] > 2 * 255.0 / (8 * 3):
+                        valuesPixCorr.append(outcorr)
+                        valuesSigCorr.append(outcorrsig)
+                        statecorr += 1
+                    else:
+                        statecorr = 0
+                elif statecorr == 7:
+                    if valuesPixCorr[-1] - outcorr > 2 * 255.0 / 3:
+                        valuesPixCorr = [outcorr] + valuesPixCorr
+                        valuesSigCorr = [outcorrsig] + valuesSigCorr
+                        from scipy import stats
+                        self._slope, self._intercept = stats.linregress(
+                            valuesSigCorr, np.arange(9) * 255.0 / 8)[:2]
+                        if len(chidFifo1) > 1 + 64 + 8:
+                            self._chIDA = int(np.round((self._slope * np.median(chidFifo1[-1 - 64 - 8:-1 - 64])
+                                                        + self._intercept) / (255.0 / 8)))
+                            self._chIDB = int(np.round((self._slope * np.median(chidFifo2[-1 - 64 - 8:-1 - 64])
+                                                        + self._intercept) / (255.0 / 8)))
+                        chidFifo1, chidFifo2 = [], []
+                    statecorr = 0
+            lcorr, lcorrsig = outcorr, outcorrsig
+            row = np.concatenate([pix[(li, "A")], pix[(li, "B")]])
+            if self._slope is None or self._intercept is None:
+                imageBuffer.append(row[:])
+                backupImage.append(quantise(255 * (row - self._low) / (self._high - self._low)))
+            else:
+                for old in imageBuffer:
+                    image.append(quantise(old * self._slope + self._intercept))
+                imageBuffer = []
+                image.append(quantise(row * self._slope + self._intercept))
+        if len(image) == 0:
+            image = backupImage
+        lens = [len(i) for i in image]
+        accepted = max(set(lens), key=lens.count)
+        self._image = np.array([i for i in image if len(i) == accepted])
+        logging.info('Image extraction complete')
+        return self._image
 
     # ---- properties -------------------------------------------------------------------
     @property

@@ -214,6 +214,16 @@ int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double
 int ddm_bank4(int device, const void *x_dev, int64_t n, int x_is_f64, const double *taps4_host, int nbuf,
               void *out_f32_dev, void *stream);
 
+/* ---- image-line assembly helpers (decode_noaa.getImage, decode_noaa.py:255-465) ---------
+ * signal.resample of many equal-length rows of one f32 array in one batch: row r is
+ * x[row_start[r] : row_start[r] + n] -> out[r][0:num]   (decode_noaa.py:350-351) */
+int ddm_resample_rows(ddm_fft *c, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t n,
+                      int64_t num, void *out_dev, void *stream);
+/* np.median of rows of one f32 array: out[r] = median(x[s : s + row_len]), s = row_start[r], or
+ * r * row_stride when row_start_dev is NULL; out f64 on the device (decode_noaa.py:317,355,372,452) */
+int ddm_row_medians(int device, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t row_stride,
+                    int64_t row_len, void *out_f64_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

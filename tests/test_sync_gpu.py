@@ -146,3 +146,24 @@ def test_afsk_bank_matches_oracle():
         nbuf = int(np.round(bw / 1200))
         assert np.all(got[max(0, n - nbuf):] == 0)
         assert O.rel_rms(got, want) <= TOL
+
+
+def test_noaa_pass_matches_unmodified_reference(golden):
+    """The whole NOAA APT decode of a synthetic 14 s pass against what the UNMODIFIED reference
+    produced for the same input (oracle/gen_golden_noaa.py): sync positions bit-exact, image
+    pixels within +-1 LSB on >= 99.9 % of pixels (BASELINE.json north_star)."""
+    from directdemod_b200 import decode_noaa
+    g = golden("noaa_pass")
+    x = apt_iq(int(g["seed"]), float(g["seconds"]), fs=int(g["fs"]), f_off=float(g["f_off"]))
+    assert abs(float(np.abs(x[::1000]).sum()) - float(g["input_checksum"][0])) < 1e-3, "generator drifted"
+    dec = decode_noaa.decode_noaa(ArraySource(x, int(g["fs"])), float(g["f_off"]))
+    syncA, syncB = dec.getCrudeSync()
+    assert dec.useful == int(g["useful"]) == 1
+    assert np.array_equal(np.asarray(syncA), g["syncA"])
+    assert np.array_equal(np.asarray(syncB), g["syncB"])
+    img = dec.getImage
+    want = g["image"]
+    assert img.dtype == np.uint8 and img.shape == want.shape
+    diff = np.abs(img.astype(np.int32) - want.astype(np.int32))
+    frac = float(np.mean(diff <= 1))
+    assert frac >= 0.999, (frac, int(diff.max()))
