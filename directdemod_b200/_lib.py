@@ -47,6 +47,7 @@ SIGNATURES = {
     "ddm_fm_demod": (_int, [_int, _vp, _i64, _vp, _vp, _pi64, _vp]),
     "ddm_fm_angle_diff": (_int, [_int, _vp, _i64, _vp, _vp, _vp, _pi64, _vp]),
     "ddm_abs": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
+    "ddm_sign": (_int, [_int, _vp, _i64, _vp, _vp]),
     "ddm_stride_copy": (_int, [_int, _vp, _i64, _int, _i64, _i64, _vp, _pi64, _vp]),
     "ddm_medfilt": (_int, [_int, _vp, _i64, _int, _vp, _vp]),
     "ddm_cu8_to_cf32": (_int, [_int, _vp, _i64, _vp, _vp]),

@@ -119,6 +119,14 @@ __global__ void abs_kernel<float>(const float *x, float *out, long long n) {
         out[i] = fabsf(x[i]);
 }
 
+__global__ void sign_kernel(const float *x, float *out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const float v = x[i];
+        out[i] = v > 0.f ? 1.f : (v < 0.f ? -1.f : v);       // np.sign: 0 -> 0, nan -> nan
+    }
+}
+
 template <typename T>
 __global__ void stride_copy_kernel(const T *x, T *out, long long m, long long off, long long step) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -367,6 +375,19 @@ int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_
     else
         abs_kernel<float><<<ops_grid(device, n), kOpsThreads, 0, st>>>(
             static_cast<const float *>(x_dev), static_cast<float *>(out_dev), n);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_sign(int device, const void *x_dev, int64_t n, void *out_dev, void *stream) {
+    DDM_REQUIRE(n >= 0, "ddm_sign: negative length");
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_sign: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_sign");
+    DeviceGuard guard(device);
+    sign_kernel<<<ops_grid(device, n), kOpsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float *>(x_dev), static_cast<float *>(out_dev), n);
     DDM_CUDA(cudaGetLastError());
     count_launch();
     return DDM_OK;

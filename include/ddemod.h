@@ -125,6 +125,8 @@ int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev
                       void *out_dev, void *last_angle_dev, int64_t *n_out, void *stream);
 /* np.abs of a cf32 (is_complex) or f32 array -> f32   (demod_am.py:29,62) */
 int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_dev, void *stream);
+/* np.sign of an f32 array (decode_afsk1200.py:157) */
+int ddm_sign(int device, const void *x_dev, int64_t n, void *out_dev, void *stream);
 /* comm.py:127  out = x[offset::step]; elem_bytes 4 (f32), 8 (cf32) or 16 (c128) */
 int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, int64_t offset,
                     int64_t step, void *out_dev, int64_t *n_out, void *stream);

@@ -167,3 +167,56 @@ def test_noaa_pass_matches_unmodified_reference(golden):
     diff = np.abs(img.astype(np.int32) - want.astype(np.int32))
     frac = float(np.mean(diff <= 1))
     assert frac >= 0.999, (frac, int(diff.max()))
+
+
+def test_afsk_front_end_matches_oracle():
+    """decode_afsk1200.getMsg up to the bit-edge correlation (decode_afsk1200.py:62-158) on a
+    synthetic FM-modulated AFSK stream at 960 kHz IQ with bw = 48000 (at a literal
+    48 kHz IQ rate the reference's own 151-tap filter wipes the packet out)."""
+    import scipy.signal as sps
+    from directdemod_b200 import afsk
+    rng = np.random.default_rng(6)
+    fs, bw, n = 960000, 48000, 1500000
+    t = np.arange(n) / fs
+    bits = rng.integers(0, 2, int(n / fs * 1200) + 2)
+    tone = np.where(bits[(t * 1200).astype(int)] == 1, 1200.0, 2200.0)
+    audio = np.sin(2 * np.pi * np.cumsum(tone) / fs)
+    x = (50 * np.exp(1j * 2 * np.pi * 3000 * np.cumsum(audio) / fs)
+         + 1.0 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    sig, bf, changes = afsk.front_end(ArraySource(x, fs), 0.0, bw, exact_iir=True)
+    # oracle
+    taps = O.taps_blackman_harris(151)[0]
+    iq, rate = O.chain_stream(x, fs, 0.0, taps, bw, demod=False)
+    assert rate == sig.sampRate == 48000
+    fm, _ = O.fm_discriminator(iq, None)
+    b, a = O.taps_butter(rate, 700, 2700, n=6, kind=O.FLT_BP)
+    aud, _ = O.filt_stateful(b, a, fm, O.initial_zi(b, a))
+    want_bf = O.afsk_bank(aud, bw)
+    spb = bw // 1200
+    kernel = np.ones(spb)
+    kernel[:spb // 2] = -1
+    want_ch = np.correlate(np.sign(want_bf), kernel, mode="same") / spb
+    # the band-pass output agrees to the filter's own roundoff floor (its input differs from the
+    # float64 oracle's by the fp32 rounding of the FM stage)
+    floor = 10 * b_floor(b, a)
+    assert O.rel_rms(sig.signal, aud) <= max(TOL, floor)
+    got_bf = bf.cpu().numpy()
+    assert O.rel_rms(got_bf, want_bf) <= max(10 * TOL, 2 * floor)
+    got_ch = changes.cpu().numpy()
+    assert got_ch.shape == want_ch.shape
+    # bit decisions: the edge correlation is built from signs, so it is exact wherever no sample of
+    # its window sat within rounding distance of zero
+    assert np.mean(np.abs(got_ch - want_ch) < 1e-9) >= 0.999
+    strong = np.abs(want_ch) > 0.5
+    assert np.array_equal(np.sign(got_ch[strong]), np.sign(want_ch[strong]))
+
+
+def b_floor(b, a):
+    import ctypes as C
+    from directdemod_b200 import _lib
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    w, nf = C.c_int64(), C.c_double()
+    _lib.check(_lib.lib().ddm_iir_analyse(b.ctypes.data_as(C.POINTER(C.c_double)), len(b),
+                                          a.ctypes.data_as(C.POINTER(C.c_double)), len(a), C.byref(w), C.byref(nf)), "analyse")
+    return nf.value
