@@ -52,8 +52,8 @@ constexpr bool kChainPacked = DDM_CHAIN_FFMA2 != 0;
 constexpr int kChainUnroll = DDM_CHAIN_UNROLL;   // 4-sample bodies per loop trip
 
 struct ChainParams {
-    const float2 *x;       // chunk, n samples
-    const float2 *halo;    // H samples that precede the chunk
+    const void *x;         // chunk, n samples (cf32 or interleaved u8 pairs)
+    const void *halo;      // H samples that precede the chunk, same format
     void *out;             // f32 (FM) or cf32 (IQ)
     const float *taps;     // [Q][DP]
     const float2 *rot;     // [DP] exp(-j 2 pi r a)
@@ -70,11 +70,18 @@ struct ChainParams {
 // ------------------------------------------------------------------------------------
 // fast path: D even, Q <= 8
 // ------------------------------------------------------------------------------------
-template <int Q, bool MIX, int OUT>
+// IN = DDM_IN_CU8: the tile is staged as raw interleaved u8 (2 B/sample, a quarter of the HBM and
+// PCIe traffic of cf32).  The bulk copies need 16-byte alignment, so a tile is copied from the
+// 8-sample boundary below its first sample and every thread indexes with that shift.  The bytes
+// become floats with one PRMT each (0x4B0000bb = 2^23 + b) and one packed add of -(2^23 + 128);
+// the remaining +0.5 of (b - 127.5) is folded into the rotation as the addend 0.5 (1+j) rot[a].
+template <int Q, bool MIX, int OUT, int IN>
 __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm)
 chain_fused_kernel(const ChainParams P) {
     constexpr int NT = kChainThreads;
     constexpr int J = NT - Q;                      // outputs per tile
+    constexpr bool U8 = IN == DDM_IN_CU8;
+    constexpr int ES = U8 ? 2 : 8;                 // bytes per input sample
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
@@ -85,12 +92,14 @@ chain_fused_kernel(const ChainParams P) {
     float *s_taps = reinterpret_cast<float *>(smem_raw + 32);                // Q*DP taps
     float *s_rx = s_taps + Q * DP;                                           // DP: cos
     float2 *s_ry = reinterpret_cast<float2 *>(s_rx + DP);                    // DP: (sin, -sin) = (-ry, ry)
-    float2 *s_e = s_ry + DP;                                                 // kChainEBufs*Q*NT float2
-    const size_t stage_bytes = static_cast<size_t>(NT) * D * sizeof(float2);
+    float2 *s_c = s_ry + DP;                                                 // DP: 0.5 (1+j) rot (u8 input)
+    float2 *s_e = s_c + DP;                                                  // kChainEBufs*Q*NT float2
+    const size_t stage_bytes = U8 ? ((static_cast<size_t>(NT) * D * 2 + 32 + 15) & ~static_cast<size_t>(15))
+                                  : static_cast<size_t>(NT) * D * sizeof(float2);
     // plain offset arithmetic from the (128-byte aligned) dynamic shared base keeps the pointer in
     // the shared address space: the tile reads must be LDS, not generic loads
     const unsigned fixed_bytes =
-        (32u + 4u * (Q * DP + DP) + 8u * (DP + kChainEBufs * Q * NT) + 127u) & ~127u;
+        (32u + 4u * (Q * DP + DP) + 8u * (2 * DP + kChainEBufs * Q * NT) + 127u) & ~127u;
     unsigned char *s_stage0 = smem_raw + fixed_bytes;
 
     if (tid == 0) {
@@ -102,6 +111,7 @@ chain_fused_kernel(const ChainParams P) {
         const float2 r = P.rot[i];          // (cos, -sin) = exp(-j 2 pi r a)
         s_rx[i] = r.x;
         s_ry[i] = make_float2(-r.y, r.y);
+        s_c[i] = make_float2(0.5f * (r.x - r.y), 0.5f * (r.x + r.y));
     }
     __syncthreads();
 
@@ -114,6 +124,34 @@ chain_fused_kernel(const ChainParams P) {
         const long long S0 = P.b0 + (tile * J - Q) * D;            // first sample (may be < 0)
         long long E = S0 + static_cast<long long>(NT) * D;
         if (E > end_all) E = end_all;
+        if (U8) {
+            const unsigned char *xb = static_cast<const unsigned char *>(P.x);
+            const unsigned char *hb = static_cast<const unsigned char *>(P.halo);
+            const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;          // floor to 8 samples = 16 B
+            const long long Ea = (E >= 0 ? E + 7 : E) / 8 * 8;              // ceil to 8 samples
+            const long long n8 = P.n & ~7LL;
+            const long long h_end = Ea < 0 ? Ea : 0;
+            const long long c_beg = S0a > 0 ? S0a : 0;
+            const long long c_end = Ea < n8 ? Ea : n8;
+            uint32_t bytes = 0;
+            if (S0a < 0) bytes += static_cast<uint32_t>((h_end - S0a) * 2);
+            if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 2);
+            // tail: the last n % 8 samples of the chunk and the pad behind them (zero-tap positions)
+            const long long t_beg = c_beg > n8 ? c_beg : n8;
+            for (long long i = t_beg; i < E; ++i) {
+                dst[(i - S0a) * 2] = i < P.n ? xb[2 * i] : 128;
+                dst[(i - S0a) * 2 + 1] = i < P.n ? xb[2 * i + 1] : 128;
+            }
+            mbar_arrive_expect_tx(&mbar[stage], bytes);
+            if (S0a < 0)
+                bulk_g2s(dst, hb + (P.H + S0a) * 2, static_cast<uint32_t>((h_end - S0a) * 2), &mbar[stage]);
+            if (c_end > c_beg)
+                bulk_g2s(dst + (c_beg - S0a) * 2, xb + c_beg * 2, static_cast<uint32_t>((c_end - c_beg) * 2),
+                         &mbar[stage]);
+            return;
+        }
+        const float2 *xf = static_cast<const float2 *>(P.x);
+        const float2 *hf = static_cast<const float2 *>(P.halo);
         uint32_t bytes = 0;
         const long long h_end = E < 0 ? E : 0;
         const long long c_beg = S0 > 0 ? S0 : 0;
@@ -123,14 +161,14 @@ chain_fused_kernel(const ChainParams P) {
         // tail: the odd last sample of the chunk and the zero pad behind it
         long long t_beg = c_beg > n_even ? c_beg : n_even;
         for (long long i = t_beg; i < E; ++i) {
-            float2 v = i < P.n ? P.x[i] : make_float2(0.f, 0.f);
+            float2 v = i < P.n ? xf[i] : make_float2(0.f, 0.f);
             reinterpret_cast<float2 *>(dst)[i - S0] = v;
         }
         mbar_arrive_expect_tx(&mbar[stage], bytes);
         if (S0 < 0)
-            bulk_g2s(dst, P.halo + (P.H + S0), static_cast<uint32_t>((h_end - S0) * 8), &mbar[stage]);
+            bulk_g2s(dst, hf + (P.H + S0), static_cast<uint32_t>((h_end - S0) * 8), &mbar[stage]);
         if (c_end > c_beg)
-            bulk_g2s(dst + (c_beg - S0) * 8, P.x + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8),
+            bulk_g2s(dst + (c_beg - S0) * 8, xf + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8),
                      &mbar[stage]);
     };
 
@@ -156,9 +194,13 @@ chain_fused_kernel(const ChainParams P) {
         const long long jblk = tile * J - Q + tid;          // this thread's block index
         float2 *e_buf = s_e + (kChainEBufs == 2 ? (it & 1) * (Q * NT) : 0);
         if (jblk < P.M) {
-            const unsigned char *sp = s_stage0 + stage * stage_bytes +
-                                      static_cast<size_t>(tid) * D * sizeof(float2);
-            const float4 *sp4 = reinterpret_cast<const float4 *>(sp);
+            size_t sp_off = static_cast<size_t>(tid) * D * ES;
+            if (U8) {
+                const long long S0 = P.b0 + (tile * J - Q) * D;
+                const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;
+                sp_off += static_cast<size_t>(S0 - S0a) * 2;         // shift of the aligned copy (even)
+            }
+            const unsigned char *sp = s_stage0 + stage * stage_bytes + sp_off;
             // Packed single precision (FFMA2): accumulators are (re, im) pairs, a tap is a
             // broadcast scalar operand, and the complex rotation is
             //   m = x * cos + swap(x) * (sin, -sin)        (swap = the LO_HI operand selector)
@@ -167,28 +209,52 @@ chain_fused_kernel(const ChainParams P) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
 
-            auto rotate = [&](float xr, float xi, float rx, float2 ry) -> unsigned long long {
-                if (!MIX) return pack_f32x2(xr, xi);
-                const unsigned long long m = fmul2(pack_f32x2(xr, xi), pack_f32x2(rx, rx));
-                return ffma2(pack_f32x2(xi, xr), pack_f32x2(ry.x, ry.y), m);
+            // two consecutive raw samples starting at block position a (a even) as packed pairs
+            auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
+                if (U8) {
+                    const unsigned int w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
+                    const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
+                    X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                          __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
+                    X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
+                                          __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
+                } else {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
+                    X0 = v.x;
+                    X1 = v.y;
+                }
+            };
+            // raw pair -> mixed sample.  cf32: x rot.  u8: (v + 0.5 (1+j)) rot with v = b - 128.
+            auto rotate = [&](unsigned long long X, float rx, float2 ry, float2 c) -> unsigned long long {
+                const float2 x = unpack_f32x2(X);
+                if (!MIX) return U8 ? fadd2(X, pack_f32x2(0.5f, 0.5f)) : X;
+                const unsigned long long m = U8 ? ffma2(X, pack_f32x2(rx, rx), pack_f32x2(c.x, c.y))
+                                                : fmul2(X, pack_f32x2(rx, rx));
+                return ffma2(pack_f32x2(x.y, x.x), pack_f32x2(ry.x, ry.y), m);
             };
             const int D4 = D & ~3;
             int a = 0;
             // four samples against the first NQ partial sums
             auto body4 = [&](auto nq_tag) {
                 constexpr int NQ = decltype(nq_tag)::value;
-                const float4 v0 = sp4[a >> 1], v1 = sp4[(a >> 1) + 1];
+                unsigned long long X0, X1, X2, X3;
+                load2(a, X0, X1);
+                load2(a + 2, X2, X3);
                 float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0;
+                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0, c0 = ry0, c1 = ry0;
                 if (MIX) {
                     rx = *reinterpret_cast<const float4 *>(s_rx + a);
                     ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
                     ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
+                    if (U8) {
+                        c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                        c1 = *reinterpret_cast<const float4 *>(s_c + a + 2);
+                    }
                 }
-                const unsigned long long M0 = rotate(v0.x, v0.y, rx.x, make_float2(ry0.x, ry0.y));
-                const unsigned long long M1 = rotate(v0.z, v0.w, rx.y, make_float2(ry0.z, ry0.w));
-                const unsigned long long M2 = rotate(v1.x, v1.y, rx.z, make_float2(ry1.x, ry1.y));
-                const unsigned long long M3 = rotate(v1.z, v1.w, rx.w, make_float2(ry1.z, ry1.w));
+                const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+                const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+                const unsigned long long M2 = rotate(X2, rx.z, make_float2(ry1.x, ry1.y), make_float2(c1.x, c1.y));
+                const unsigned long long M3 = rotate(X3, rx.w, make_float2(ry1.z, ry1.w), make_float2(c1.z, c1.w));
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
@@ -206,15 +272,17 @@ chain_fused_kernel(const ChainParams P) {
 #pragma unroll(kChainUnroll)
             for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
             if (a < D) {                                    // D % 4 == 2 (D is even on this path)
-                const float4 v0 = sp4[a >> 1];
+                unsigned long long X0, X1;
+                load2(a, X0, X1);
                 float2 rx = make_float2(1.f, 1.f);
-                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = ry0;
                 if (MIX) {
                     rx = *reinterpret_cast<const float2 *>(s_rx + a);
                     ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                    if (U8) c0 = *reinterpret_cast<const float4 *>(s_c + a);
                 }
-                const unsigned long long M0 = rotate(v0.x, v0.y, rx.x, make_float2(ry0.x, ry0.y));
-                const unsigned long long M1 = rotate(v0.z, v0.w, rx.y, make_float2(ry0.z, ry0.w));
+                const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+                const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
@@ -270,14 +338,25 @@ chain_fused_kernel(const ChainParams P) {
 // Correct for every configuration; used when the fast path's constraints do not hold.
 // ------------------------------------------------------------------------------------
 struct GenericParams {
-    const float2 *x;
-    const float2 *halo;
+    const void *x;
+    const void *halo;
     double2 *y;            // y[m+1] for m = -1..M-1
     const double *taps;    // K taps
     long long n, n0, M, off;
+    long long virt_before; // chunk-relative index below which history is virtual: the mixed value
+                           // is 1.0 there (the all-ones history behind lfilter_zi, filters.py:45)
     double r_hi, r_lo;
-    int K, D, H, mix;
+    int K, D, H, mix, in_format;
 };
+
+__device__ __forceinline__ float2 chain_fetch(const void *x, const void *halo, int H, long long i, int in_format) {
+    if (in_format == DDM_IN_CU8) {
+        const unsigned char *p = i >= 0 ? static_cast<const unsigned char *>(x) + 2 * i
+                                        : static_cast<const unsigned char *>(halo) + 2 * (H + i);
+        return make_float2(static_cast<float>(p[0]) - 127.5f, static_cast<float>(p[1]) - 127.5f);
+    }
+    return i >= 0 ? static_cast<const float2 *>(x)[i] : static_cast<const float2 *>(halo)[H + i];
+}
 
 __global__ void chain_generic_y_kernel(const GenericParams P) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -290,8 +369,13 @@ __global__ void chain_generic_y_kernel(const GenericParams P) {
     for (int k = 0; k < P.K; ++k) {
         const long long i = pos - k;
         if (i < -static_cast<long long>(P.H)) break;
-        float2 v = i >= 0 ? P.x[i] : P.halo[P.H + i];
-        if (P.mix) v = cmul(v, phase_rotator(P.r_hi, P.r_lo, P.n0 + i));
+        float2 v;
+        if (i < P.virt_before) {
+            v = make_float2(1.f, 0.f);
+        } else {
+            v = chain_fetch(P.x, P.halo, P.H, i, P.in_format);
+            if (P.mix) v = cmul(v, phase_rotator(P.r_hi, P.r_lo, P.n0 + i));
+        }
         const double t = P.taps[k];
         ax = fma(t, static_cast<double>(v.x), ax);
         ay = fma(t, static_cast<double>(v.y), ay);
@@ -335,8 +419,10 @@ struct ddm_chain {
     float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
     double *d_taps_lin = nullptr;            // K
     float2 *d_rot = nullptr;                 // DP
-    float2 *d_halo[2] = {nullptr, nullptr};
-    float2 *d_halo_init = nullptr;           // the reference's initial condition as raw history
+    void *d_halo[2] = {nullptr, nullptr};    // H samples of raw input in the handle's input format
+    void *d_halo_init = nullptr;             // the reference's initial condition as raw history (cf32)
+    int es = 8;                              // bytes per input sample
+    long long n_real = 0;                    // real samples in the halo (u8: the rest is virtual)
     int cur = 0;
     double2 *d_ytmp = nullptr;
     size_t ytmp_cap = 0;
@@ -350,17 +436,20 @@ namespace {
 
 using namespace ddm;
 
-size_t chain_smem_bytes(int Q, int D, int DP) {
-    size_t fixed = 32 + sizeof(float) * (Q * DP + DP) + sizeof(float2) * DP +
+size_t chain_smem_bytes(int Q, int D, int DP, int in_format = DDM_IN_CF32) {
+    size_t fixed = 32 + sizeof(float) * (Q * DP + DP) + sizeof(float2) * 2 * DP +
                    sizeof(float2) * kChainEBufs * Q * kChainThreads;
     fixed = (fixed + 127) & ~static_cast<size_t>(127);
-    return fixed + kChainStages * static_cast<size_t>(kChainThreads) * D * sizeof(float2);
+    const size_t stage = in_format == DDM_IN_CU8
+                             ? ((static_cast<size_t>(kChainThreads) * D * 2 + 32 + 15) & ~static_cast<size_t>(15))
+                             : static_cast<size_t>(kChainThreads) * D * sizeof(float2);
+    return fixed + kChainStages * stage;
 }
 
-template <int Q, bool MIX, int OUT>
+template <int Q, bool MIX, int OUT, int IN>
 int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
-    const size_t smem = chain_smem_bytes(Q, c->D, c->DP);
-    auto kern = chain_fused_kernel<Q, MIX, OUT>;
+    const size_t smem = chain_smem_bytes(Q, c->D, c->DP, IN);
+    auto kern = chain_fused_kernel<Q, MIX, OUT, IN>;
     int &per_sm = c->per_sm[p.s];
     if (per_sm == 0) {   // first launch of this variant on this handle's device
         DDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -380,20 +469,26 @@ int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
     return DDM_OK;
 }
 
-template <bool MIX, int OUT>
-int launch_fused_mo(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
+template <bool MIX, int OUT, int IN>
+int launch_fused_moi(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
     switch (Q) {
-        case 1: return launch_fused_q<1, MIX, OUT>(c, p, st);
-        case 2: return launch_fused_q<2, MIX, OUT>(c, p, st);
-        case 3: return launch_fused_q<3, MIX, OUT>(c, p, st);
-        case 4: return launch_fused_q<4, MIX, OUT>(c, p, st);
-        case 5: return launch_fused_q<5, MIX, OUT>(c, p, st);
-        case 6: return launch_fused_q<6, MIX, OUT>(c, p, st);
-        case 7: return launch_fused_q<7, MIX, OUT>(c, p, st);
-        case 8: return launch_fused_q<8, MIX, OUT>(c, p, st);
+        case 1: return launch_fused_q<1, MIX, OUT, IN>(c, p, st);
+        case 2: return launch_fused_q<2, MIX, OUT, IN>(c, p, st);
+        case 3: return launch_fused_q<3, MIX, OUT, IN>(c, p, st);
+        case 4: return launch_fused_q<4, MIX, OUT, IN>(c, p, st);
+        case 5: return launch_fused_q<5, MIX, OUT, IN>(c, p, st);
+        case 6: return launch_fused_q<6, MIX, OUT, IN>(c, p, st);
+        case 7: return launch_fused_q<7, MIX, OUT, IN>(c, p, st);
+        case 8: return launch_fused_q<8, MIX, OUT, IN>(c, p, st);
     }
     set_error("internal: Q=%d out of range", Q);
     return DDM_ERR_UNSUPPORTED;
+}
+
+template <bool MIX, int OUT>
+int launch_fused_mo(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
+    return c->in_format == DDM_IN_CU8 ? launch_fused_moi<MIX, OUT, DDM_IN_CU8>(c, Q, p, st)
+                                      : launch_fused_moi<MIX, OUT, DDM_IN_CF32>(c, Q, p, st);
 }
 
 int launch_fused(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
@@ -438,6 +533,13 @@ int build_initial_halo(ddm_chain *c) {
 }
 
 int fill_initial_halo(ddm_chain *c, cudaStream_t st) {
+    c->n_real = 0;
+    if (c->in_format == DDM_IN_CU8) {
+        // u8 cannot encode the all-ones mixed history: it is kept virtual (n_real = 0) and the
+        // first H samples of a fresh stream go through the general kernel, which knows about it
+        DDM_CUDA(cudaMemsetAsync(c->d_halo[c->cur], 128, static_cast<size_t>(c->es) * c->H, st));
+        return DDM_OK;
+    }
     DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], c->d_halo_init, sizeof(float2) * c->H,
                              cudaMemcpyDeviceToDevice, st));
     return DDM_OK;
@@ -456,10 +558,8 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     DDM_REQUIRE(samp_rate > 0, "ddm_chain_create: sampling rate must be positive");
     DDM_REQUIRE(out_mode == DDM_CHAIN_OUT_FM || out_mode == DDM_CHAIN_OUT_IQ,
                 "ddm_chain_create: bad out_mode %d", out_mode);
-    if (in_format != DDM_IN_CF32) {
-        set_error("ddm_chain_create: input format %d not implemented", in_format);
-        return DDM_ERR_UNSUPPORTED;
-    }
+    DDM_REQUIRE(in_format == DDM_IN_CF32 || in_format == DDM_IN_CU8, "ddm_chain_create: bad in_format %d",
+                in_format);
     int ndev = 0;
     DDM_CUDA(cudaGetDeviceCount(&ndev));
     DDM_REQUIRE(device >= 0 && device < ndev, "ddm_chain_create: no such device %d", device);
@@ -487,10 +587,12 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     const int D = decim, K = ntaps;
     const int qmax = (K + 1 + D - 1) / D;
     c->DP = (D + 3) & ~3;
+    c->es = in_format == DDM_IN_CU8 ? 2 : 8;
     c->fast = (D % 2 == 0) && qmax <= kChainMaxQ &&
-              chain_smem_bytes(qmax, D, c->DP) <= 227 * 1024;
+              chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024;
     c->H = (qmax + 1) * D;
     if (c->H & 1) c->H += 1;
+    if (in_format == DDM_IN_CU8) c->H = (c->H + 7) / 8 * 8 + 8;   // aligned tile copies may start 7 samples early
 
     auto fail = [&](int code) {
         ddm_chain_destroy(c);
@@ -498,7 +600,7 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     };
     cudaError_t e;
     for (int i = 0; i < 2; ++i) {
-        e = cudaMalloc(&c->d_halo[i], sizeof(float2) * c->H);
+        e = cudaMalloc(&c->d_halo[i], static_cast<size_t>(c->es) * c->H);
         if (e != cudaSuccess) {
             set_error("cudaMalloc(halo) failed: %s", cudaGetErrorString(e));
             return fail(DDM_ERR_NOMEM);
@@ -622,15 +724,16 @@ int ddm_chain_set_position(ddm_chain *c, int64_t n0, int64_t dec_off, int has_pr
     c->dec_off = dec_off;
     c->has_prev = has_prev ? 1 : 0;
     if (halo_dev == nullptr) return fill_initial_halo(c, st);
-    DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], halo_dev, sizeof(float2) * c->H,
+    DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], halo_dev, static_cast<size_t>(c->es) * c->H,
                              cudaMemcpyDeviceToDevice, st));
+    c->n_real = c->H;
     return DDM_OK;
 }
 
 int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream) {
     DDM_REQUIRE(c != nullptr && halo_dev != nullptr, "ddm_chain_get_halo: NULL argument");
     DeviceGuard guard(c->device);
-    DDM_CUDA(cudaMemcpyAsync(halo_dev, c->d_halo[c->cur], sizeof(float2) * c->H,
+    DDM_CUDA(cudaMemcpyAsync(halo_dev, c->d_halo[c->cur], static_cast<size_t>(c->es) * c->H,
                              cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return DDM_OK;
 }
@@ -640,13 +743,26 @@ int ddm_chain_export_state(const ddm_chain *c, double *zi_c128_host, double *las
     DDM_REQUIRE(c != nullptr, "ddm_chain_export_state: NULL handle");
     DeviceGuard guard(c->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    std::vector<float2> h(c->H);
-    DDM_CUDA(cudaMemcpyAsync(h.data(), c->d_halo[c->cur], sizeof(float2) * c->H, cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned char> raw(static_cast<size_t>(c->es) * c->H);
+    DDM_CUDA(cudaMemcpyAsync(raw.data(), c->d_halo[c->cur], raw.size(), cudaMemcpyDeviceToHost, st));
     DDM_CUDA(cudaStreamSynchronize(st));
     // mixed history x'[g], g = n0-H .. n0-1, rounded to complex64 like the reference's in-place mixer
     std::vector<double> xr(c->H), xi(c->H);
+    const bool u8 = c->in_format == DDM_IN_CU8;
     for (int i = 0; i < c->H; ++i) {
-        double re = h[i].x, im = h[i].y;
+        if (u8 && i < c->H - c->n_real) {            // virtual history: the all-ones mixed signal
+            xr[i] = 1.0;
+            xi[i] = 0.0;
+            continue;
+        }
+        double re, im;
+        if (u8) {
+            re = static_cast<double>(raw[2 * i]) - 127.5;
+            im = static_cast<double>(raw[2 * i + 1]) - 127.5;
+        } else {
+            re = reinterpret_cast<const float2 *>(raw.data())[i].x;
+            im = reinterpret_cast<const float2 *>(raw.data())[i].y;
+        }
         if (c->mix) {
             const double g = static_cast<double>(c->n0 - c->H + i);
             const double p = c->r_hi * g;
@@ -695,6 +811,10 @@ int ddm_chain_export_state(const ddm_chain *c, double *zi_c128_host, double *las
     return DDM_OK;
 }
 
+namespace {
+int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev, int64_t *n_out, cudaStream_t st);
+}
+
 int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
                         int64_t out_capacity, int64_t *n_out, void *stream) {
     DDM_REQUIRE(c != nullptr, "ddm_chain_apply_dev: NULL handle");
@@ -702,7 +822,6 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
     DDM_REQUIRE(n == 0 || x_dev != nullptr, "ddm_chain_apply_dev: NULL input");
     DeviceGuard guard(c->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int64_t M = positions_in(c, n);
     int64_t produced = 0;
     ddm_chain_out_count(c, n, &produced);
     if (n_out) *n_out = produced;
@@ -712,16 +831,44 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
         return DDM_ERR_CAPACITY;
     }
     DDM_REQUIRE(produced == 0 || out_dev != nullptr, "ddm_chain_apply_dev: NULL output");
-    const float2 *x = static_cast<const float2 *>(x_dev);
+    // A fresh u8 stream has virtual history the fused kernel cannot stage: its first H samples go
+    // through the general kernel (as one piece), the rest through the fused kernel.
+    const unsigned char *xb = static_cast<const unsigned char *>(x_dev);
+    unsigned char *ob = static_cast<unsigned char *>(out_dev);
+    const size_t oes = c->out_mode == DDM_CHAIN_OUT_IQ ? sizeof(float2) : sizeof(float);
+    int64_t done = 0;
+    while (done < n || (n == 0 && done == 0)) {
+        int64_t piece = n - done;
+        if (c->in_format == DDM_IN_CU8 && c->fast && c->n_real < c->H && piece > c->H - c->n_real)
+            piece = c->H - c->n_real;
+        int64_t got = 0;
+        int rc = chain_apply_piece(c, xb + static_cast<size_t>(done) * c->es, piece, ob, &got, st);
+        if (rc != DDM_OK) return rc;
+        ob += static_cast<size_t>(got) * oes;
+        done += piece;
+        if (n == 0) break;
+    }
+    return DDM_OK;
+}
+
+namespace {
+int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev, int64_t *n_out, cudaStream_t st) {
+    const int64_t M = positions_in(c, n);
+    int64_t produced = 0;
+    ddm_chain_out_count(c, n, &produced);
+    *n_out = produced;
+    const unsigned char *x = static_cast<const unsigned char *>(x_dev);
     const int D = c->D;
+    const size_t es = static_cast<size_t>(c->es);
 
     if (M > 0) {
         const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0;
-        if (c->fast && aligned) {
+        const bool history_ok = c->in_format != DDM_IN_CU8 || c->n_real >= c->H;
+        if (c->fast && aligned && history_ok) {
             const int s = static_cast<int>((c->dec_off + 1) & 1);
             const int Q = c->Q[s];
             ChainParams p{};
-            p.x = x;
+            p.x = x_dev;
             p.halo = c->d_halo[c->cur];
             p.out = out_dev;
             p.taps = c->d_taps[s];
@@ -753,7 +900,7 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
                 c->ytmp_cap = need;
             }
             GenericParams g{};
-            g.x = x;
+            g.x = x_dev;
             g.halo = c->d_halo[c->cur];
             g.y = c->d_ytmp;
             g.taps = c->d_taps_lin;
@@ -767,6 +914,8 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
             g.D = D;
             g.H = c->H;
             g.mix = c->mix ? 1 : 0;
+            g.in_format = c->in_format;
+            g.virt_before = c->in_format == DDM_IN_CU8 ? -c->n_real : -static_cast<long long>(c->H) - 1;
             const int tb = 128;
             chain_generic_y_kernel<<<static_cast<unsigned>((M + 1 + tb - 1) / tb), tb, 0, st>>>(g);
             DDM_CUDA(cudaGetLastError());
@@ -779,22 +928,23 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n, void *out_de
 
     // ---- carry: halo <- last H samples of (halo ++ x) ----
     if (n >= c->H) {
-        DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], x + (n - c->H), sizeof(float2) * c->H,
-                                 cudaMemcpyDeviceToDevice, st));
+        DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], x + (n - c->H) * es, es * c->H, cudaMemcpyDeviceToDevice, st));
     } else if (n > 0) {
         const int nxt = c->cur ^ 1;
-        DDM_CUDA(cudaMemcpyAsync(c->d_halo[nxt], c->d_halo[c->cur] + n, sizeof(float2) * (c->H - n),
-                                 cudaMemcpyDeviceToDevice, st));
-        DDM_CUDA(cudaMemcpyAsync(c->d_halo[nxt] + (c->H - n), x, sizeof(float2) * n,
-                                 cudaMemcpyDeviceToDevice, st));
+        const unsigned char *old = static_cast<const unsigned char *>(c->d_halo[c->cur]);
+        unsigned char *neu = static_cast<unsigned char *>(c->d_halo[nxt]);
+        DDM_CUDA(cudaMemcpyAsync(neu, old + n * es, es * (c->H - n), cudaMemcpyDeviceToDevice, st));
+        DDM_CUDA(cudaMemcpyAsync(neu + (c->H - n) * es, x, es * n, cudaMemcpyDeviceToDevice, st));
         c->cur = nxt;
     }
+    c->n_real = std::min<long long>(c->H, c->n_real + n);
     // comm.py:124  nextOff = (j - (len - off) % j) % j   (python modulo)
     c->dec_off = positive_mod(D - positive_mod(n - c->dec_off, D), D);
     c->n0 += n;
     if (M > 0) c->has_prev = 1;
     return DDM_OK;
 }
+}  // namespace
 
 int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_host,
                          int64_t out_capacity, int64_t *n_out, void *stream) {
@@ -811,7 +961,7 @@ int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_
                   static_cast<long long>(produced), static_cast<long long>(out_capacity));
         return DDM_ERR_CAPACITY;
     }
-    const size_t in_bytes = sizeof(float2) * static_cast<size_t>(n);
+    const size_t in_bytes = static_cast<size_t>(c->es) * static_cast<size_t>(n);
     const size_t out_elem = c->out_mode == DDM_CHAIN_OUT_IQ ? sizeof(float2) : sizeof(float);
     const size_t out_bytes = out_elem * static_cast<size_t>(produced);
     if (in_bytes > c->in_cap) {

@@ -29,7 +29,10 @@ def _stream_ptr(device_index):
 
 
 class FusedChain:
-    def __init__(self, taps, decim, freq_offset, samp_rate, demod=True, device=None):
+    def __init__(self, taps, decim, freq_offset, samp_rate, demod=True, device=None, in_format="cf32"):
+        """in_format: "cf32" (complex64 samples) or "cu8" (interleaved unsigned 8-bit I/Q exactly as
+        an RTL-SDR recording stores them; the kernel applies source.py:117's ``- 127.5`` itself and
+        moves a quarter of the bytes)."""
         torch = _torch()
         if not torch.cuda.is_available():
             raise RuntimeError("directdemod_b200 needs a CUDA device; there is no CPU fallback")
@@ -43,11 +46,15 @@ class FusedChain:
         self.freq_offset = float(freq_offset)
         self.samp_rate = float(samp_rate)
         self.demod = bool(demod)
+        if in_format not in ("cf32", "cu8"):
+            raise ValueError("in_format must be 'cf32' or 'cu8'")
+        self.in_format = in_format
         h = C.c_void_p()
         _lib.check(self._l.ddm_chain_create(
             self.device, taps.ctypes.data_as(C.POINTER(C.c_double)), self.ntaps, self.decim,
             self.freq_offset, self.samp_rate,
-            _lib.CHAIN_OUT_FM if demod else _lib.CHAIN_OUT_IQ, _lib.IN_CF32, C.byref(h)),
+            _lib.CHAIN_OUT_FM if demod else _lib.CHAIN_OUT_IQ,
+            _lib.IN_CU8 if in_format == "cu8" else _lib.IN_CF32, C.byref(h)),
             "ddm_chain_create")
         self._h = h
         n = C.c_int64()
@@ -84,8 +91,10 @@ class FusedChain:
         ptr = C.c_void_p(0)
         if halo is not None:
             torch = _torch()
-            if halo.dtype != torch.complex64 or not halo.is_cuda or halo.numel() != self.halo_len:
-                raise ValueError("halo must be a cuda complex64 tensor of halo_len samples")
+            want = torch.uint8 if self.in_format == "cu8" else torch.complex64
+            count = 2 * self.halo_len if self.in_format == "cu8" else self.halo_len
+            if halo.dtype != want or not halo.is_cuda or halo.numel() != count:
+                raise ValueError("halo must be a cuda %s tensor of halo_len samples" % want)
             halo = halo.contiguous()
             ptr = C.c_void_p(halo.data_ptr())
         _lib.check(self._l.ddm_chain_set_position(self._h, int(n0), int(dec_off), int(bool(has_prev)),
@@ -94,7 +103,10 @@ class FusedChain:
 
     def get_halo(self):
         torch = _torch()
-        out = torch.empty(self.halo_len, dtype=torch.complex64, device="cuda:%d" % self.device)
+        if self.in_format == "cu8":
+            out = torch.empty((self.halo_len, 2), dtype=torch.uint8, device="cuda:%d" % self.device)
+        else:
+            out = torch.empty(self.halo_len, dtype=torch.complex64, device="cuda:%d" % self.device)
         _lib.check(self._l.ddm_chain_get_halo(self._h, C.c_void_p(out.data_ptr()),
                                               _stream_ptr(self.device)), "ddm_chain_get_halo")
         return out
@@ -121,14 +133,21 @@ class FusedChain:
         """x: cuda complex64 tensor (one chunk).  Returns a cuda tensor (float32 FM output or
         complex64 IQ) holding exactly the samples the reference chain returns for it."""
         torch = _torch()
-        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.complex64):
-            raise TypeError("apply() wants a cuda complex64 tensor; use apply_host() for numpy")
-        if x.dim() != 1:
-            raise TypeError("The signal array must be 1-D")
+        if self.in_format == "cu8":
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.uint8):
+                raise TypeError("apply() wants a cuda uint8 tensor of interleaved I/Q for a cu8 chain")
+            if x.numel() % 2:
+                raise TypeError("interleaved I/Q needs an even number of bytes")
+            n = x.numel() // 2
+        else:
+            if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.complex64):
+                raise TypeError("apply() wants a cuda complex64 tensor; use apply_host() for numpy")
+            if x.dim() != 1:
+                raise TypeError("The signal array must be 1-D")
+            n = x.numel()
         if x.device.index != self.device:
             raise ValueError("tensor is on cuda:%d, chain on cuda:%d" % (x.device.index, self.device))
         x = x.contiguous()
-        n = x.numel()
         m = self.out_count(n)
         dt = torch.float32 if self.demod else torch.complex64
         if out is None:
@@ -147,10 +166,16 @@ class FusedChain:
         chain, copies the result back; returns a numpy array."""
         if hasattr(x, "numpy") and not isinstance(x, np.ndarray):
             x = x.numpy()
-        x = np.ascontiguousarray(x, dtype=np.complex64)
-        if x.ndim != 1:
-            raise TypeError("The signal array must be 1-D")
-        n = x.size
+        if self.in_format == "cu8":
+            x = np.ascontiguousarray(x, dtype=np.uint8).reshape(-1)
+            if x.size % 2:
+                raise TypeError("interleaved I/Q needs an even number of bytes")
+            n = x.size // 2
+        else:
+            x = np.ascontiguousarray(x, dtype=np.complex64)
+            if x.ndim != 1:
+                raise TypeError("The signal array must be 1-D")
+            n = x.size
         m = self.out_count(n)
         dt = np.float32 if self.demod else np.complex64
         if out is None:

@@ -143,3 +143,55 @@ def test_full_chunk_tone_property_and_chunk_invariance():
     assert float((y2 - y).abs().max()) < 1e-5
     ch.close()
     ch2.close()
+
+
+def _u8_iq(seed, n, fs, f, f_mod, beta):
+    """RTL-SDR style recording: unsigned 8-bit interleaved I/Q of an FM tone plus noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / fs
+    ph = 2 * np.pi * f * t + beta * np.sin(2 * np.pi * f_mod * t)
+    z = 70 * np.exp(1j * ph) + 6 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    iq = np.empty((n, 2), dtype=np.uint8)
+    iq[:, 0] = np.clip(np.round(z.real + 127.5), 0, 255)
+    iq[:, 1] = np.clip(np.round(z.imag + 127.5), 0, 255)
+    return iq
+
+
+@pytest.mark.parametrize("ntaps,decim,fs,f,n,ncuts", [
+    (151, 34, 2048000, 30000.0, 400000, 6),
+    (151, 50, 10000000, -125000.0, 300000, 5),
+    (151, 34, 2048000, 0.0, 100000, 3),        # no mixer
+    (492, 64, 2048000, -30000.0, 200000, 4),
+    (151, 33, 2048000, 30000.0, 60000, 4),     # odd decimation -> general path throughout
+])
+@pytest.mark.parametrize("demod", [True, False])
+def test_u8_ingest_matches_oracle(ntaps, decim, fs, f, n, ncuts, demod):
+    """The chain fed with raw unsigned 8-bit I/Q (source.py:117-118: u8 - 127.5, fused into the
+    kernel) equals the oracle run on the converted complex64 samples, for random chunkings that
+    include the fresh-stream hand-over from the general to the fused kernel."""
+    import torch
+    from directdemod_b200.fused import FusedChain
+    iq = _u8_iq(ntaps + decim, n, fs, f, min(fs / decim / 40.0, 0.1 * fs / ntaps), 2.0)
+    x = (iq[:, 0].astype(np.float32) - 127.5) + 1j * (iq[:, 1].astype(np.float32) - 127.5)
+    x = x.astype(np.complex64)
+    taps = O.taps_blackman_harris(ntaps)[0]
+    cuts = random_cuts(decim + 1, n, ncuts, small=2)
+    want, _ = oracle_chain(x, fs, f, taps, fs / decim, cuts, demod)
+    ch = FusedChain(taps, decim, f, fs, demod=demod, in_format="cu8")
+    parts = []
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        if i % 2:
+            parts.append(np.array(ch.apply_host(iq[a:b])))
+        else:
+            parts.append(ch.apply(torch.from_numpy(iq[a:b].copy()).cuda()).cpu().numpy())
+    got = np.concatenate(parts)
+    assert got.shape == want.shape
+    err = wrap_rel_rms(got, want) if demod else O.rel_rms(got, want)
+    assert err <= TOL, err
+    # state hand-over to the stand-alone operators works from a u8 halo too
+    zi, last = ch.export_state()
+    st = O.ChainState(taps)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        O.chain_chunk(x[a:b], fs, f, taps, fs / decim, st, demod=False)
+    assert O.rel_rms(zi, st.zi) <= 1e-5
+    ch.close()
