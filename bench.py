@@ -326,6 +326,61 @@ def run_ours(args):
                "h2d": int(h2d), "d2h": int(d2h)}
     except Exception as exc:  # pinned allocation can fail on a small host
         e2e = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    # ---- extra (not the headline): the same pass fed with raw unsigned 8-bit I/Q, the format the
+    # reference's sources actually read (source.py:117-118); 2 B/sample instead of 8 ----
+    u8 = None
+    if not args.no_u8:
+        try:
+            n_u8 = min(n, args.e2e_samples)
+            chain8 = FusedChain(taps, DECIM, F_OFF, FS, demod=True, device=local, in_format="cu8")
+            xu = torch.empty((n_u8, 2), dtype=torch.uint8, device=dev)
+            for a in range(0, n_u8, slab):
+                b = min(n_u8, a + slab)
+                xu[a:b] = (torch.view_as_real(x[a:b]) + 127.5).clamp_(0, 255).to(torch.uint8)
+            out8 = torch.empty(chain8.out_count(n_u8) + 2, dtype=torch.float32, device=dev)
+
+            def pass8():
+                chain8.set_position(0, 0, False)
+                return chain8.apply(xu, out=out8)
+            for _ in range(3):
+                pass8()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(max(3, min(args.steps, 10))):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pass8()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            dev_ms = sum(ts) / len(ts)
+            host8 = torch.empty((n_u8, 2), dtype=torch.uint8, pin_memory=True)
+            host8.copy_(xu)
+            h8 = host8.numpy()
+            oh8 = torch.empty(n_u8 // DECIM + 2, dtype=torch.float32, pin_memory=True).numpy()
+
+            def e2e8():
+                chain8.set_position(0, 0, False)
+                pos = 0
+                for a in range(0, n_u8, CHUNK):
+                    b = min(n_u8, a + CHUNK)
+                    pos += chain8.apply_host(h8[a:b], out=oh8[pos:]).size
+                return pos
+            e2e8()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps8 = max(1, min(args.steps, args.e2e_steps))
+            for _ in range(reps8):
+                e2e8()
+            torch.cuda.synchronize()
+            host_ms = (time.perf_counter() - t0) / reps8 * 1e3
+            u8 = {"samples_per_step": n_u8, "device_resident_msps": round(n_u8 / dev_ms / 1e3, 1),
+                  "device_ms": round(dev_ms, 4), "e2e_msps": round(n_u8 / host_ms / 1e3, 1),
+                  "e2e_ms": round(host_ms, 3), "h2d_bytes_per_step": 2 * n_u8,
+                  "note": "same chain and capture quantised to unsigned 8-bit I/Q; per GPU, rank 0"}
+            del xu, host8
+        except Exception as exc:
+            u8 = {"error": "%s: %s" % (type(exc).__name__, exc)}
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -375,6 +430,8 @@ def run_ours(args):
         else:
             line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": str(e2e)}
+        if u8 is not None:
+            line["cu8_input"] = u8
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(reps=args.cpu_reps)
         print(json.dumps(line), flush=True)
@@ -394,6 +451,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-u8", action="store_true", help="skip the extra unsigned 8-bit input measurement")
     ap.add_argument("--ref-procs", type=int, default=64, help="max processes of the reference arm")
     args = ap.parse_args()
     if args.impl == "reference":
