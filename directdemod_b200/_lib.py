@@ -41,6 +41,7 @@ SIGNATURES = {
     "ddm_chain_get_halo": (_int, [_vp, _vp, _vp]),
     "ddm_chain_export_state": (_int, [_vp, _pdbl, _pdbl, _vp]),
     "ddm_chain_apply_dev": (_int, [_vp, _vp, _i64, _vp, _i64, _pi64, _vp]),
+    "ddm_chain_apply_batch_dev": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _pi64, _vp]),
     "ddm_chain_apply_host": (_int, [_vp, _vp, _i64, _vp, _i64, _pi64, _vp]),
     "ddm_mix_cf32": (_int, [_int, _vp, _i64, _dbl, _dbl, _i64, _vp]),
     "ddm_mix_var_cf32": (_int, [_int, _vp, _vp, _i64, _dbl, _i64, _vp]),

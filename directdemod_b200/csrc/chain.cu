@@ -65,6 +65,9 @@ struct ChainParams {
     double r_hi, r_lo;
     int D, DP, H, s, has_prev;
     int a_lastq;           // taps of the last partial sum are zero for a < a_lastq (multiple of 4)
+    // batch of independent captures (ddm_chain_apply_batch_dev): capture k reads x + k*x_stride
+    // samples and writes out + k*out_stride elements; every capture starts from the same state
+    long long batch, x_stride, out_stride;
 };
 
 // ------------------------------------------------------------------------------------
@@ -119,13 +122,15 @@ chain_fused_kernel(const ChainParams P) {
     const long long end_all = P.b0 + P.M * D;      // end of the last needed block
 
     // thread 0: start the TMA copies that fill one stage with tile `tile`
-    auto issue = [&](long long tile, int stage) {
+    auto issue = [&](long long gtile, int stage) {
         unsigned char *dst = s_stage0 + stage * stage_bytes;
+        const long long cap = gtile / P.num_tiles;
+        const long long tile = gtile - cap * P.num_tiles;
         const long long S0 = P.b0 + (tile * J - Q) * D;            // first sample (may be < 0)
         long long E = S0 + static_cast<long long>(NT) * D;
         if (E > end_all) E = end_all;
         if (U8) {
-            const unsigned char *xb = static_cast<const unsigned char *>(P.x);
+            const unsigned char *xb = static_cast<const unsigned char *>(P.x) + cap * P.x_stride * 2;
             const unsigned char *hb = static_cast<const unsigned char *>(P.halo);
             const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;          // floor to 8 samples = 16 B
             const long long Ea = (E >= 0 ? E + 7 : E) / 8 * 8;              // ceil to 8 samples
@@ -150,7 +155,7 @@ chain_fused_kernel(const ChainParams P) {
                          &mbar[stage]);
             return;
         }
-        const float2 *xf = static_cast<const float2 *>(P.x);
+        const float2 *xf = static_cast<const float2 *>(P.x) + cap * P.x_stride;
         const float2 *hf = static_cast<const float2 *>(P.halo);
         uint32_t bytes = 0;
         const long long h_end = E < 0 ? E : 0;
@@ -172,18 +177,21 @@ chain_fused_kernel(const ChainParams P) {
                      &mbar[stage]);
     };
 
-    long long tile = blockIdx.x;
+    const long long total_tiles = P.num_tiles * P.batch;
+    long long gtile = blockIdx.x;
     if (tid == 0) {
         for (int i = 0; i < S - 1; ++i) {
-            const long long t = tile + static_cast<long long>(i) * gridDim.x;
-            if (t < P.num_tiles) issue(t, i);
+            const long long t = gtile + static_cast<long long>(i) * gridDim.x;
+            if (t < total_tiles) issue(t, i);
         }
     }
 
-    for (int it = 0; tile < P.num_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; gtile < total_tiles; gtile += gridDim.x, ++it) {
         const int stage = it % S;
-        const long long nxt = tile + static_cast<long long>(S - 1) * gridDim.x;
-        if (tid == 0 && nxt < P.num_tiles) {
+        const long long cap = gtile / P.num_tiles;
+        const long long tile = gtile - cap * P.num_tiles;
+        const long long nxt = gtile + static_cast<long long>(S - 1) * gridDim.x;
+        if (tid == 0 && nxt < total_tiles) {
             // the stage being refilled was consumed in iteration it-1 (all threads are past
             // that iteration's __syncthreads)
             fence_proxy_async();
@@ -315,7 +323,7 @@ chain_fused_kernel(const ChainParams P) {
                 y.y += p.y;
             }
             if (OUT == DDM_CHAIN_OUT_IQ) {
-                reinterpret_cast<float2 *>(P.out)[m] = y;
+                reinterpret_cast<float2 *>(P.out)[cap * P.out_stride + m] = y;
             } else if (m > 0 || P.has_prev) {
                 float2 yp = make_float2(0.f, 0.f);
 #pragma unroll
@@ -326,7 +334,7 @@ chain_fused_kernel(const ChainParams P) {
                 }
                 const float re = fmaf(y.x, yp.x, y.y * yp.y);
                 const float im = fmaf(y.y, yp.x, -y.x * yp.y);
-                reinterpret_cast<float *>(P.out)[m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
+                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
             }
         }
         if (kChainEBufs == 1) __syncthreads();        // e_buf is reused by the next tile
@@ -462,7 +470,7 @@ int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
         }
     }
     long long grid = static_cast<long long>(c->sms) * per_sm;
-    if (grid > p.num_tiles) grid = p.num_tiles;
+    if (grid > p.num_tiles * p.batch) grid = p.num_tiles * p.batch;
     kern<<<static_cast<unsigned>(grid), kChainThreads, smem, st>>>(p);
     DDM_CUDA(cudaGetLastError());
     count_launch();
@@ -887,6 +895,8 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             p.s = s;
             p.has_prev = c->has_prev;
             p.a_lastq = c->a_lastq[s];
+            p.batch = 1;
+            p.x_stride = p.out_stride = 0;
             int rc = launch_fused(c, Q, p, st);
             if (rc != DDM_OK) return rc;
         } else {
@@ -945,6 +955,75 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
     return DDM_OK;
 }
 }  // namespace
+
+int ddm_chain_apply_batch_dev(ddm_chain *c, const void *x_dev, int64_t n, int64_t batch, int64_t x_stride,
+                              void *out_dev, int64_t out_stride, int64_t *n_out, void *stream) {
+    DDM_REQUIRE(c != nullptr, "ddm_chain_apply_batch_dev: NULL handle");
+    DDM_REQUIRE(n >= 0 && batch >= 0 && x_stride >= n, "ddm_chain_apply_batch_dev: bad sizes");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // every capture is a fresh stream: reset the handle (it is left in that state)
+    c->n0 = 0;
+    c->dec_off = 0;
+    c->has_prev = 0;
+    int rc = fill_initial_halo(c, st);
+    if (rc != DDM_OK) return rc;
+    int64_t per = 0;
+    ddm_chain_out_count(c, n, &per);
+    if (n_out) *n_out = per;
+    DDM_REQUIRE(out_stride >= per, "ddm_chain_apply_batch_dev: out_stride %lld is below the %lld outputs per capture",
+                static_cast<long long>(out_stride), static_cast<long long>(per));
+    if (batch == 0 || n == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_chain_apply_batch_dev: NULL buffer");
+    const int64_t M = positions_in(c, n);
+    const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (x_stride * c->es) % 16 == 0;
+    if (c->fast && aligned && c->in_format == DDM_IN_CF32 && M > 0) {
+        const int s = 1;                                  // dec_off = 0 -> (0 + 1) & 1
+        const int Q = c->Q[s];
+        ChainParams p{};
+        p.x = x_dev;
+        p.halo = c->d_halo[c->cur];
+        p.out = out_dev;
+        p.taps = c->d_taps[s];
+        p.rot = c->d_rot;
+        p.n = n;
+        p.n0 = 0;
+        p.M = M;
+        p.b0 = 0 + s + 1 - c->D;
+        const int J = kChainThreads - Q;
+        p.num_tiles = (M + J - 1) / J;
+        p.r_hi = c->r_hi;
+        p.r_lo = c->r_lo;
+        p.D = c->D;
+        p.DP = c->DP;
+        p.H = c->H;
+        p.s = s;
+        p.has_prev = 0;
+        p.a_lastq = c->a_lastq[s];
+        p.batch = batch;
+        p.x_stride = x_stride;
+        p.out_stride = out_stride;
+        return launch_fused(c, Q, p, st);
+    }
+    // general configurations: capture by capture
+    const size_t oes = c->out_mode == DDM_CHAIN_OUT_IQ ? sizeof(float2) : sizeof(float);
+    for (int64_t k = 0; k < batch; ++k) {
+        c->n0 = 0;
+        c->dec_off = 0;
+        c->has_prev = 0;
+        rc = fill_initial_halo(c, st);
+        if (rc != DDM_OK) return rc;
+        int64_t got = 0;
+        rc = ddm_chain_apply_dev(c, static_cast<const unsigned char *>(x_dev) + static_cast<size_t>(k) * x_stride * c->es, n,
+                                 static_cast<unsigned char *>(out_dev) + static_cast<size_t>(k) * out_stride * oes,
+                                 out_stride, &got, stream);
+        if (rc != DDM_OK) return rc;
+    }
+    c->n0 = 0;
+    c->dec_off = 0;
+    c->has_prev = 0;
+    return fill_initial_halo(c, st);
+}
 
 int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_host,
                          int64_t out_capacity, int64_t *n_out, void *stream) {

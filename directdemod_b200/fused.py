@@ -161,6 +161,28 @@ class FusedChain:
                    "ddm_chain_apply_dev")
         return out[:got.value]
 
+    def apply_batch(self, x2d, out=None):
+        """x2d: cuda complex64 tensor [captures, n], each row an independent capture demodulated as
+        a fresh stream (reference initial state) -- all rows in one launch.  Returns [captures, m].
+        The chain is reset by this call."""
+        torch = _torch()
+        if not (isinstance(x2d, torch.Tensor) and x2d.is_cuda and x2d.dim() == 2):
+            raise TypeError("apply_batch() wants a 2-D cuda tensor [captures, samples]")
+        if self.in_format == "cu8":
+            raise TypeError("apply_batch() takes complex64 captures")
+        x2d = x2d.contiguous()
+        batch, n = x2d.shape
+        self.reset()
+        m = self.out_count(n)
+        dt = torch.float32 if self.demod else torch.complex64
+        if out is None:
+            out = torch.empty((batch, m), dtype=dt, device=x2d.device)
+        got = C.c_int64()
+        _lib.check(self._l.ddm_chain_apply_batch_dev(
+            self._h, C.c_void_p(x2d.data_ptr()), n, batch, x2d.stride(0), C.c_void_p(out.data_ptr()),
+            out.stride(0), C.byref(got), _stream_ptr(self.device)), "ddm_chain_apply_batch_dev")
+        return out[:, :got.value]
+
     def apply_host(self, x, out=None):
         """x: host complex64 array (numpy, or a pinned torch tensor).  Copies in, runs the
         chain, copies the result back; returns a numpy array."""

@@ -99,6 +99,12 @@ int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream);
 
 int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n,
                         void *out_dev, int64_t out_capacity, int64_t *n_out, void *stream);
+/* `batch` independent captures of n samples each (capture k at x_dev + k*x_stride samples), every
+ * one demodulated as a fresh stream from the reference's initial state, in ONE launch (BASELINE
+ * config 5: 256 separate captures).  Output k at out_dev + k*out_stride elements, *n_out outputs
+ * per capture.  The handle is reset and left in its reset state. */
+int ddm_chain_apply_batch_dev(ddm_chain *c, const void *x_dev, int64_t n, int64_t batch, int64_t x_stride,
+                              void *out_dev, int64_t out_stride, int64_t *n_out, void *stream);
 int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n,
                          void *out_host, int64_t out_capacity, int64_t *n_out, void *stream);
 

@@ -195,3 +195,29 @@ def test_u8_ingest_matches_oracle(ntaps, decim, fs, f, n, ncuts, demod):
         O.chain_chunk(x[a:b], fs, f, taps, fs / decim, st, demod=False)
     assert O.rel_rms(zi, st.zi) <= 1e-5
     ch.close()
+
+
+def test_batch_of_independent_captures_in_one_launch():
+    """BASELINE config 5 in miniature: every row is its own fresh stream; one launch."""
+    import torch
+    from directdemod_b200 import _lib
+    from directdemod_b200.fused import FusedChain
+    fs, f, decim, n, ncap = 10000000, -125000.0, 50, 120002, 5      # rows stay 16-byte aligned
+    taps = O.taps_blackman_harris(151)[0]
+    caps = np.stack([fm_tone_c64(100 + k, n, fs, f, 4000.0 + 300 * k, 2.0) for k in range(ncap)])
+    ch = FusedChain(taps, decim, f, fs)
+    l0 = _lib.launch_count()
+    got = ch.apply_batch(torch.from_numpy(caps).cuda()).cpu().numpy()
+    assert _lib.launch_count() - l0 == 1
+    for k in range(ncap):
+        want, _ = O.chain_stream(caps[k], fs, f, taps, fs / decim)
+        assert got[k].shape == want.shape
+        assert wrap_rel_rms(got[k], want) <= TOL, k
+    # rows that are not 16-byte aligned, and odd decimation -> capture by capture, same results
+    got1 = ch.apply_batch(torch.from_numpy(np.ascontiguousarray(caps[:2, :120001])).cuda()).cpu().numpy()
+    want, _ = O.chain_stream(caps[1, :120001], fs, f, taps, fs / decim)
+    assert got1[1].shape == want.shape and wrap_rel_rms(got1[1], want) <= TOL
+    ch2 = FusedChain(taps, 33, f, fs)
+    got2 = ch2.apply_batch(torch.from_numpy(caps[:2]).cuda()).cpu().numpy()
+    want, _ = O.chain_stream(caps[1], fs, f, taps, fs / 33)
+    assert wrap_rel_rms(got2[1], want) <= TOL
