@@ -206,7 +206,9 @@ class decode_noaa:
 
         # ---- host: colour-calibration state machine over the precomputed lines -------
         image, imageBuffer, backupImage = [], [], []
-        lowFifo, highFifo = [], []
+        lowFifo, highFifo = np.zeros(0), np.zeros(0)
+        low_rows = [j for j in range(len(constants.NOAA_SYNCA)) if constants.NOAA_SYNCA[j] == 0]
+        high_rows = [j for j in range(len(constants.NOAA_SYNCA)) if constants.NOAA_SYNCA[j] != 0]
         corrfifo, corrfifosig, corrfifosig2 = [], [], []
         ncorrfifo = 3
         lcorr = lcorrsig = None
@@ -225,14 +227,11 @@ class decode_noaa:
             if pix.get((li, "A")) is None or pix.get((li, "B")) is None:
                 raise ValueError("cannot reshape array of size 0 into shape (%d,0)" % half)
             if csyncA[k] in ucsync:
+                # :358-366 two FIFOs of the last 10 000 samples seen under the low / high sync bits
+                # (appending row by row and truncating each time == appending all, truncating once)
                 pxA = sync_px[li]
-                for j in range(nsync):
-                    if constants.NOAA_SYNCA[j] == 0:
-                        lowFifo.extend(pxA[j])
-                    else:
-                        highFifo.extend(pxA[j])
-                    lowFifo = lowFifo[-fifoLen:]
-                    highFifo = highFifo[-fifoLen:]
+                lowFifo = np.concatenate([lowFifo, pxA[low_rows].ravel()])[-fifoLen:]
+                highFifo = np.concatenate([highFifo, pxA[high_rows].ravel()])[-fifoLen:]
                 val11, val244 = np.median(lowFifo), np.median(highFifo)
                 self._low = val11 - (val244 - val11) * (11 - 0) / (244 - 11)
                 self._high = val11 - (val244 - val11) * (11 - 255) / (244 - 11)
