@@ -1,0 +1,7 @@
+#!/bin/bash
+# ncu --set full of one launch of each non-FFT hot-path kernel (scripts/prof_ops.py, second round)
+mkdir -p gpurun_out
+timeout 1500 ncu --set full --clock-control none --import-source on \
+    -k regex:'fir_kernel|iir_kernel|ncc_tile_kernel|mix_kernel|fm_kernel|select_hist2|compact_write|bank4|row_median|chain_fused' \
+    -s 16 -c 16 -o gpurun_out/prof_ops2 -f python scripts/prof_ops.py > gpurun_out/prof_ops2.log 2>&1
+tail -n 2 gpurun_out/prof_ops2.log
