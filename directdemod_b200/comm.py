@@ -23,6 +23,7 @@ from . import _dev, _lib, constants
 from . import demod_fm as _demod_fm
 from . import filters as _filters
 from .fused import FusedChain
+from .source import RawIQ8
 
 
 def _is_cuda_tensor(x):
@@ -42,7 +43,11 @@ class commSignal:
         self._host = None
         self._dev = None
         self._parts = []             # device pieces appended by extend(), joined on demand
-        if _is_cuda_tensor(sig):
+        self._raw8 = None            # RawIQ8 block not yet converted (source.readRaw)
+        if isinstance(sig, RawIQ8):
+            self._raw8 = sig
+            self._complex = True
+        elif _is_cuda_tensor(sig):
             if sig.dim() != 1:
                 raise TypeError("The signal array must be 1-D")
             self._dev = _dev.to_device(sig).clone()
@@ -67,6 +72,9 @@ class commSignal:
     def signal(self):
         """The samples as a numpy array (float64 / complex128 once an operator has run)."""
         self._flush()
+        if self._raw8 is not None:
+            self._host = self._raw8.to_complex64()
+            self._raw8 = None
         if self._host is None or self._parts:
             self._host = _dev.to_host(self._device_array())
             self._dev = None          # the caller may now mutate the array it was given
@@ -79,6 +87,17 @@ class commSignal:
         return self._device_array()
 
     def _device_array(self):
+        if self._raw8 is not None:
+            # bytes -> cf32 on the device (ddm_cu8_to_cf32), 2 B/sample over PCIe
+            t = _dev.require_cuda()
+            raw = t.from_numpy(np.array(self._raw8.data)).to("cuda")       # (copy: memmaps are read-only)
+            out = _dev.empty_like_kind(raw.shape[0], True)
+            _lib.check(_lib.lib().ddm_cu8_to_cf32(out.device.index, _dev.ptr(raw), raw.shape[0], _dev.ptr(out),
+                                                  _dev.stream_ptr(out.device.index)), "ddm_cu8_to_cf32")
+            self._raw8 = None
+            self._dev = out
+            self._host = None
+            return self._dev
         if self._parts:
             t = _dev.torch()
             parts = self._parts
@@ -227,6 +246,7 @@ class commSignal:
             raise TypeError("The signal array must be 1-D")
         self._host = arr
         self._dev = None
+        self._raw8 = None
         self._len = len(arr)
         self._complex = bool(np.iscomplexobj(arr))
         return self
@@ -234,6 +254,7 @@ class commSignal:
     # ---- execution ------------------------------------------------------------------
     def _set_device(self, tensor):
         self._parts = []
+        self._raw8 = None
         self._dev = tensor
         self._host = None
         self._len = int(tensor.numel())
@@ -252,8 +273,16 @@ class commSignal:
         if not ops:
             return
         self._pending = []
-        x = self._device_array()
+        x = None
         i = 0
+        if self._raw8 is not None:
+            took, y = self._try_fused(ops, 0, None, raw=self._raw8)
+            if took:
+                self._raw8 = None
+                x = y
+                i = took
+        if x is None:
+            x = self._device_array()
         try:
             while i < len(ops):
                 took, y = self._try_fused(ops, i, x)
@@ -272,8 +301,9 @@ class commSignal:
         self._len = int(x.numel())
         self._complex = bool(x.is_complex())
 
-    def _try_fused(self, ops, i, x):
-        """Match [mix] filter [decim] [fm] at ops[i:] and run it as one fused launch."""
+    def _try_fused(self, ops, i, x, raw=None):
+        """Match [mix] filter [decim] [fm] at ops[i:] and run it as one fused launch.  With
+        ``raw`` (a RawIQ8 block) the chain ingests the unsigned 8-bit bytes directly."""
         j = i
         mix = filt = dec = fm = None
         if j < len(ops) and ops[j][0] == "mix":
@@ -290,8 +320,10 @@ class commSignal:
         if j < len(ops) and ops[j][0] == "fm":
             fm = ops[j][1]
             j += 1
-        if dec is None or dec[1] < 2 or not x.is_complex():
+        if dec is None or dec[1] < 2 or (raw is None and not x.is_complex()):
             return 0, None          # without a decimator the stand-alone FIR kernel is the better tool
+        fmt = "cu8" if raw is not None else "cf32"
+        dev_index = _dev.device_index() if raw is not None else x.device.index
         if not (filt.isFIR and filt._storeState and not filt._needs_lfiltic):
             return 0, None
         if fm is not None and not fm._storeState:
@@ -301,9 +333,9 @@ class commSignal:
         n0 = mix[2] if mix is not None else None
         jump, off = dec[1], dec[2]
         ch = filt._chain
-        key = (float(freq), int(fs), int(jump), fm is not None)
+        key = (float(freq), int(fs), int(jump), fm is not None, fmt)
         if ch is not None:
-            if getattr(ch, "_key", None) != key or ch.device != x.device.index:
+            if getattr(ch, "_key", None) != key or ch.device != dev_index:
                 return 0, None
             pos_n0, pos_off, pos_prev = ch.position
             if (n0 is not None and n0 != pos_n0) or off != pos_off:
@@ -315,11 +347,17 @@ class commSignal:
                 return 0, None
             if fm is not None and not fm._fresh:
                 return 0, None
+            if raw is not None:
+                _dev.require_cuda()
             ch = FusedChain(filt._bd, jump, freq, fs if mix is not None else 1.0,
-                            demod=fm is not None, device=x.device.index)
+                            demod=fm is not None, device=dev_index, in_format=fmt)
             ch._key = key
             ch.set_position(0, off, False)
-        y = ch.apply(x)
+        if raw is not None:
+            t = _dev.torch()
+            y = ch.apply(t.from_numpy(np.array(raw.data)).to("cuda:%d" % dev_index))
+        else:
+            y = ch.apply(x)
         filt._chain = ch
         filt._used = True
         if fm is not None:

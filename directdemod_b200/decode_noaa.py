@@ -314,7 +314,9 @@ class decode_noaa:
         chunkerObj = chunker.chunker(self._sigsrc)
         for num, i in enumerate(chunkerObj.getChunks):
             logging.info('Processing chunk %d of %d chunks', num + 1, len(chunkerObj.getChunks))
-            sig = comm.commSignal(self._sigsrc.sampFreq, self._sigsrc.read(*i), chunkerObj) \
+            raw = getattr(self._sigsrc, "readRaw", None)       # 8-bit sources: bytes straight into the kernel
+            block = raw(*i) if raw is not None else self._sigsrc.read(*i)
+            sig = comm.commSignal(self._sigsrc.sampFreq, block, chunkerObj) \
                 .offsetFreq(self._offset).filter(bhFilter).bwLim(self._bw, uniq="First") \
                 .funcApply(fmDemdulator.demod).bwLim(audioFreq, strictness)
             audioOut.extend(sig)

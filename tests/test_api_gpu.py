@@ -423,3 +423,45 @@ def test_resample_all_branches_match_scipy():
         got = _dev.to_host(fftops.resample(_dev.to_device(xc), num))
         want = sps.resample(xc.astype(np.complex128), num)
         assert got.shape == want.shape and O.rel_rms(got, want) <= TOL, ("cplx", n, num, O.rel_rms(got, want))
+
+
+def test_raw_8bit_source_blocks_take_the_fused_u8_path(tmp_path):
+    """source.readRaw -> commSignal: same chain, same results as the complex64 route, the
+    unsigned 8-bit bytes converted inside the fused kernel (one launch per chunk)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    from directdemod_b200 import _lib, decode_fm, source
+    rng = np.random.default_rng(13)
+    n, fs = 300000, 2048000
+    t = np.arange(n) / fs
+    z = 70 * np.exp(1j * (2 * np.pi * 30000 * t + 2.0 * np.sin(2 * np.pi * 1300 * t))) \
+        + 5 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    pairs = np.stack([np.clip(np.round(z.real + 127.5), 0, 255), np.clip(np.round(z.imag + 127.5), 0, 255)], 1).astype(np.uint8)
+    dat = tmp_path / "iq.dat"
+    pairs.tofile(dat)
+    src = source.IQdat(str(dat), fs)
+    outs = []
+    for raw_mode in (False, True):
+        ck = chunker.chunker(src, 70001)
+        bh, fm = filters.blackmanHarris(151), demod_fm.demod_fm()
+        out = comm.commSignal(1)
+        l0 = _lib.launch_count()
+        for a, b in ck.getChunks:
+            block = src.readRaw(a, b) if raw_mode else src.read(a, b)
+            out.extend(comm.commSignal(fs, block, ck).offsetFreq(30000).filter(bh).bwLim(60000, uniq="First")
+                       .funcApply(fm.demod))
+        assert _lib.launch_count() - l0 <= len(ck.getChunks) + 3       # raw: + the fresh-stream general-kernel piece
+        outs.append(out.signal)
+    x = src.read(0, n)
+    want, _ = O.chain_stream(x, fs, 30000.0, O.taps_blackman_harris(151)[0], 60000, chunk_size=70001)
+    for got in outs:
+        assert got.shape == want.shape and wrap_rel_rms(got, want) <= TOL
+    # raw block used outside the fusable pattern: converted on the device, .signal == reference read()
+    assert np.array_equal(comm.commSignal(fs, src.readRaw(5, 1000)).signal, src.read(5, 1000))
+    got = comm.commSignal(fs, src.readRaw(0, 5000)).offsetFreq(1000.0).signal
+    assert O.rel_rms(got, O.mix(src.read(0, 5000), 1000.0, fs, 0)[0]) <= TOL
+    # decode_fm.getAudio (decode_fm.py:41-72) on the 8-bit source: chain + strict resample per chunk
+    aud = decode_fm.decode_fm(src, 30000.0).getAudio
+    fmw, rate = O.chain_stream(x, fs, 30000.0, O.taps_blackman_harris(151)[0], 30000)
+    want_a, _ = O.resample_strict(fmw, rate, 15000)
+    assert aud.sampRate == 15000 and aud.length == len(want_a)
+    assert O.rel_rms(aud.signal, want_a) <= TOL

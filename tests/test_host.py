@@ -150,3 +150,43 @@ def test_no_cpu_fallback_without_a_device():
         FusedChain(np.ones(4), 2, 0.0, 1000.0)
     with pytest.raises(RuntimeError):
         filters.rollingAverage(3).applyOn(np.arange(10.0))
+
+
+def _write_wav_u8(path, pairs, fs):
+    """Two-channel unsigned 8-bit PCM WAV with the canonical 44-byte header (source.py:66)."""
+    import struct
+    data = np.ascontiguousarray(pairs, dtype=np.uint8).tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 2, fs, fs * 2, 2, 8) \
+        + b"data" + struct.pack("<I", len(data))
+    assert len(hdr) == 44
+    with open(path, "wb") as fh:
+        fh.write(hdr + data)
+
+
+def test_sources_read_like_the_reference(tmp_path):
+    from directdemod_b200 import constants, source
+    rng = np.random.default_rng(12)
+    pairs = rng.integers(0, 256, (5000, 2), dtype=np.uint8)
+    want = (pairs[:, 0] + 1j * pairs[:, 1]).astype("complex64") - (127.5 + 1j * 127.5)
+    wav = tmp_path / "iq.wav"
+    dat = tmp_path / "iq.dat"
+    _write_wav_u8(wav, pairs, 2048000)
+    pairs.tofile(dat)
+    for src in (source.IQwav(str(wav)), source.IQwavAlt(str(wav)), source.IQdat(str(dat), 2048000)):
+        assert src.length == 5000 and src.sampFreq == 2048000
+        got = src.read(10, 4000)
+        assert got.dtype == np.complex64 and np.array_equal(got, want[10:4000])
+        assert np.array_equal(src.read(7), want[7:8])
+        raw = src.readRaw(10, 4000)
+        assert isinstance(raw, source.RawIQ8) and len(raw) == 3990 and np.array_equal(raw.to_complex64(), want[10:4000])
+        for bad in ((-1, 5), (0, 5001), (5000, 5000)):
+            with pytest.raises(ValueError):
+                src.read(*bad)
+        src.limitData(100, 600)
+        assert src.length == 500 and np.array_equal(src.read(0, 500), want[100:600])
+        src.limitData()
+        assert src.length == 5000
+    assert source.IQwav(str(wav)).sourceType == constants.SOURCE_IQWAV
+    assert source.IQdat(str(dat)).sourceType == constants.SOURCE_IQDAT
+    assert source.IQdat(str(dat)).sampFreq == constants.IQ_SDRSAMPRATE
+    assert source.IQwav(str(wav), 1000000).sampFreq == 1000000
