@@ -95,6 +95,11 @@ class filter:
                              "be time-sharded; shard it by independent units" % nf)
         return w
 
+    def setFIRMode(self, mode):
+        """0 auto (default), 1 direct convolution, 2 overlap-save FFT (see ddemod.h)."""
+        _lib.check(_lib.lib().ddm_filter_set_fir_mode(self._handle(), int(mode)), "ddm_filter_set_fir_mode")
+        return self
+
     def info(self):
         """(is_fir, parallel warm-up length, measured float64 roundoff floor of the recursion)."""
         fir, w, nf = C.c_int(), C.c_int64(), C.c_double()

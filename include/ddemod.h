@@ -175,6 +175,13 @@ int ddm_filter_set_zi_base(ddm_filter *f, const double *zi_host);
 #define DDM_IIR_PARALLEL 1
 #define DDM_IIR_SEQUENTIAL 2
 int ddm_filter_set_iir_mode(ddm_filter *f, int mode);
+/* FIR execution path: direct register-tiled convolution (FP32-pipe bound, cost grows with the tap
+ * count) or overlap-save through 4096-point FFTs in shared memory (HBM bound, up to 2049 taps).
+ * AUTO takes the FFT path from 96 taps on. */
+#define DDM_FIR_AUTO 0
+#define DDM_FIR_DIRECT 1
+#define DDM_FIR_FFT 2
+int ddm_filter_set_fir_mode(ddm_filter *f, int mode);
 /* is_fir, warm-up length of the segment-parallel IIR (-1: never decays), measured noise floor */
 int ddm_filter_info(const ddm_filter *f, int *is_fir, int64_t *warmup, double *noise_floor);
 /* host only (no device needed): warm-up length of the segment-parallel IIR (-1: the zero-input
