@@ -44,13 +44,17 @@ class commSignal:
         self._dev = None
         self._parts = []             # device pieces appended by extend(), joined on demand
         self._raw8 = None            # RawIQ8 block not yet converted (source.readRaw)
+        self._shared = False         # _dev aliases the caller's tensor (copy before writing)
         if isinstance(sig, RawIQ8):
             self._raw8 = sig
             self._complex = True
         elif _is_cuda_tensor(sig):
             if sig.dim() != 1:
                 raise TypeError("The signal array must be 1-D")
-            self._dev = _dev.to_device(sig).clone()
+            # the reference copies its input (np.array(sig)); here the copy is deferred until an
+            # operator would write into the caller's tensor (only the un-fused mixer works in place)
+            self._dev = _dev.to_device(sig)
+            self._shared = self._dev.data_ptr() == sig.data_ptr()
             self._complex = bool(sig.is_complex())
         else:
             arr = np.array(sig)
@@ -218,7 +222,7 @@ class commSignal:
         # bytes); here the pieces stay on the device and are joined once, when first read
         self._flush()
         sig._flush()
-        piece = sig._device_array().clone()
+        piece = sig._device_array().clone()      # must not alias a tensor its owner may still write to
         if self._len == 0:
             self._parts = [piece]
             self._complex = bool(piece.is_complex())
@@ -255,6 +259,7 @@ class commSignal:
     def _set_device(self, tensor):
         self._parts = []
         self._raw8 = None
+        self._shared = False
         self._dev = tensor
         self._host = None
         self._len = int(tensor.numel())
@@ -296,6 +301,8 @@ class commSignal:
             for op in ops:
                 if op[0] in ("filter", "fm") and getattr(op[1], "_pending_owner", None) is self:
                     op[1]._pending_owner = None
+        if self._dev is None or x.data_ptr() != self._dev.data_ptr():
+            self._shared = False     # the operators produced a fresh tensor
         self._dev = x
         self._host = None
         self._len = int(x.numel())
@@ -368,6 +375,9 @@ class commSignal:
     def _run_single(self, op, x):
         kind = op[0]
         if kind == "mix":
+            if self._shared:
+                x = x.clone()
+                self._shared = False
             _lib.check(_lib.lib().ddm_mix_cf32(x.device.index, _dev.ptr(x), x.numel(), op[1], float(op[3]),
                                                op[2], _dev.stream_ptr(x.device.index)), "ddm_mix_cf32")
             return x
@@ -390,6 +400,10 @@ class commSignal:
     def _run_mix_var(self, f, offset):
         t = _dev.torch()
         x = self._device_array()
+        if self._shared:
+            x = x.clone()
+            self._dev = x
+            self._shared = False
         fd = t.from_numpy(f).to(x.device)
         _lib.check(_lib.lib().ddm_mix_var_cf32(x.device.index, _dev.ptr(x), _dev.ptr(fd), x.numel(),
                                                float(self._sampRate), int(offset),

@@ -751,29 +751,6 @@ int setup_fir(ddm_filter *f) {
     if (rc != DDM_OK) return rc;
     rc = dev_alloc_copy(&f->d_b, f->b.data(), static_cast<size_t>(K));
     if (rc != DDM_OK) return rc;
-    if (K <= kFftFirMaxTaps) {
-        // spectrum of the taps, float64 on the host (O(N K), once per filter), 1/N folded in
-        const int N = kFftFirN;
-        std::vector<double> cs(N), sn(N);
-        for (int t2 = 0; t2 < N; ++t2) {
-            cs[t2] = std::cos(2.0 * M_PI * t2 / N);
-            sn[t2] = -std::sin(2.0 * M_PI * t2 / N);
-        }
-        std::vector<float2> H(N), tw(N);
-        for (int bin = 0; bin < N; ++bin) {
-            double re = 0.0, im = 0.0;
-            for (int k = 0; k < K; ++k) {
-                const int idx = static_cast<int>((static_cast<long long>(bin) * k) % N);
-                re += f->b[k] * cs[idx];
-                im += f->b[k] * sn[idx];
-            }
-            H[bin] = make_float2(static_cast<float>(re / N), static_cast<float>(im / N));
-            tw[bin] = make_float2(static_cast<float>(cs[bin]), static_cast<float>(sn[bin]));
-        }
-        rc = dev_alloc_copy(&f->d_H, H.data(), H.size());
-        if (rc != DDM_OK) return rc;
-        rc = dev_alloc_copy(&f->d_tw, tw.data(), tw.size());
-    }
     return rc;
 }
 
@@ -936,15 +913,62 @@ int launch_iir(ddm_filter *f, const void *x, void *y, long long n, bool cplx, in
     return DDM_ERR_UNSUPPORTED;
 }
 
-// taps from which the overlap-save FFT kernel beats the direct one (measured on B200)
+// taps / samples from which the overlap-save FFT kernel beats the direct one (measured on B200,
+// DESIGN.md 3.2): short signals do not fill the GPU with 4096-sample blocks
 constexpr int kFftFirMinTaps = 96;
+constexpr long long kFftFirMinSamples = 1 << 20;
+
+// spectrum of the taps (float64 radix-2 FFT on the host, 1/N folded in) and the twiddle table;
+// built on first use of the FFT path
+int build_fft_fir_tables(ddm_filter *f) {
+    if (f->d_H != nullptr) return DDM_OK;
+    const int N = kFftFirN;
+    std::vector<double> re(N, 0.0), im(N, 0.0);
+    for (int k = 0; k < f->nb; ++k) re[k] = f->b[k];
+    // bit reversal
+    for (int i = 1, j = 0; i < N; ++i) {
+        int bit = N >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) {
+            std::swap(re[i], re[j]);
+            std::swap(im[i], im[j]);
+        }
+    }
+    for (int len = 2; len <= N; len <<= 1) {
+        const double ang = -2.0 * M_PI / len;
+        for (int i = 0; i < N; i += len) {
+            for (int k = 0; k < len / 2; ++k) {
+                const double wr = std::cos(ang * k), wi = std::sin(ang * k);
+                const int u = i + k, v = i + k + len / 2;
+                const double tr = re[v] * wr - im[v] * wi, ti = re[v] * wi + im[v] * wr;
+                re[v] = re[u] - tr;
+                im[v] = im[u] - ti;
+                re[u] += tr;
+                im[u] += ti;
+            }
+        }
+    }
+    std::vector<float2> H(N), tw(N);
+    for (int bin = 0; bin < N; ++bin) {
+        H[bin] = make_float2(static_cast<float>(re[bin] / N), static_cast<float>(im[bin] / N));
+        tw[bin] = make_float2(static_cast<float>(std::cos(2.0 * M_PI * bin / N)),
+                              static_cast<float>(-std::sin(2.0 * M_PI * bin / N)));
+    }
+    int rc = dev_alloc_copy(&f->d_H, H.data(), H.size());
+    if (rc != DDM_OK) return rc;
+    return dev_alloc_copy(&f->d_tw, tw.data(), tw.size());
+}
 
 template <bool CPLX>
 int launch_fir(ddm_filter *f, const void *x, void *y, long long n, const double2 *zi, cudaStream_t st) {
     using T = typename FirTraits<CPLX>::T;
-    const bool can_fft = f->d_H != nullptr;
-    const bool use_fft = can_fft && (f->fir_mode == DDM_FIR_FFT || (f->fir_mode == DDM_FIR_AUTO && f->nb >= kFftFirMinTaps));
+    const bool can_fft = f->nb <= kFftFirMaxTaps;
+    const bool use_fft = can_fft && (f->fir_mode == DDM_FIR_FFT ||
+                                     (f->fir_mode == DDM_FIR_AUTO && f->nb >= kFftFirMinTaps && n >= kFftFirMinSamples));
     if (use_fft) {
+        int rc = build_fft_fir_tables(f);
+        if (rc != DDM_OK) return rc;
         const int V = kFftFirN - (f->nb - 1);
         const long long blocks = (n + V - 1) / V;
         fir_fft_kernel<CPLX><<<static_cast<unsigned>(blocks), kFftFirThreads, 0, st>>>(
@@ -1103,7 +1127,7 @@ int ddm_filter_set_fir_mode(ddm_filter *f, int mode) {
     DDM_REQUIRE(f != nullptr, "ddm_filter_set_fir_mode: NULL handle");
     DDM_REQUIRE(mode == DDM_FIR_AUTO || mode == DDM_FIR_DIRECT || mode == DDM_FIR_FFT,
                 "ddm_filter_set_fir_mode: bad mode %d", mode);
-    DDM_REQUIRE(mode != DDM_FIR_FFT || f->d_H != nullptr,
+    DDM_REQUIRE(mode != DDM_FIR_FFT || (f->fir && f->nb <= kFftFirMaxTaps),
                 "ddm_filter_set_fir_mode: the FFT path needs a FIR with at most %d taps", kFftFirMaxTaps);
     f->fir_mode = mode;
     return DDM_OK;

@@ -317,6 +317,29 @@ def test_blackman_harris_conv_same():
         assert O.rel_rms(filters.blackmanHarrisConv(151).applyOn(x), want) <= TOL, n
 
 
+def test_fir_direct_and_overlap_save_fft_paths_agree_with_scipy():
+    """Both FIR kernels (register-tiled direct convolution, overlap-save 4096-point FFT) against
+    scipy for complex and real input, stateful over uneven chunks, incl. chunks shorter than a block."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(19)
+    n = 50000
+    xc = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    xr = rng.standard_normal(n).astype(np.float32)
+    cuts = [0, 3000, 3001, 20000, n]
+    for mk in (lambda: filters.blackmanHarris(151), lambda: filters.hamming(492),
+               lambda: filters.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023),
+               lambda: filters.gaussian(2049, 300)):
+        for x in (xc, xr):
+            b = np.asarray(mk().getB, dtype=np.float64)
+            want, _ = O.filt_stateful(b, [1], x.astype(np.complex128 if np.iscomplexobj(x) else np.float64), O.initial_zi(b))
+            for mode in (1, 2):
+                f = mk().setFIRMode(mode)
+                got = np.concatenate([f.applyOn(x[a:c]) for a, c in zip(cuts[:-1], cuts[1:])])
+                assert O.rel_rms(got, want) <= TOL, (len(b), mode, O.rel_rms(got, want))
+    with pytest.raises(Exception):
+        filters.gaussian(2050, 300).setFIRMode(2)        # above the FFT path's tap limit
+
+
 def test_median_filter_matches_scipy():
     chunker, comm, constants, demod_fm, filters = _mods()
     import scipy.signal as sps
