@@ -475,8 +475,8 @@ int ddm_correlate(int device, const void *hay_dev, int64_t n, int hay_is_f64, co
     }
     DevBuf nd;
     if ((rc = nd.alloc(device, 0, sizeof(double) * m)) != DDM_OK) return rc;
+    // (a copy from pageable host memory is staged before cudaMemcpyAsync returns: needle_host is free)
     DDM_CUDA(cudaMemcpyAsync(nd.p, needle_host, sizeof(double) * m, cudaMemcpyHostToDevice, st));
-    DDM_CUDA(cudaStreamSynchronize(st));          // needle_host may be reused by the caller
     const unsigned grid = static_cast<unsigned>((n + 255) / 256);
     if (hay_is_f64)
         ncc_direct_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(hay_dev), n,

@@ -47,7 +47,22 @@ class filter:
         self._used = False
 
     # -- handle management ------------------------------------------------------------
+    # Filters without carried state (zeroPhase / storeState=False) are pure functions of their
+    # coefficients: their native handles are shared per (device, b, a), so code that builds a new
+    # filter object per window (decode_noaa.getAccurateSync, decode_noaa.py:852) does not pay for
+    # device allocations and coefficient uploads every time.
+    _shared_handles = {}
+
     def _handle(self):
+        if self._h is None and not self._storeState and not getattr(self, "_private", False):
+            _dev.require_cuda()
+            key = (_dev.device_index(), self._bd.tobytes(), self._ad.tobytes())
+            cached = filter._shared_handles.get(key)
+            if cached is not None:
+                self._h = cached
+                self._owns_handle = False
+                self._dev_index = key[0]
+                return self._h
         if self._h is None:
             _dev.require_cuda()
             l = _lib.lib()
@@ -66,10 +81,22 @@ class filter:
                            "ddm_filter_set_zi_base")
             if self._storeState and not self._needs_lfiltic:
                 _lib.check(l.ddm_filter_reset(h, _dev.stream_ptr()), "ddm_filter_reset")
+            if not self._storeState and not getattr(self, "_private", False):
+                if len(filter._shared_handles) < 256:
+                    filter._shared_handles[(self._dev_index, self._bd.tobytes(), self._ad.tobytes())] = h
+                    self._owns_handle = False
         return self._h
+
+    def _unshare(self):
+        """Execution modes are per-handle settings: a filter that changes one gets its own handle."""
+        if getattr(self, "_h", None) is not None and not getattr(self, "_owns_handle", True):
+            self._h = None
+        self._private = True
+        self._owns_handle = True
 
     def setIIRMode(self, mode):
         """0 auto (default), 1 segment-parallel, 2 sequential bit-exact replay (see ddemod.h)."""
+        self._unshare()
         _lib.check(_lib.lib().ddm_filter_set_iir_mode(self._handle(), int(mode)), "ddm_filter_set_iir_mode")
         return self
 
@@ -97,6 +124,7 @@ class filter:
 
     def setFIRMode(self, mode):
         """0 auto (default), 1 direct convolution, 2 overlap-save FFT (see ddemod.h)."""
+        self._unshare()
         _lib.check(_lib.lib().ddm_filter_set_fir_mode(self._handle(), int(mode)), "ddm_filter_set_fir_mode")
         return self
 
@@ -109,9 +137,9 @@ class filter:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None) is not None:
+            if getattr(self, "_h", None) is not None and getattr(self, "_owns_handle", True):
                 _lib.lib().ddm_filter_destroy(self._h)
-                self._h = None
+            self._h = None
         except Exception:
             pass
 
