@@ -488,3 +488,39 @@ def test_raw_8bit_source_blocks_take_the_fused_u8_path(tmp_path):
     want_a, _ = O.resample_strict(fmw, rate, 15000)
     assert aud.sampRate == 15000 and aud.length == len(want_a)
     assert O.rel_rms(aud.signal, want_a) <= TOL
+
+
+def test_empty_and_tiny_inputs_behave_like_the_reference():
+    """Edge cases the reference defines: empty arrays flow through filters / mixer / decimator,
+    the stateful FM discriminator rejects an empty chunk, one-sample chunks carry state."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    from directdemod_b200 import demod_am
+    e = np.zeros(0, dtype=np.complex64)
+    f = filters.blackmanHarris(151)
+    assert f.applyOn(e).shape == (0,)
+    assert filters.butter(48000, 1000).applyOn(np.zeros(0)).shape == (0,)
+    s = comm.commSignal(2048000, e).offsetFreq(1000.0).filter(filters.blackmanHarris(151)).bwLim(60000)
+    assert s.length == 0 and s.signal.shape == (0,) and s.sampRate == 60235
+    with pytest.raises(IndexError):
+        demod_fm.demod_fm().demod(e)
+    assert demod_fm.demod_fm(storeState=False).demod(e).shape == (0,)
+    out = comm.commSignal(1)
+    out.extend(comm.commSignal(100, np.zeros(0)))
+    assert out.length == 0 and out.sampRate == 100
+    # one-sample chunks through a stateful FIR + IIR + FM: same as one call
+    rng = np.random.default_rng(23)
+    x = (rng.standard_normal(40) + 1j * rng.standard_normal(40)).astype(np.complex64)
+    f1, f2 = filters.hamming(7), filters.hamming(7)
+    g1, g2 = filters.butter(48000, 3000, n=3), filters.butter(48000, 3000, n=3)
+    d1, d2 = demod_fm.demod_fm(), demod_fm.demod_fm()
+    one = d1.demod(g1.applyOn(f1.applyOn(x)))
+    parts = [d2.demod(g2.applyOn(f2.applyOn(x[i:i + 1]))) for i in range(40)]
+    assert O.rel_rms(np.concatenate(parts), one) <= TOL
+    # AM of a single sample / two samples (scipy.hilbert of tiny arrays)
+    for m in (1, 2, 3):
+        v = np.arange(1.0, m + 1)
+        assert O.rel_rms(demod_am.demod_am().demod(v), O.am_envelope(v)) <= TOL
+    # non-contiguous and integer inputs are accepted like numpy accepts them
+    y = filters.rollingAverage(4).applyOn(np.arange(40)[::2])
+    want, _ = O.filt_stateful([0.25] * 4, [1], np.arange(40)[::2].astype(float), O.initial_zi([0.25] * 4))
+    assert O.rel_rms(y, want) <= TOL
