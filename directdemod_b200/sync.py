@@ -44,6 +44,19 @@ def correlate(hay, needle, normalised=True):
     return out
 
 
+_stage = {"buf": None}
+
+
+def _pinned(count):
+    """A pinned float64 host buffer of at least ``count`` elements, grown geometrically."""
+    t = _dev.torch()
+    buf = _stage["buf"]
+    if buf is None or buf.numel() < count:
+        buf = t.empty(max(count + count // 4, 1 << 16), dtype=t.float64, pin_memory=True)
+        _stage["buf"] = buf
+    return buf
+
+
 def pick_peaks(cor, samp_rate, needle_len):
     """Threshold + group-maximum scan of decode_noaa.py:710-751 on a cuda float64 tensor.
     Returns (sorted int64 numpy array of sync START positions, threshold)."""
@@ -74,8 +87,14 @@ def pick_peaks(cor, samp_rate, needle_len):
     if m == 0:
         # the reference appends currentMaxIndex == None and fails on None - int
         raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int'")
-    idx_h = np.ascontiguousarray(idx[:m].cpu().numpy())
-    val_h = np.ascontiguousarray(val[:m].cpu().numpy())
+    # candidates -> host through a cached pinned staging buffer (a noisy pass can have millions)
+    stage = _pinned(2 * m)
+    stage[:m].copy_(idx[:m].view(t.float64), non_blocking=True)
+    stage[m:2 * m].copy_(val[:m], non_blocking=True)
+    t.cuda.current_stream(dev).synchronize()
+    both = stage[:2 * m].numpy()
+    idx_h = both[:m].view(np.int64)
+    val_h = both[m:2 * m]
     peaks = np.empty(m, dtype=np.int64)
     npk = C.c_int64()
     _lib.check(l.ddm_group_peaks(idx_h.ctypes.data_as(C.POINTER(C.c_int64)),
