@@ -70,6 +70,11 @@ SIGNATURES = {
     "ddm_fft_destroy": (_int, [_vp]),
     "ddm_am_hilbert": (_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "ddm_resample": (_int, [_vp, _vp, _i64, _int, _i64, _vp, _vp]),
+    "ddm_mix_rows_cf32": (_int, [_int, _vp, _i64, _i64, _dbl, _dbl, _vp]),
+    "ddm_filter_filtfilt_rows_dev": (_int, [_vp, _vp, _i64, _i64, _int, _vp, _vp]),
+    "ddm_fm_demod_rows": (_int, [_int, _vp, _i64, _i64, _vp, _vp]),
+    "ddm_rows_argmax": (_int, [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "ddm_rows_mean": (_int, [_int, _vp, _vp, _i64, _i64, _vp, _vp]),
     "ddm_resample_rows": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ddm_row_medians": (_int, [_int, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ddm_correlate": (_int, [_int, _vp, _i64, _int, _pdbl, _int, _int, _vp, _vp]),

@@ -643,6 +643,56 @@ __global__ void scale_state_kernel(const double *zi_base, int p, const S *x, dou
     state[i] = make_double2(__dmul_rn(zi_base[i], v.x), __dmul_rn(zi_base[i], v.y));
 }
 
+// ---- zero-phase FIR over many equal-length rows in one go --------------------------------
+// Row layout: [K-1 copies of the first extended sample | odd extension of the row].  The constant
+// prefix IS the state zi = lfilter_zi * ext[0] that filtfilt seeds each pass with (a FIR remembers
+// K-1 samples), and it shields a row from its predecessor, so one zero-state FIR over the
+// concatenation of all rows filters every row correctly; outputs under the prefix are discarded.
+template <typename S>
+__device__ __forceinline__ S ff_odd(const S e, const S v) {
+    if constexpr (std::is_same<S, float2>::value) return make_float2(2.f * e.x - v.x, 2.f * e.y - v.y);
+    else return 2.f * e - v;
+}
+
+template <typename S>
+__global__ void ff_rows_ext_kernel(const S *__restrict__ x, long long n, int pad, int hist, S *__restrict__ ext,
+                                   long long ls) {
+    const S *row = x + static_cast<size_t>(blockIdx.y) * n;
+    S *out = ext + static_cast<size_t>(blockIdx.y) * ls;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < ls; p += stride) {
+        const long long q = p < hist ? 0 : p - hist;              // position in the odd extension
+        S v;
+        if (q < pad) v = ff_odd<S>(row[0], row[pad - q]);
+        else if (q < pad + n) v = row[q - pad];
+        else v = ff_odd<S>(row[n - 1], row[n - 2 - (q - pad - n)]);
+        out[p] = v;
+    }
+}
+
+// second pass input: the valid outputs of the first pass reversed, behind a constant prefix
+template <typename S>
+__global__ void ff_rows_rev_kernel(const S *__restrict__ f1, long long m, int hist, S *__restrict__ e2, long long ls) {
+    const S *row = f1 + static_cast<size_t>(blockIdx.y) * ls + hist;
+    S *out = e2 + static_cast<size_t>(blockIdx.y) * ls;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < ls; p += stride) {
+        const long long q = p < hist ? 0 : p - hist;
+        out[p] = row[m - 1 - q];
+    }
+}
+
+// result: second pass outputs reversed again, extension trimmed
+template <typename S>
+__global__ void ff_rows_out_kernel(const S *__restrict__ f2, long long n, long long m, int pad, int hist,
+                                   long long ls, S *__restrict__ y) {
+    const S *row = f2 + static_cast<size_t>(blockIdx.y) * ls + hist;
+    S *out = y + static_cast<size_t>(blockIdx.y) * n;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        out[i] = row[m - 1 - (pad + i)];
+}
+
 }  // namespace ddm
 
 // =====================================================================================
@@ -1025,6 +1075,64 @@ int run_filter(ddm_filter *f, const void *x, long long n, bool cplx, void *y, co
 }  // namespace
 
 extern "C" {
+
+int ddm_filter_filtfilt_rows_dev(ddm_filter *f, const void *x_dev, int64_t rows, int64_t n, int is_complex,
+                                 void *y_dev, void *stream) {
+    DDM_REQUIRE(f != nullptr, "ddm_filter_filtfilt_rows_dev: NULL handle");
+    DDM_REQUIRE(rows >= 0 && n >= 0, "ddm_filter_filtfilt_rows_dev: bad sizes");
+    if (rows == 0) return DDM_OK;
+    const size_t esz = is_complex ? sizeof(float2) : sizeof(float);
+    if (!f->fir || f->order == 0) {
+        // IIR (or a single tap): row by row through the one-row entry point
+        for (int64_t r = 0; r < rows; ++r) {
+            int rc = ddm_filter_filtfilt_dev(f, static_cast<const unsigned char *>(x_dev) + r * n * esz, n, is_complex,
+                                             static_cast<unsigned char *>(y_dev) + r * n * esz, stream);
+            if (rc != DDM_OK) return rc;
+        }
+        return DDM_OK;
+    }
+    const int pad = 3 * (f->order + 1);
+    DDM_REQUIRE(n > pad, "ddm_filter_filtfilt_rows_dev: row length %lld must be greater than padlen %d",
+                static_cast<long long>(n), pad);
+    DDM_REQUIRE(x_dev != nullptr && y_dev != nullptr, "ddm_filter_filtfilt_rows_dev: NULL buffer");
+    DDM_REQUIRE(rows <= 65535, "ddm_filter_filtfilt_rows_dev: at most 65535 rows per call");
+    DeviceGuard guard(f->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int hist = f->order;                       // K - 1
+    const long long m = n + 2LL * pad;
+    const long long ls = hist + m;
+    const size_t need = esz * static_cast<size_t>(ls) * rows;
+    if (need > f->tmp_cap) {
+        DDM_CUDA(cudaStreamSynchronize(st));
+        cudaFree(f->d_tmp[0]);
+        cudaFree(f->d_tmp[1]);
+        f->d_tmp[0] = f->d_tmp[1] = nullptr;
+        f->tmp_cap = 0;
+        DDM_CUDA(cudaMalloc(&f->d_tmp[0], need));
+        DDM_CUDA(cudaMalloc(&f->d_tmp[1], need));
+        f->tmp_cap = need;
+    }
+    void *t0 = f->d_tmp[0], *t1 = f->d_tmp[1];
+    const bool cplx = is_complex != 0;
+    const int tb = 256;
+    const dim3 grid(static_cast<unsigned>(std::min<long long>((ls + tb - 1) / tb, 1024)), static_cast<unsigned>(rows));
+    int rc;
+#define DDM_FF_ROWS(S)                                                                                     \
+    ff_rows_ext_kernel<S><<<grid, tb, 0, st>>>(static_cast<const S *>(x_dev), n, pad, hist, static_cast<S *>(t0), ls); \
+    count_launch();                                                                                        \
+    rc = run_filter(f, t0, ls * rows, cplx, t1, nullptr, nullptr, st);                                     \
+    if (rc != DDM_OK) return rc;                                                                           \
+    ff_rows_rev_kernel<S><<<grid, tb, 0, st>>>(static_cast<const S *>(t1), m, hist, static_cast<S *>(t0), ls); \
+    count_launch();                                                                                        \
+    rc = run_filter(f, t0, ls * rows, cplx, t1, nullptr, nullptr, st);                                     \
+    if (rc != DDM_OK) return rc;                                                                           \
+    ff_rows_out_kernel<S><<<grid, tb, 0, st>>>(static_cast<const S *>(t1), n, m, pad, hist, ls, static_cast<S *>(y_dev)); \
+    count_launch();
+    if (cplx) { DDM_FF_ROWS(float2) } else { DDM_FF_ROWS(float) }
+#undef DDM_FF_ROWS
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
 
 int ddm_lfilter_zi(const double *b, int nb, const double *a, int na, double *zi_out) {
     DDM_REQUIRE(b && a && zi_out && nb >= 1 && na >= 1, "ddm_lfilter_zi: bad arguments");

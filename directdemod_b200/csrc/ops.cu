@@ -165,6 +165,81 @@ __global__ void cu8_kernel_scalar(const unsigned char *in, float2 *out, long lon
                              static_cast<float>(in[2 * i + 1]) - 127.5f);
 }
 
+// ---- operators over many equal-length rows (batched accurate sync, decode_noaa.py:844-877) ----
+// mixer restarting its sample index at every row (a commSignal without a chunker starts at 0)
+__global__ void mix_rows_kernel(float2 *x, long long row_len, long long total, double r_hi, double r_lo) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += stride)
+        x[i] = cmul(x[i], phase_rotator(r_hi, r_lo, i % row_len));
+}
+
+// out[r][i] = arg(x[r][i+1] conj x[r][i]), i < row_len - 1 (a fresh demod_fm per row)
+__global__ void fm_rows_kernel(const float2 *__restrict__ x, long long row_len, long long rows, float *__restrict__ out) {
+    const long long per = row_len - 1;
+    const long long total = per * rows;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total; t += stride) {
+        const long long r = t / per, i = t - r * per;
+        const float2 p = x[r * row_len + i], c = x[r * row_len + i + 1];
+        out[t] = atan2f(fmaf(c.y, p.x, -c.x * p.y), fmaf(c.x, p.x, c.y * p.y));
+    }
+}
+
+// first index of the maximum of every row of a float64 matrix (strict '<' scan order: the first
+// of equal maxima wins, like decode_noaa.py:742), and the maximum itself
+__global__ void __launch_bounds__(256)
+rows_argmax_kernel(const double *__restrict__ x, long long row_stride, long long row_len, long long *__restrict__ idx,
+                   double *__restrict__ val) {
+    __shared__ double sv[256];
+    __shared__ long long si[256];
+    const double *row = x + static_cast<size_t>(blockIdx.x) * row_stride;
+    double best = -INFINITY;
+    long long bi = -1;
+    for (long long i = threadIdx.x; i < row_len; i += blockDim.x) {
+        const double v = row[i];
+        if (bi < 0 || v > best) {          // ascending i per thread: '>' keeps the first maximum
+            best = v;
+            bi = i;
+        }
+    }
+    sv[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            const double ov = sv[threadIdx.x + off];
+            const long long oi = si[threadIdx.x + off];
+            const double mv = sv[threadIdx.x];
+            const long long mi = si[threadIdx.x];
+            if (oi >= 0 && (mi < 0 || ov > mv || (ov == mv && oi < mi))) {
+                sv[threadIdx.x] = ov;
+                si[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        idx[blockIdx.x] = si[0];
+        val[blockIdx.x] = sv[0];
+    }
+}
+
+// mean of x[start[r] : start[r] + len] per row (np.average of a float32 slice, accumulated in f64)
+__global__ void __launch_bounds__(256)
+rows_mean_kernel(const float *__restrict__ x, const long long *__restrict__ start, long long len, double *__restrict__ out) {
+    __shared__ double ss[256];
+    const float *p = x + start[blockIdx.x];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) s += static_cast<double>(p[i]);
+    ss[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) ss[threadIdx.x] += ss[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = ss[0] / static_cast<double>(len);
+}
+
 // scipy.signal.medfilt(x, k): median of the k-sample window centred on each sample, zeros
 // outside the array (filters.py:322-326).  One thread per output; the window is kept sorted by
 // insertion in local memory (k is small: the reference's default is 5).
@@ -415,6 +490,66 @@ int ddm_stride_copy(int device, const void *x_dev, int64_t n, int elem_bytes, in
     else
         stride_copy_kernel<double2><<<grid, kOpsThreads, 0, st>>>(
             static_cast<const double2 *>(x_dev), static_cast<double2 *>(out_dev), m, offset, step);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_mix_rows_cf32(int device, void *x_dev, int64_t rows, int64_t row_len, double freq_offset, double samp_rate,
+                      void *stream) {
+    DDM_REQUIRE(rows >= 0 && row_len >= 0, "ddm_mix_rows_cf32: bad sizes");
+    DDM_REQUIRE(samp_rate > 0, "ddm_mix_rows_cf32: sampling rate must be positive");
+    if (rows == 0 || row_len == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr, "ddm_mix_rows_cf32: NULL signal");
+    DDM_CHECK_DEVICE(device, "ddm_mix_rows_cf32");
+    DeviceGuard guard(device);
+    const double r_hi = freq_offset / samp_rate;
+    const double r_lo = std::fma(-r_hi, samp_rate, freq_offset) / samp_rate;
+    mix_rows_kernel<<<ops_grid(device, rows * row_len), kOpsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float2 *>(x_dev), row_len, rows * row_len, r_hi, r_lo);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_fm_demod_rows(int device, const void *x_dev, int64_t rows, int64_t row_len, void *out_dev, void *stream) {
+    DDM_REQUIRE(rows >= 0 && row_len >= 0, "ddm_fm_demod_rows: bad sizes");
+    if (rows == 0 || row_len < 2) return DDM_OK;
+    DDM_REQUIRE(x_dev != nullptr && out_dev != nullptr, "ddm_fm_demod_rows: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_fm_demod_rows");
+    DeviceGuard guard(device);
+    fm_rows_kernel<<<ops_grid(device, rows * (row_len - 1)), kOpsThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float2 *>(x_dev), row_len, rows, static_cast<float *>(out_dev));
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_rows_argmax(int device, const void *x_f64_dev, int64_t rows, int64_t row_stride, int64_t row_len,
+                    void *idx_i64_dev, void *val_f64_dev, void *stream) {
+    DDM_REQUIRE(rows >= 0 && row_len >= 1 && row_stride >= row_len, "ddm_rows_argmax: bad sizes");
+    if (rows == 0) return DDM_OK;
+    DDM_REQUIRE(x_f64_dev && idx_i64_dev && val_f64_dev, "ddm_rows_argmax: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_rows_argmax");
+    DeviceGuard guard(device);
+    rows_argmax_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const double *>(x_f64_dev), row_stride, row_len, static_cast<long long *>(idx_i64_dev),
+        static_cast<double *>(val_f64_dev));
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
+int ddm_rows_mean(int device, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t len,
+                  void *out_f64_dev, void *stream) {
+    DDM_REQUIRE(rows >= 0 && len >= 1, "ddm_rows_mean: bad sizes");
+    if (rows == 0) return DDM_OK;
+    DDM_REQUIRE(x_dev && row_start_dev && out_f64_dev, "ddm_rows_mean: NULL argument");
+    DDM_CHECK_DEVICE(device, "ddm_rows_mean");
+    DeviceGuard guard(device);
+    rows_mean_kernel<<<static_cast<unsigned>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float *>(x_dev), reinterpret_cast<const long long *>(row_start_dev), len,
+        static_cast<double *>(out_f64_dev));
     DDM_CUDA(cudaGetLastError());
     count_launch();
     return DDM_OK;

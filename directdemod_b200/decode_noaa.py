@@ -379,7 +379,86 @@ class decode_noaa:
                 logging.info('NOAA Signal was not found')
         return [self._syncA, self._syncB]
 
-    def _accurate(self, csync, syncBits, width, useNormCorrelate):
+    def _accurate(self, csync, syncBits, width, useNormCorrelate, batch=256):
+        """All windows of one sync kind, ``batch`` at a time through row-batched kernels: the
+        windows are independent and equally long, so mixer, zero-phase filters, FM, Hilbert AM and
+        correlation each run ONCE per batch instead of once per window (decode_noaa.py:844-877).
+        With a single candidate group per window (window < minimum peak distance) the reference's
+        threshold + group scan reduces to the first maximum of the correlation."""
+        t = _dev.torch()
+        l = _lib.lib()
+        fs = self._sigsrc.sampFreq
+        starts = [int(i) - int(width) for i in csync
+                  if int(i) - int(width) >= 0 and int(i) + int(width) <= self._sigsrc.length]
+        n = 2 * int(width)
+        needle = sync.sync_needle(syncBits, fs, useNormCorrelate)
+        m = len(needle)
+        if not starts or n - 1 >= constants.NOAA_MINPEAKDIST * fs or n - 1 <= 3 * 492:
+            return self._accurate_loop(csync, syncBits, width, useNormCorrelate)
+        bh = filters.blackmanHarris(151, zeroPhase=True)
+        ham = filters.hamming(492, zeroPhase=True)
+        out, pk, tm = [], [], []
+        raw = getattr(self._sigsrc, "readRaw", None)
+        for b0 in range(0, len(starts), batch):
+            rows_s = starts[b0:b0 + batch]
+            w = len(rows_s)
+            # ---- gather the windows into a [w][n] cf32 matrix on the device ----
+            if raw is not None:
+                u8 = t.from_numpy(np.stack([raw(s0, s0 + n).data for s0 in rows_s])).to("cuda")
+                x = t.empty((w, n), dtype=t.complex64, device=u8.device)
+                _lib.check(l.ddm_cu8_to_cf32(x.device.index, _dev.ptr(u8), w * n, _dev.ptr(x),
+                                             _dev.stream_ptr(x.device.index)), "ddm_cu8_to_cf32")
+            else:
+                blocks = [self._sigsrc.read(s0, s0 + n) for s0 in rows_s]
+                if _dev.is_tensor(blocks[0]):
+                    x = t.stack([bk.to(t.complex64) for bk in blocks]).contiguous()
+                else:
+                    x = t.from_numpy(np.stack(blocks).astype(np.complex64)).to("cuda")
+            dev = x.device.index
+            st = _dev.stream_ptr(dev)
+            _lib.check(l.ddm_mix_rows_cf32(dev, _dev.ptr(x), w, n, float(self._offset), float(fs), st),
+                       "ddm_mix_rows_cf32")
+            y = t.empty_like(x)
+            _lib.check(l.ddm_filter_filtfilt_rows_dev(bh._handle(), _dev.ptr(x), w, n, 1, _dev.ptr(y), st),
+                       "ddm_filter_filtfilt_rows_dev")
+            fm = t.empty((w, n - 1), dtype=t.float32, device=x.device)
+            _lib.check(l.ddm_fm_demod_rows(dev, _dev.ptr(y), w, n, _dev.ptr(fm), st), "ddm_fm_demod_rows")
+            am = fftops.hilbert_envelope(fm.reshape(-1), n - 1).reshape(w, n - 1)       # one transform per row
+            hay = t.empty_like(am)
+            _lib.check(l.ddm_filter_filtfilt_rows_dev(ham._handle(), _dev.ptr(am), w, n - 1, 0, _dev.ptr(hay), st),
+                       "ddm_filter_filtfilt_rows_dev")
+            # rows separated by m zeros: one flat correlation serves all rows (windows never reach a neighbour)
+            c = m // 2
+            stride = (n - 1) + m
+            padded = t.zeros((w, stride), dtype=t.float32, device=x.device)
+            padded[:, c:c + n - 1] = hay
+            cor = sync.correlate(padded.reshape(-1), needle, normalised=useNormCorrelate)
+            idx = t.empty(w, dtype=t.int64, device=x.device)
+            val = t.empty(w, dtype=t.float64, device=x.device)
+            # output i of row r sits at flat index r*stride + i + c
+            _lib.check(l.ddm_rows_argmax(dev, C.c_void_p(cor.data_ptr() + 8 * c), w, stride, n - 1, _dev.ptr(idx),
+                                         _dev.ptr(val), st), "ddm_rows_argmax")
+            idx_h = idx.cpu().numpy()
+            val_h = val.cpu().numpy()
+            det = idx_h - int(m / 2)                                   # start of the sync inside the window
+            # np.average(sig[i + m : i + 2 m]) of the AM signal where it fits (decode_noaa.py:757-758)
+            fits = [r for r in range(w) if det[r] + 2 * m < n - 1]
+            means = {}
+            if fits:
+                so = t.as_tensor(np.array([r * (n - 1) + det[r] + m for r in fits], dtype=np.int64), device=x.device)
+                mo = t.empty(len(fits), dtype=t.float64, device=x.device)
+                _lib.check(l.ddm_rows_mean(dev, _dev.ptr(am), _dev.ptr(so), len(fits), m, _dev.ptr(mo), st),
+                           "ddm_rows_mean")
+                means = dict(zip(fits, mo.cpu().numpy().tolist()))
+            for r in range(w):
+                out.append(int(det[r]) + rows_s[r])
+                pk.append(float(val_h[r]))
+                tm.append(means.get(r))
+        return out, pk, tm
+
+    def _accurate_loop(self, csync, syncBits, width, useNormCorrelate):
+        """The reference's per-window formulation, operator by operator (kept as the general
+        path and as the cross-check of the batched one)."""
         out, pk, tm = [], [], []
         for i in csync:
             startI = int(i) - int(width)

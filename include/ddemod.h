@@ -229,6 +229,23 @@ int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double
 int ddm_bank4(int device, const void *x_dev, int64_t n, int x_is_f64, const double *taps4_host, int nbuf,
               void *out_f32_dev, void *stream);
 
+/* ---- many equal-length rows at once (the accurate-sync windows of decode_noaa.py:844-877) ----
+ * Each row is an independent short signal; batching them removes ~60 launches per window. */
+/* offsetFreq with the sample index restarting at 0 on every row (cf32 [rows][row_len], in place) */
+int ddm_mix_rows_cf32(int device, void *x_dev, int64_t rows, int64_t row_len, double freq_offset,
+                      double samp_rate, void *stream);
+/* filtfilt(b, a, row) for every row; x, y: [rows][n] f32 or cf32 */
+int ddm_filter_filtfilt_rows_dev(ddm_filter *f, const void *x_dev, int64_t rows, int64_t n, int is_complex,
+                                 void *y_dev, void *stream);
+/* a fresh demod_fm per row: out [rows][row_len - 1] f32 */
+int ddm_fm_demod_rows(int device, const void *x_dev, int64_t rows, int64_t row_len, void *out_dev, void *stream);
+/* first index and value of the maximum of every row of a float64 matrix */
+int ddm_rows_argmax(int device, const void *x_f64_dev, int64_t rows, int64_t row_stride, int64_t row_len,
+                    void *idx_i64_dev, void *val_f64_dev, void *stream);
+/* mean of x[row_start[r] : row_start[r] + len] (f32 in, f64 out) */
+int ddm_rows_mean(int device, const void *x_dev, const int64_t *row_start_dev, int64_t rows, int64_t len,
+                  void *out_f64_dev, void *stream);
+
 /* ---- image-line assembly helpers (decode_noaa.getImage, decode_noaa.py:255-465) ---------
  * signal.resample of many equal-length rows of one f32 array in one batch: row r is
  * x[row_start[r] : row_start[r] + n] -> out[r][0:num]   (decode_noaa.py:350-351) */

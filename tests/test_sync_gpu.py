@@ -134,6 +134,25 @@ def test_accurate_sync_positions_bit_exact(apt_pass):
         assert list(map(int, got[:len(want)])) == list(map(int, want))
 
 
+def test_batched_accurate_sync_equals_per_window_path(apt_pass):
+    """The row-batched accurate sync (one launch sequence per 256 windows) against the per-window
+    operator-by-operator path: identical positions, peak heights and time-sync means."""
+    from directdemod_b200 import constants, decode_noaa
+    x, fs = apt_pass
+    dec = decode_noaa.decode_noaa(ArraySource(x[:int(7.2 * fs)], fs), 30000.0)
+    dec.getCrudeSync()
+    width = int(3 * constants.NOAA_T * 40 * fs)
+    csync = dec._syncA / dec._syncCrudeSampRate * fs
+    for norm in (True, False):
+        a = dec._accurate(csync, constants.NOAA_SYNCA, width, norm, batch=5)       # several batches
+        b = dec._accurate_loop(csync, constants.NOAA_SYNCA, width, norm)
+        assert len(a[0]) == len(b[0]) >= 8
+        assert list(map(int, a[0])) == list(map(int, b[0]))
+        np.testing.assert_allclose(a[1], b[1], rtol=1e-5)
+        assert [v is None for v in a[2]] == [v is None for v in b[2]]
+        np.testing.assert_allclose([v for v in a[2] if v is not None], [v for v in b[2] if v is not None], rtol=1e-5)
+
+
 def test_afsk_bank_matches_oracle():
     from directdemod_b200 import afsk
     rng = np.random.default_rng(5)
