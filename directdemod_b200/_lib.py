@@ -80,6 +80,7 @@ SIGNATURES = {
     "ddm_correlate": (_int, [_int, _vp, _i64, _int, _pdbl, _int, _int, _vp, _vp]),
     "ddm_topk_sums": (_int, [_int, _vp, _i64, _i64, _pdbl, _pdbl, _vp]),
     "ddm_compact_above": (_int, [_int, _vp, _i64, _dbl, _vp, _vp, _i64, _pi64, _vp]),
+    "ddm_pick_peaks": (_int, [_int, _vp, _i64, _dbl, _dbl, _pi64, _i64, _pi64, _vp]),
     "ddm_group_peaks": (_int, [_pi64, _pdbl, _i64, _dbl, _pi64, _i64, _pi64]),
     "ddm_bank4": (_int, [_int, _vp, _i64, _int, _pdbl, _int, _vp, _vp]),
 }

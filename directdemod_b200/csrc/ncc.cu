@@ -346,6 +346,181 @@ __global__ void compact_write_kernel(const double *__restrict__ x, long long n, 
     }
 }
 
+// ---- the group-maximum scan of decode_noaa.py:731-746, exactly, without the candidate list ----
+// The reference walks the sorted candidates (cor > thr) keeping a running maximum; a candidate at
+// distance >= minPkDist from the CURRENT maximum closes the group.  Restated: call a candidate r
+// "dominant" when no later sample within ceil(minPkDist) - 1 positions is strictly greater.  The
+// running maximum climbs the chain of next-strictly-greater elements and stops at the first
+// dominant one, and no chain step can jump over the first dominant candidate at or after the group
+// start (if it did, a greater value would sit inside that candidate's window).  Hence
+//     peak(group) = first dominant candidate >= group start,
+//     next group start = first candidate >= peak + ceil(minPkDist),
+// which needs (1) a sliding-window maximum (van Herk / Gil-Werman: prefix and suffix maxima inside
+// blocks of the window length), (2) "next flagged index" tables (suffix-min scans), and (3) a walk
+// of two loads per peak.  A noisy pass has millions of candidates; none of them leaves the device.
+constexpr int kWmThreads = 256;
+
+// F[j] = max(x[block start .. j]), B[j] = max(x[j .. block end]) for blocks of `w` samples
+__global__ void __launch_bounds__(kWmThreads)
+winmax_blocks_kernel(const double *__restrict__ x, long long n, long long w, double *__restrict__ F,
+                     double *__restrict__ B) {
+    __shared__ double pm[kWmThreads], sm[kWmThreads];
+    const long long b0 = static_cast<long long>(blockIdx.x) * w;
+    const long long b1 = b0 + w < n ? b0 + w : n;
+    const long long len = b1 - b0;
+    const long long per = (len + kWmThreads - 1) / kWmThreads;
+    const long long c0 = b0 + static_cast<long long>(threadIdx.x) * per;
+    const long long c1 = c0 + per < b1 ? c0 + per : b1;
+    double m = -INFINITY;
+    for (long long i = c0; i < c1; ++i) m = fmax(m, x[i]);
+    pm[threadIdx.x] = m;
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int off = 1; off < kWmThreads; off <<= 1) {
+        double a = -INFINITY, c = -INFINITY;
+        if (threadIdx.x >= off) a = pm[threadIdx.x - off];
+        if (threadIdx.x + off < kWmThreads) c = sm[threadIdx.x + off];
+        __syncthreads();
+        pm[threadIdx.x] = fmax(pm[threadIdx.x], a);
+        sm[threadIdx.x] = fmax(sm[threadIdx.x], c);
+        __syncthreads();
+    }
+    double run = threadIdx.x > 0 ? pm[threadIdx.x - 1] : -INFINITY;
+    for (long long i = c0; i < c1; ++i) {
+        run = fmax(run, x[i]);
+        F[i] = run;
+    }
+    run = threadIdx.x + 1 < kWmThreads ? sm[threadIdx.x + 1] : -INFINITY;
+    for (long long i = c1 - 1; i >= c0; --i) {
+        run = fmax(run, x[i]);
+        B[i] = run;
+    }
+}
+
+constexpr int kFlagBlock = 1024;
+constexpr long long kNoIndex = 0x7FFFFFFFFFFFFFFFLL;
+
+// per sample: candidate / dominant flags, turned into "next flagged index inside this 1024-block"
+// tables plus the first flagged index of every block
+__global__ void __launch_bounds__(kFlagBlock)
+peak_flags_kernel(const double *__restrict__ x, const double *__restrict__ F, const double *__restrict__ B,
+                  long long n, long long w, double thr, long long *__restrict__ next_cand,
+                  long long *__restrict__ next_dom, long long *__restrict__ first_cand,
+                  long long *__restrict__ first_dom) {
+    __shared__ long long sc[kFlagBlock], sd[kFlagBlock];
+    const long long i = static_cast<long long>(blockIdx.x) * kFlagBlock + threadIdx.x;
+    long long c = kNoIndex, d = kNoIndex;
+    if (i < n) {
+        const double v = x[i];
+        if (v > thr) {
+            c = i;
+            // maximum over (i, i + w], clipped at the end of the array
+            double mx = -HUGE_VAL;
+            const long long a = i + 1;
+            long long b = i + w;
+            if (b > n - 1) b = n - 1;
+            if (a <= b) {
+                const long long ba = a / w, bb = b / w;
+                if (ba != bb) {
+                    mx = fmax(B[a], F[b]);
+                } else if (b == n - 1 || (b + 1) % w == 0) {
+                    mx = B[a];                   // the window runs to the end of its block (or of the array)
+                } else {
+                    // shorter than a block: never for windows of exactly w samples, kept for safety
+                    for (long long k = a; k <= b; ++k) mx = fmax(mx, x[k]);
+                }
+            }
+            if (!(mx > v)) d = i;
+        }
+    }
+    sc[threadIdx.x] = c;
+    sd[threadIdx.x] = d;
+    __syncthreads();
+    // suffix minimum inside the block
+    for (int off = 1; off < kFlagBlock; off <<= 1) {
+        long long oc = kNoIndex, od = kNoIndex;
+        if (threadIdx.x + off < kFlagBlock) {
+            oc = sc[threadIdx.x + off];
+            od = sd[threadIdx.x + off];
+        }
+        __syncthreads();
+        if (oc < sc[threadIdx.x]) sc[threadIdx.x] = oc;
+        if (od < sd[threadIdx.x]) sd[threadIdx.x] = od;
+        __syncthreads();
+    }
+    if (i < n) {
+        next_cand[i] = sc[threadIdx.x];
+        next_dom[i] = sd[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        first_cand[blockIdx.x] = sc[0];
+        first_dom[blockIdx.x] = sd[0];
+    }
+}
+
+// carry[b] = first flagged index in blocks >= b (suffix minimum over the per-block firsts); one CTA
+__global__ void __launch_bounds__(1024)
+peak_carry_kernel(long long *__restrict__ first_cand, long long *__restrict__ first_dom, long long nblk) {
+    __shared__ long long sc[1024], sd[1024];
+    // each thread owns a contiguous range of blocks; ranges are combined right to left
+    const long long per = (nblk + 1023) / 1024;
+    const long long r0 = static_cast<long long>(threadIdx.x) * per;
+    const long long r1 = r0 + per < nblk ? r0 + per : nblk;
+    long long mc = kNoIndex, md = kNoIndex;
+    for (long long b = r0; b < r1; ++b) {
+        if (first_cand[b] < mc) mc = first_cand[b];
+        if (first_dom[b] < md) md = first_dom[b];
+    }
+    sc[threadIdx.x] = mc;
+    sd[threadIdx.x] = md;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        long long oc = kNoIndex, od = kNoIndex;
+        if (threadIdx.x + off < 1024) {
+            oc = sc[threadIdx.x + off];
+            od = sd[threadIdx.x + off];
+        }
+        __syncthreads();
+        if (oc < sc[threadIdx.x]) sc[threadIdx.x] = oc;
+        if (od < sd[threadIdx.x]) sd[threadIdx.x] = od;
+        __syncthreads();
+    }
+    long long cc = threadIdx.x + 1 < 1024 ? sc[threadIdx.x + 1] : kNoIndex;
+    long long cd = threadIdx.x + 1 < 1024 ? sd[threadIdx.x + 1] : kNoIndex;
+    for (long long b = r1 - 1; b >= r0; --b) {
+        if (first_cand[b] < cc) cc = first_cand[b];
+        if (first_dom[b] < cd) cd = first_dom[b];
+        first_cand[b] = cc;
+        first_dom[b] = cd;
+    }
+}
+
+__device__ __forceinline__ long long next_flagged(const long long *__restrict__ local, const long long *__restrict__ carry,
+                                                  long long nblk, long long i) {
+    const long long v = local[i];
+    if (v != kNoIndex) return v;
+    const long long b = i / kFlagBlock + 1;
+    return b < nblk ? carry[b] : kNoIndex;
+}
+
+__global__ void peak_walk_kernel(const long long *__restrict__ next_cand, const long long *__restrict__ next_dom,
+                                 const long long *__restrict__ carry_cand, const long long *__restrict__ carry_dom,
+                                 long long n, long long nblk, long long close_dist, long long *__restrict__ peaks,
+                                 long long cap, long long *__restrict__ count) {
+    long long np = 0;
+    long long s = next_flagged(next_cand, carry_cand, nblk, 0);
+    while (s != kNoIndex) {
+        const long long d = next_flagged(next_dom, carry_dom, nblk, s);
+        if (d == kNoIndex) break;                    // cannot happen: the last candidate is dominant
+        if (np < cap) peaks[np] = d;
+        ++np;
+        const long long p = d + close_dist;
+        if (p >= n) break;
+        s = next_flagged(next_cand, carry_cand, nblk, p);
+    }
+    *count = np;
+}
+
 // ---- AFSK correlator bank ---------------------------------------------------------------
 // out[s] = (sum x[s+k] t0[k])^2 + (sum x[s+k] t1[k])^2 - (sum x[s+k] t2[k])^2 - (sum x[s+k] t3[k])^2
 // for s < n - nbuf, 0 for the last nbuf outputs (loop bound of decode_afsk1200.py:129)
@@ -631,6 +806,61 @@ int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double
     if (np > capacity) {
         set_error("ddm_group_peaks: %lld peaks, capacity %lld", static_cast<long long>(np),
                   static_cast<long long>(capacity));
+        return DDM_ERR_CAPACITY;
+    }
+    return DDM_OK;
+}
+
+int ddm_pick_peaks(int device, const void *x_f64_dev, int64_t n, double threshold, double min_dist,
+                   int64_t *peaks_host, int64_t capacity, int64_t *n_peaks, void *stream) {
+    DDM_REQUIRE(n >= 0 && capacity >= 0 && n_peaks != nullptr, "ddm_pick_peaks: bad arguments");
+    *n_peaks = 0;
+    if (n == 0) return DDM_OK;
+    DDM_REQUIRE(x_f64_dev != nullptr, "ddm_pick_peaks: NULL buffer");
+    DDM_REQUIRE(min_dist > 1.0, "ddm_pick_peaks: the minimum peak distance must exceed one sample");
+    int rc = check_device(device, "ddm_pick_peaks");
+    if (rc != DDM_OK) return rc;
+    DeviceGuard guard(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const double *x = static_cast<const double *>(x_f64_dev);
+    const long long close_dist = static_cast<long long>(std::ceil(min_dist));   // i - r >= min_dist
+    long long w = close_dist - 1;                                               // records possible up to here
+    if (w > n) w = n;
+    const long long wblocks = (n + w - 1) / w;
+    const long long nblk = (n + kFlagBlock - 1) / kFlagBlock;
+    DevBuf F, B, nc, nd, fc, fd, out;
+    if ((rc = F.alloc(device, 0, sizeof(double) * n)) != DDM_OK) return rc;
+    if ((rc = B.alloc(device, 1, sizeof(double) * n)) != DDM_OK) return rc;
+    if ((rc = nc.alloc(device, 2, sizeof(long long) * n)) != DDM_OK) return rc;
+    if ((rc = nd.alloc(device, 3, sizeof(long long) * n)) != DDM_OK) return rc;
+    if ((rc = fc.alloc(device, 4, sizeof(long long) * nblk)) != DDM_OK) return rc;
+    if ((rc = fd.alloc(device, 5, sizeof(long long) * nblk)) != DDM_OK) return rc;
+    if ((rc = out.alloc(device, 6, sizeof(long long) * (capacity + 1))) != DDM_OK) return rc;
+    winmax_blocks_kernel<<<static_cast<unsigned>(wblocks), kWmThreads, 0, st>>>(x, n, w, static_cast<double *>(F.p),
+                                                                                static_cast<double *>(B.p));
+    peak_flags_kernel<<<static_cast<unsigned>(nblk), kFlagBlock, 0, st>>>(
+        x, static_cast<const double *>(F.p), static_cast<const double *>(B.p), n, w, threshold,
+        static_cast<long long *>(nc.p), static_cast<long long *>(nd.p), static_cast<long long *>(fc.p),
+        static_cast<long long *>(fd.p));
+    peak_carry_kernel<<<1, 1024, 0, st>>>(static_cast<long long *>(fc.p), static_cast<long long *>(fd.p), nblk);
+    long long *peaks_dev = static_cast<long long *>(out.p);
+    peak_walk_kernel<<<1, 1, 0, st>>>(static_cast<const long long *>(nc.p), static_cast<const long long *>(nd.p),
+                                     static_cast<const long long *>(fc.p), static_cast<const long long *>(fd.p), n, nblk,
+                                     close_dist, peaks_dev + 1, capacity, peaks_dev);
+    count_launch(4);
+    DDM_CUDA(cudaGetLastError());
+    long long cnt = 0;
+    DDM_CUDA(cudaMemcpyAsync(&cnt, peaks_dev, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    DDM_CUDA(cudaStreamSynchronize(st));
+    *n_peaks = cnt;
+    const long long take = cnt < capacity ? cnt : capacity;
+    if (take > 0) {
+        DDM_REQUIRE(peaks_host != nullptr, "ddm_pick_peaks: NULL output");
+        DDM_CUDA(cudaMemcpyAsync(peaks_host, peaks_dev + 1, sizeof(long long) * take, cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+    }
+    if (cnt > capacity) {
+        set_error("ddm_pick_peaks: %lld peaks, capacity %lld", cnt, static_cast<long long>(capacity));
         return DDM_ERR_CAPACITY;
     }
     return DDM_OK;

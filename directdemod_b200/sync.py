@@ -44,6 +44,43 @@ def correlate(hay, needle, normalised=True):
     return out
 
 
+def _pick_peaks_host_scan(cor, avgpk, min_dist, expected):
+    """Candidates to the host, then the sequential scan (ddm_compact_above + ddm_group_peaks): the
+    general form, used for degenerate minimum distances and as the cross-check of ddm_pick_peaks."""
+    t = _dev.torch()
+    l = _lib.lib()
+    n = cor.numel()
+    dev = cor.device.index
+    st = _dev.stream_ptr(dev)
+    cap = max(4096, 64 * expected)
+    while True:
+        idx = t.empty(cap, dtype=t.int64, device=cor.device)
+        val = t.empty(cap, dtype=t.float64, device=cor.device)
+        cnt = C.c_int64()
+        _lib.check(l.ddm_compact_above(dev, _dev.ptr(cor), n, avgpk, _dev.ptr(idx), _dev.ptr(val), cap,
+                                       C.byref(cnt), st), "ddm_compact_above")
+        if cnt.value <= cap:
+            break
+        cap = int(cnt.value)
+    m = int(cnt.value)
+    if m == 0:
+        raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int'")
+    stage = _pinned(2 * m)
+    stage[:m].copy_(idx[:m].view(t.float64), non_blocking=True)
+    stage[m:2 * m].copy_(val[:m], non_blocking=True)
+    t.cuda.current_stream(dev).synchronize()
+    both = stage[:2 * m].numpy()
+    idx_h = both[:m].view(np.int64)
+    val_h = both[m:2 * m]
+    peaks = np.empty(m, dtype=np.int64)
+    npk = C.c_int64()
+    _lib.check(l.ddm_group_peaks(idx_h.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 val_h.ctypes.data_as(C.POINTER(C.c_double)), m, float(min_dist),
+                                 peaks.ctypes.data_as(C.POINTER(C.c_int64)), m, C.byref(npk)),
+               "ddm_group_peaks")
+    return peaks, npk
+
+
 _stage = {"buf": None}
 
 
@@ -73,34 +110,24 @@ def pick_peaks(cor, samp_rate, needle_len):
                "ddm_topk_sums")
     avgpk = top.value / expected
     avgpk -= constants.NOAA_PEAKHEIGHTWIGGLE * (avgpk - (bottom.value / expected))
-    cap = max(4096, 64 * expected)
-    while True:
-        idx = t.empty(cap, dtype=t.int64, device=cor.device)
-        val = t.empty(cap, dtype=t.float64, device=cor.device)
-        cnt = C.c_int64()
-        _lib.check(l.ddm_compact_above(dev, _dev.ptr(cor), n, avgpk, _dev.ptr(idx), _dev.ptr(val), cap,
-                                       C.byref(cnt), st), "ddm_compact_above")
-        if cnt.value <= cap:
+    min_dist = float(constants.NOAA_MINPEAKDIST * samp_rate)
+    if min_dist > 1.0:
+        # threshold test + group-maximum scan entirely on the device (ddm_pick_peaks)
+        cap = max(4096, 8 * expected)
+        while True:
+            peaks = np.empty(cap, dtype=np.int64)
+            npk = C.c_int64()
+            rc = l.ddm_pick_peaks(dev, _dev.ptr(cor), n, avgpk, min_dist,
+                                  peaks.ctypes.data_as(C.POINTER(C.c_int64)), cap, C.byref(npk), st)
+            if rc == _lib.ERR_CAPACITY:
+                cap = int(npk.value)
+                continue
+            _lib.check(rc, "ddm_pick_peaks")
             break
-        cap = int(cnt.value)
-    m = int(cnt.value)
-    if m == 0:
-        # the reference appends currentMaxIndex == None and fails on None - int
-        raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int'")
-    # candidates -> host through a cached pinned staging buffer (a noisy pass can have millions)
-    stage = _pinned(2 * m)
-    stage[:m].copy_(idx[:m].view(t.float64), non_blocking=True)
-    stage[m:2 * m].copy_(val[:m], non_blocking=True)
-    t.cuda.current_stream(dev).synchronize()
-    both = stage[:2 * m].numpy()
-    idx_h = both[:m].view(np.int64)
-    val_h = both[m:2 * m]
-    peaks = np.empty(m, dtype=np.int64)
-    npk = C.c_int64()
-    _lib.check(l.ddm_group_peaks(idx_h.ctypes.data_as(C.POINTER(C.c_int64)),
-                                 val_h.ctypes.data_as(C.POINTER(C.c_double)), m,
-                                 float(constants.NOAA_MINPEAKDIST * samp_rate),
-                                 peaks.ctypes.data_as(C.POINTER(C.c_int64)), m, C.byref(npk)),
-               "ddm_group_peaks")
+        if npk.value == 0:
+            # the reference appends currentMaxIndex == None and fails on None - int
+            raise TypeError("unsupported operand type(s) for -: 'NoneType' and 'int'")
+    else:
+        peaks, npk = _pick_peaks_host_scan(cor, avgpk, min_dist, expected)
     peaks = peaks[:npk.value] - int(needle_len / 2)
     return np.sort(peaks), avgpk

@@ -239,3 +239,41 @@ def b_floor(b, a):
     _lib.check(_lib.lib().ddm_iir_analyse(b.ctypes.data_as(C.POINTER(C.c_double)), len(b),
                                           a.ctypes.data_as(C.POINTER(C.c_double)), len(a), C.byref(w), C.byref(nf)), "analyse")
     return nf.value
+
+
+def test_device_group_scan_equals_sequential_scan():
+    """ddm_pick_peaks (dominance formulation on the device) against the sequential scan of
+    decode_noaa.py:731-746 (ddm_compact_above + ddm_group_peaks, and the oracle's Python loop) on
+    random data: dense candidates, plateaus and exact ties, various window lengths."""
+    import ctypes as C
+    import torch
+    from directdemod_b200 import _dev, _lib, sync
+    rng = np.random.default_rng(31)
+    l = _lib.lib()
+    for trial, (n, dist, thr_q) in enumerate([(50000, 449.5, 0.3), (50000, 450.0, 0.6), (200003, 2710.75, 0.1),
+                                             (10000, 37.2, 0.5), (5000, 6000.0, 0.2), (300000, 1024.0, 0.45)]):
+        x = rng.standard_normal(n)
+        if trial % 2 == 0:
+            x = np.round(x * 4) / 4            # many exact ties and plateaus
+        x[rng.integers(0, n, 20)] = x.max()    # repeated global maxima
+        thr = float(np.quantile(x, thr_q))
+        xd = torch.from_numpy(x).cuda()
+        got = np.empty(n, dtype=np.int64)
+        cnt = C.c_int64()
+        _lib.check(l.ddm_pick_peaks(0, _dev.ptr(xd), n, thr, dist, got.ctypes.data_as(C.POINTER(C.c_int64)), n,
+                                    C.byref(cnt), _dev.stream_ptr(0)), "ddm_pick_peaks")
+        # sequential reference scan over the candidate list
+        cand = np.argwhere(x > thr).ravel().astype(np.int64)
+        want = np.empty(len(cand), dtype=np.int64)
+        wc = C.c_int64()
+        _lib.check(l.ddm_group_peaks(cand.ctypes.data_as(C.POINTER(C.c_int64)),
+                                     np.ascontiguousarray(x[cand]).ctypes.data_as(C.POINTER(C.c_double)), len(cand),
+                                     dist, want.ctypes.data_as(C.POINTER(C.c_int64)), len(want), C.byref(wc)), "group")
+        assert cnt.value == wc.value, (trial, cnt.value, wc.value)
+        assert np.array_equal(got[:cnt.value], want[:wc.value]), trial
+    # and through pick_peaks against the oracle's restatement of the reference loop
+    fs = 1000
+    cor = rng.standard_normal(40000) * 0.2
+    cor[::500] += 3.0
+    got, _ = sync.pick_peaks(torch.from_numpy(cor).cuda(), fs, 40)
+    assert np.array_equal(got, O.pick_sync_peaks(cor, fs, 40))
