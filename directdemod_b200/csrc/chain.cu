@@ -33,7 +33,7 @@
 namespace ddm {
 
 constexpr int kChainThreads = 128;   // blocks (threads) per tile
-constexpr int kChainMaxQ = 8;
+constexpr int kChainMaxQ = 10;
 constexpr int kChainCtasPerSm = 2;
 #ifndef DDM_CHAIN_STAGES
 #define DDM_CHAIN_STAGES 2
@@ -68,10 +68,11 @@ struct ChainParams {
     // batch of independent captures (ddm_chain_apply_batch_dev): capture k reads x + k*x_stride
     // samples and writes out + k*out_stride elements; every capture starts from the same state
     long long batch, x_stride, out_stride;
+    int J;                 // outputs per tile (see the kernel)
 };
 
 // ------------------------------------------------------------------------------------
-// fast path: D even, Q <= 8
+// fast path: D >= 2, Q <= 8
 // ------------------------------------------------------------------------------------
 // IN = DDM_IN_CU8: the tile is staged as raw interleaved u8 (2 B/sample, a quarter of the HBM and
 // PCIe traffic of cf32).  The bulk copies need 16-byte alignment, so a tile is copied from the
@@ -82,7 +83,10 @@ template <int Q, bool MIX, int OUT, int IN>
 __global__ void __launch_bounds__(kChainThreads, kChainCtasPerSm)
 chain_fused_kernel(const ChainParams P) {
     constexpr int NT = kChainThreads;
-    constexpr int J = NT - Q;                      // outputs per tile
+    // outputs per tile; QH = NT - J >= Q halo blocks lead every tile.  J = NT - Q for even D; for odd
+    // D it is rounded down to even so that every tile starts on an even sample (16-byte TMA source)
+    const int J = P.J;
+    const int QH = NT - J;
     constexpr bool U8 = IN == DDM_IN_CU8;
     constexpr int ES = U8 ? 2 : 8;                 // bytes per input sample
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -126,7 +130,7 @@ chain_fused_kernel(const ChainParams P) {
         unsigned char *dst = s_stage0 + stage * stage_bytes;
         const long long cap = gtile / P.num_tiles;
         const long long tile = gtile - cap * P.num_tiles;
-        const long long S0 = P.b0 + (tile * J - Q) * D;            // first sample (may be < 0)
+        const long long S0 = P.b0 + (tile * J - QH) * D;           // first sample (may be < 0)
         long long E = S0 + static_cast<long long>(NT) * D;
         if (E > end_all) E = end_all;
         if (U8) {
@@ -158,9 +162,10 @@ chain_fused_kernel(const ChainParams P) {
         const float2 *xf = static_cast<const float2 *>(P.x) + cap * P.x_stride;
         const float2 *hf = static_cast<const float2 *>(P.halo);
         uint32_t bytes = 0;
-        const long long h_end = E < 0 ? E : 0;
+        const long long Eu = E + (E & 1);          // odd D: an odd end is rounded up (16-byte copies)
+        const long long h_end = Eu < 0 ? Eu : 0;
         const long long c_beg = S0 > 0 ? S0 : 0;
-        const long long c_end = E < n_even ? E : n_even;
+        const long long c_end = Eu < n_even ? Eu : n_even;
         if (S0 < 0) bytes += static_cast<uint32_t>((h_end - S0) * 8);
         if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 8);
         // tail: the odd last sample of the chunk and the zero pad behind it
@@ -199,12 +204,12 @@ chain_fused_kernel(const ChainParams P) {
         }
         mbar_wait(&mbar[stage], (it / S) & 1);
 
-        const long long jblk = tile * J - Q + tid;          // this thread's block index
+        const long long jblk = tile * J - QH + tid;         // this thread's block index
         float2 *e_buf = s_e + (kChainEBufs == 2 ? (it & 1) * (Q * NT) : 0);
         if (jblk < P.M) {
             size_t sp_off = static_cast<size_t>(tid) * D * ES;
             if (U8) {
-                const long long S0 = P.b0 + (tile * J - Q) * D;
+                const long long S0 = P.b0 + (tile * J - QH) * D;
                 const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;
                 sp_off += static_cast<size_t>(S0 - S0a) * 2;         // shift of the aligned copy (even)
             }
@@ -218,19 +223,38 @@ chain_fused_kernel(const ChainParams P) {
             for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
 
             // two consecutive raw samples starting at block position a (a even) as packed pairs
+            const bool odd = (D & 1) != 0;       // blocks of odd threads are then only element aligned
             auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
                 if (U8) {
-                    const unsigned int w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
+                    unsigned int w;
+                    if (odd) {
+                        const unsigned short *h = reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                        w = static_cast<unsigned int>(h[0]) | (static_cast<unsigned int>(h[1]) << 16);
+                    } else {
+                        w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
+                    }
                     const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
                     X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
                     X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
                                           __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
+                } else if (odd) {
+                    X0 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
+                    X1 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a + 8);
                 } else {
                     const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
                     X0 = v.x;
                     X1 = v.y;
                 }
+            };
+            auto load1 = [&](int a) -> unsigned long long {
+                if (U8) {
+                    const unsigned int w = *reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                    return fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                            __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))),
+                                 pack_f32x2(-8388736.f, -8388736.f));
+                }
+                return *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
             };
             // raw pair -> mixed sample.  cf32: x rot.  u8: (v + 0.5 (1+j)) rot with v = b - 128.
             auto rotate = [&](unsigned long long X, float rx, float2 ry, float2 c) -> unsigned long long {
@@ -279,23 +303,20 @@ chain_fused_kernel(const ChainParams P) {
             }
 #pragma unroll(kChainUnroll)
             for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
-            if (a < D) {                                    // D % 4 == 2 (D is even on this path)
-                unsigned long long X0, X1;
-                load2(a, X0, X1);
-                float2 rx = make_float2(1.f, 1.f);
-                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = ry0;
+            for (; a < D; ++a) {                            // the D % 4 samples left over
+                const unsigned long long X0 = load1(a);
+                float rx = 1.f;
+                float2 ry = make_float2(0.f, 0.f), c0 = ry;
                 if (MIX) {
-                    rx = *reinterpret_cast<const float2 *>(s_rx + a);
-                    ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
-                    if (U8) c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                    rx = s_rx[a];
+                    ry = s_ry[a];
+                    if (U8) c0 = s_c[a];
                 }
-                const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
-                const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+                const unsigned long long M0 = rotate(X0, rx, ry, c0);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
-                    acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
-                    acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                    const float t = s_taps[q * DP + a];
+                    acc[q] = ffma2(pack_f32x2(t, t), M0, acc[q]);
                 }
             }
             float2 w0 = make_float2(1.f, 0.f);
@@ -318,7 +339,7 @@ chain_fused_kernel(const ChainParams P) {
             float2 y = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const float2 p = e_buf[q * NT + (tid + Q - q)];
+                const float2 p = e_buf[q * NT + (tid + QH - q)];
                 y.x += p.x;
                 y.y += p.y;
             }
@@ -328,7 +349,7 @@ chain_fused_kernel(const ChainParams P) {
                 float2 yp = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float2 p = e_buf[q * NT + (tid + Q - 1 - q)];
+                    const float2 p = e_buf[q * NT + (tid + QH - 1 - q)];
                     yp.x += p.x;
                     yp.y += p.y;
                 }
@@ -488,6 +509,8 @@ int launch_fused_moi(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st)
         case 6: return launch_fused_q<6, MIX, OUT, IN>(c, p, st);
         case 7: return launch_fused_q<7, MIX, OUT, IN>(c, p, st);
         case 8: return launch_fused_q<8, MIX, OUT, IN>(c, p, st);
+        case 9: return launch_fused_q<9, MIX, OUT, IN>(c, p, st);
+        case 10: return launch_fused_q<10, MIX, OUT, IN>(c, p, st);
     }
     set_error("internal: Q=%d out of range", Q);
     return DDM_ERR_UNSUPPORTED;
@@ -596,9 +619,10 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     const int qmax = (K + 1 + D - 1) / D;
     c->DP = (D + 3) & ~3;
     c->es = in_format == DDM_IN_CU8 ? 2 : 8;
-    c->fast = (D % 2 == 0) && qmax <= kChainMaxQ &&
+    c->fast = D >= 2 && qmax <= kChainMaxQ &&
               chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024;
-    c->H = (qmax + 1) * D;
+    // halo: the Q (odd D: up to Q + 1) leading blocks of a tile plus one block of slack
+    c->H = (qmax + 1 + (D & 1)) * D;
     if (c->H & 1) c->H += 1;
     if (in_format == DDM_IN_CU8) c->H = (c->H + 7) / 8 * 8 + 8;   // aligned tile copies may start 7 samples early
 
@@ -873,7 +897,7 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
         const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0;
         const bool history_ok = c->in_format != DDM_IN_CU8 || c->n_real >= c->H;
         if (c->fast && aligned && history_ok) {
-            const int s = static_cast<int>((c->dec_off + 1) & 1);
+            const int s = static_cast<int>((c->dec_off + 1 + D) & 1);     // makes block 0 start on an even sample
             const int Q = c->Q[s];
             ChainParams p{};
             p.x = x_dev;
@@ -885,7 +909,8 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             p.n0 = c->n0;
             p.M = M;
             p.b0 = c->dec_off + s + 1 - D;
-            const int J = kChainThreads - Q;
+            const int J = (D & 1) ? ((kChainThreads - Q) & ~1) : (kChainThreads - Q);
+            p.J = J;
             p.num_tiles = (M + J - 1) / J;
             p.r_hi = c->r_hi;
             p.r_lo = c->r_lo;
@@ -978,7 +1003,7 @@ int ddm_chain_apply_batch_dev(ddm_chain *c, const void *x_dev, int64_t n, int64_
     const int64_t M = positions_in(c, n);
     const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0 && (x_stride * c->es) % 16 == 0;
     if (c->fast && aligned && c->in_format == DDM_IN_CF32 && M > 0) {
-        const int s = 1;                                  // dec_off = 0 -> (0 + 1) & 1
+        const int s = (1 + c->D) & 1;                     // dec_off = 0: block 0 starts on an even sample
         const int Q = c->Q[s];
         ChainParams p{};
         p.x = x_dev;
@@ -990,7 +1015,8 @@ int ddm_chain_apply_batch_dev(ddm_chain *c, const void *x_dev, int64_t n, int64_
         p.n0 = 0;
         p.M = M;
         p.b0 = 0 + s + 1 - c->D;
-        const int J = kChainThreads - Q;
+        const int J = (c->D & 1) ? ((kChainThreads - Q) & ~1) : (kChainThreads - Q);
+        p.J = J;
         p.num_tiles = (M + J - 1) / J;
         p.r_hi = c->r_hi;
         p.r_lo = c->r_lo;

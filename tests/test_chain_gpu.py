@@ -52,9 +52,12 @@ CASES = [
     (255, 32, 2400000, 100000.0, 150000, 4),
     (492, 64, 2048000, -30000.0, 150000, 4),
     (1, 2, 1000, 10.0, 4000, 3),               # single tap
-    (151, 33, 2048000, 30000.0, 60000, 5),     # odd decimation -> general path
+    (151, 33, 2048000, 30000.0, 60000, 5),     # odd decimation: element-aligned blocks, even tiles
+    (151, 17, 1024000, 30000.0, 90000, 6),     # 1.024 Msps recordings: D = 17, Q = 9
+    (151, 35, 2100000, -20000.0, 90000, 4),
+    (101, 25, 1500000, 12000.0, 90000, 7),
     (151, 1, 60235, 500.0, 20000, 4),          # no decimation -> general path
-    (600, 8, 2048000, 30000.0, 30000, 3),      # Q > 8 -> general path
+    (600, 8, 2048000, 30000.0, 30000, 3),      # Q > 10 -> general path
 ]
 
 
@@ -162,7 +165,8 @@ def _u8_iq(seed, n, fs, f, f_mod, beta):
     (151, 50, 10000000, -125000.0, 300000, 5),
     (151, 34, 2048000, 0.0, 100000, 3),        # no mixer
     (492, 64, 2048000, -30000.0, 200000, 4),
-    (151, 33, 2048000, 30000.0, 60000, 4),     # odd decimation -> general path throughout
+    (151, 33, 2048000, 30000.0, 60000, 4),     # odd decimation
+    (151, 35, 2100000, -20000.0, 150000, 5),
 ])
 @pytest.mark.parametrize("demod", [True, False])
 def test_u8_ingest_matches_oracle(ntaps, decim, fs, f, n, ncuts, demod):
