@@ -458,7 +458,20 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-u8", action="store_true", help="skip the extra unsigned 8-bit input measurement")
     ap.add_argument("--ref-procs", type=int, default=64, help="max processes of the reference arm")
+    ap.add_argument("--configs", action="store_true",
+                    help="per-config table (BASELINE configs C1..C5, one JSON object per line) instead of the "
+                         "headline line: scripts/bench_configs.py with the oracle CPU legs switched on")
+    ap.add_argument("--quick", action="store_true", help="with --configs: reduced sizes")
+    ap.add_argument("--only", default="", help="with --configs: comma-separated subset, e.g. c2,c4")
     args = ap.parse_args()
+    if args.configs:
+        # cpu_baseline leg of the per-config table: the one place besides the headline's
+        # cpu_baseline / --impl reference where bench.py executes oracle/
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_configs
+        from oracle import ddoracle
+        bench_configs.set_cpu_oracle(ddoracle)
+        return bench_configs.main((["--quick"] if args.quick else []) + (["--only", args.only] if args.only else []))
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -1,9 +1,13 @@
 #!/usr/bin/env python
-"""BASELINE.json configs C1..C5 on one GPU, next to the oracle port of the reference on a bounded
-CPU slice of the same workload (1 core).  One JSON object per line.  This is the per-config table
-of DESIGN.md; the driver's bench is bench.py.
+"""BASELINE.json configs C1..C5 on one GPU.  One JSON object per line; this is the per-config table
+of DESIGN.md (the driver's bench is bench.py).
 
-    python scripts/bench_configs.py [--quick]
+    python scripts/bench_configs.py [--quick] [--only c2,c4]      GPU legs only
+    python bench.py --configs [--quick]                           plus the CPU legs
+
+The CPU legs time the oracle port of the reference on a bounded slice of the same workload
+(1 core).  Only bench.py may execute oracle/ outside the tests, so the oracle module is injected
+by bench.py's cpu_baseline leg (``set_cpu_oracle``); run directly, this script skips the CPU legs.
 """
 import argparse
 import json
@@ -19,7 +23,12 @@ import torch
 
 from directdemod_b200 import afsk, comm, constants, decode_noaa, demod_fm, filters, shard
 from directdemod_b200.fused import FusedChain
-from oracle import ddoracle as O
+O = None          # the oracle module, injected by bench.py --configs (see the module docstring)
+
+
+def set_cpu_oracle(module):
+    global O
+    O = module
 
 
 def sync():
@@ -53,8 +62,8 @@ def apt_iq_device(seconds, fs=2048000, f_off=30000.0, dev_hz=17000.0, amp=60.0, 
     """tests/util.apt_iq on the device, chunked (a 15-minute pass is 1.84e9 samples)."""
     rng = np.random.default_rng(seed)
     n_lines = int(np.ceil(seconds * 2)) + 1
-    sync_a = np.array(O.NOAA_SYNCA[:39]) * 233 + 11
-    sync_b = np.array(O.NOAA_SYNCB[:39]) * 233 + 11
+    sync_a = np.array(constants.NOAA_SYNCA[:39]) * 233 + 11
+    sync_b = np.array(constants.NOAA_SYNCB[:39]) * 233 + 11
     lines = []
     for ln in range(n_lines):
         img_a = (128 + 100 * np.sin(np.arange(909) / 30.0 + ln / 5.0) + rng.integers(-10, 10, 909)).clip(0, 255)
@@ -94,6 +103,10 @@ def c1(quick):
         return s.signal
     ours()
     t, y = wall(ours, 3)
+    if O is None:
+        emit(config="C1 tutorial chain (bh151 -> bwLim 30k -> FM -> butter BP), host in/out", samples=n,
+             gpu_ms=round(t * 1e3, 2), gpu_msps=round(n / t / 1e6, 1))
+        return
     ncpu = min(n, 4096000)
     t0 = time.perf_counter()
     b = O.taps_blackman_harris(151)[0]
@@ -133,6 +146,8 @@ def c2(quick):
     emit(config="C2 accurate sync, %d windows of 118152 samples (of ~%d per pass)" % (2 * nw, 4 * seconds),
          windows=2 * nw, total_ms=round(t_acc * 1e3, 1), ms_per_window=round(t_acc * 1e3 / (2 * nw), 3),
          spacing=[int(v) for v in np.unique(res[1])][:6])
+    if O is None:
+        return
     # CPU: the oracle's crude-sync path on a 14 s slice (1 core)
     xs = x[:int(14 * fs)].cpu().numpy()
     t0 = time.perf_counter()
@@ -170,6 +185,8 @@ def c3(quick):
     t_fe, (sig, bf, ch) = wall(lambda: afsk.front_end(DeviceSource(x, fs), 0.0, bw))
     emit(config="C3 AFSK1200 front end, %d s @ 960 kHz IQ -> 48 kHz (chain, FM, BP, bank, edges)" % seconds,
          samples=n, audio_samples=int(bf.numel()), total_ms=round(t_fe * 1e3, 2), msps_iq=round(n / t_fe / 1e6, 1))
+    if O is None:
+        return
     ns = 48000 * 5
     aud = sig.signal[:ns]
     t0 = time.perf_counter()
@@ -200,6 +217,8 @@ def c4(quick):
          fir_tflops=round(n * 4 * 1023 / t_fir / 1e12, 1), iir_ms=round(t_iir * 1e3, 2),
          iir_msps=round(n / t_iir / 1e6, 1), total_msps=round(n / (t_fir + t_iir) / 1e6, 1),
          halo_samples=fir.lookback() + iir.lookback())
+    if O is None:
+        return
     nc = 8_000_000
     xs = x[:nc].cpu().numpy().astype(np.complex128)
     b1, a1 = np.asarray(fir.getB), [1.0]
@@ -217,7 +236,8 @@ def c5(quick):
     n = fs
     caps = torch.empty((ncap, n), dtype=torch.complex64, device="cuda")
     torch.view_as_real(caps).normal_(0, 40)
-    taps = O.taps_blackman_harris(151)[0]
+    import scipy.signal as sps
+    taps = sps.windows.blackmanharris(151)
     ch = FusedChain(taps, 50, 125000.0, fs)
     out = torch.empty(ch.out_count(n) + 1, dtype=torch.float32, device="cuda")
 
@@ -230,6 +250,8 @@ def c5(quick):
     emit(config="C5 %d of 256 captures (1 s @ 10 Msps each), bh151 -> D=50 -> FM, one batched launch" % ncap,
          samples=ncap * n, total_ms=round(t * 1e3, 3), msps=round(ncap * n / t / 1e6, 1),
          hbm_gbs=round(ncap * n * (8 + 4 / 50) / t / 1e9, 1))
+    if O is None:
+        return
     xs = caps[0, :8_000_000].cpu().numpy()
     t0 = time.perf_counter()
     O.chain_stream(xs, fs, 125000.0, taps, fs / 50)
@@ -237,11 +259,11 @@ def c5(quick):
     emit(config="C5 CPU oracle: same chain on 8 M samples, 1 core", samples=len(xs), cpu_msps_1core=round(len(xs) / tc / 1e6, 2))
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     torch.cuda.set_device(0)
     for name, fn in (("c1", c1), ("c2", c2), ("c3", c3), ("c4", c4), ("c5", c5)):
         if args.only and name not in args.only.split(","):
