@@ -1,6 +1,8 @@
 // Library-level entry points of libddemod.so: version, error string, launch counter.
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "ddm_common.cuh"
 
@@ -64,6 +66,66 @@ void scratch_release(int device) {
     }
 }
 
+// Small-block pool: the fixed buffers of a handle (taps, halos, delay lines, tables) are a few KB;
+// decoders create and drop handles per call, and cudaMalloc / cudaFree cost milliseconds each on
+// a context that holds gigabytes.  Blocks are rounded up to a power of two (>= 4 KB), recycled
+// through per-device free lists and only returned to the driver by ddm_release_scratch.
+namespace {
+struct PoolEntry {
+    int device;
+    int cls;
+};
+std::mutex g_pool_mu;
+std::vector<void *> g_pool_free[kScratchDevices][24];
+std::unordered_map<void *, PoolEntry> g_pool_live;
+int pool_class(size_t bytes) {
+    int c = 12;                                   // 4 KB
+    while ((static_cast<size_t>(1) << c) < bytes) ++c;
+    return c;
+}
+}  // namespace
+
+cudaError_t pool_alloc(void **out, size_t bytes) {
+    int device = 0;
+    cudaError_t e = cudaGetDevice(&device);
+    if (e != cudaSuccess) return e;
+    const int cls = pool_class(bytes ? bytes : 1);
+    if (device < 0 || device >= kScratchDevices || cls >= 36) return cudaMalloc(out, bytes);
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (cls - 12 < 24 && !g_pool_free[device][cls - 12].empty()) {
+        *out = g_pool_free[device][cls - 12].back();
+        g_pool_free[device][cls - 12].pop_back();
+    } else {
+        e = cudaMalloc(out, static_cast<size_t>(1) << cls);
+        if (e != cudaSuccess) return e;
+    }
+    g_pool_live[*out] = PoolEntry{device, cls};
+    return cudaSuccess;
+}
+
+void pool_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_live.find(p);
+    if (it == g_pool_live.end()) {
+        cudaFree(p);                              // not ours (allocated with cudaMalloc directly)
+        return;
+    }
+    const PoolEntry e = it->second;
+    g_pool_live.erase(it);
+    if (e.cls - 12 < 24 && g_pool_free[e.device][e.cls - 12].size() < 4096) g_pool_free[e.device][e.cls - 12].push_back(p);
+    else cudaFree(p);
+}
+
+void pool_release(int device) {
+    if (device < 0 || device >= kScratchDevices) return;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto &lst : g_pool_free[device]) {
+        for (void *p : lst) cudaFree(p);
+        lst.clear();
+    }
+}
+
 int sm_count(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0)
@@ -87,6 +149,7 @@ int ddm_release_scratch(int device) {
     DDM_REQUIRE(device >= 0 && device < ndev, "ddm_release_scratch: no such device %d", device);
     ddm::DeviceGuard guard(device);
     ddm::scratch_release(device);
+    ddm::pool_release(device);
     return DDM_OK;
 }
 

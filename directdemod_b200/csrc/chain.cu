@@ -558,7 +558,7 @@ int build_initial_halo(ddm_chain *c) {
         h[i] = make_float2(static_cast<float>(std::cos(2.0 * M_PI * t)),
                            static_cast<float>(std::sin(2.0 * M_PI * t)));
     }
-    DDM_CUDA(cudaMalloc(&c->d_halo_init, sizeof(float2) * c->H));
+    DDM_CUDA(pool_alloc(&c->d_halo_init, sizeof(float2) * c->H));
     DDM_CUDA(cudaMemcpy(c->d_halo_init, h.data(), sizeof(float2) * c->H, cudaMemcpyHostToDevice));
     return DDM_OK;
 }
@@ -632,14 +632,14 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     };
     cudaError_t e;
     for (int i = 0; i < 2; ++i) {
-        e = cudaMalloc(&c->d_halo[i], static_cast<size_t>(c->es) * c->H);
+        e = pool_alloc(&c->d_halo[i], static_cast<size_t>(c->es) * c->H);
         if (e != cudaSuccess) {
             set_error("cudaMalloc(halo) failed: %s", cudaGetErrorString(e));
             return fail(DDM_ERR_NOMEM);
         }
     }
     {
-        e = cudaMalloc(&c->d_taps_lin, sizeof(double) * K);
+        e = pool_alloc_t(&c->d_taps_lin, sizeof(double) * K);
         if (e == cudaSuccess)
             e = cudaMemcpy(c->d_taps_lin, taps, sizeof(double) * K, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -665,7 +665,7 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
                     break;
                 }
             c->a_lastq[s] = Q > 1 ? std::min(first & ~3, D & ~3) : 0;
-            e = cudaMalloc(&c->d_taps[s], sizeof(float) * t.size());
+            e = pool_alloc_t(&c->d_taps[s], sizeof(float) * t.size());
             if (e == cudaSuccess)
                 e = cudaMemcpy(c->d_taps[s], t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) {
@@ -681,7 +681,7 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
             rot[a] = make_float2(static_cast<float>(std::cos(2.0 * M_PI * t)),
                                  static_cast<float>(-std::sin(2.0 * M_PI * t)));
         }
-        e = cudaMalloc(&c->d_rot, sizeof(float2) * c->DP);
+        e = pool_alloc_t(&c->d_rot, sizeof(float2) * c->DP);
         if (e == cudaSuccess)
             e = cudaMemcpy(c->d_rot, rot.data(), sizeof(float2) * c->DP, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -700,13 +700,14 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
 int ddm_chain_destroy(ddm_chain *c) {
     if (!c) return DDM_OK;
     DeviceGuard guard(c->device);
+    cudaDeviceSynchronize();          // pooled blocks are recycled at once: nothing may still read them
     for (int i = 0; i < 2; ++i) {
-        cudaFree(c->d_halo[i]);
-        cudaFree(c->d_taps[i]);
+        pool_free(c->d_halo[i]);
+        pool_free(c->d_taps[i]);
     }
-    cudaFree(c->d_halo_init);
-    cudaFree(c->d_taps_lin);
-    cudaFree(c->d_rot);
+    pool_free(c->d_halo_init);
+    pool_free(c->d_taps_lin);
+    pool_free(c->d_rot);
     cudaFree(c->d_ytmp);
     cudaFree(c->d_in);
     cudaFree(c->d_out);

@@ -49,6 +49,15 @@ struct DeviceGuard {
 int sm_count(int device);
 void *scratch_get(int device, int slot, size_t bytes);   // nullptr (+ error message) on failure
 void scratch_release(int device);
+// recycled small device blocks for per-handle buffers (current device); pool_free also accepts
+// plain cudaMalloc pointers
+cudaError_t pool_alloc(void **out, size_t bytes);
+void pool_free(void *p);
+void pool_release(int device);
+template <typename T>
+inline cudaError_t pool_alloc_t(T **out, size_t bytes) {
+    return pool_alloc(reinterpret_cast<void **>(out), bytes);
+}
 
 // ---- device-side primitives ------------------------------------------------------------
 #ifdef __CUDACC__

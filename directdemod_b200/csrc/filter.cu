@@ -22,6 +22,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -788,7 +790,7 @@ int pick_P(int order) {
 
 template <typename T>
 int dev_alloc_copy(T **dst, const T *src, size_t count) {
-    DDM_CUDA(cudaMalloc(dst, sizeof(T) * count));
+    DDM_CUDA(pool_alloc_t(dst, sizeof(T) * count));
     DDM_CUDA(cudaMemcpy(*dst, src, sizeof(T) * count, cudaMemcpyHostToDevice));
     return DDM_OK;
 }
@@ -807,8 +809,33 @@ int setup_fir(ddm_filter *f) {
 
 // Host-side analysis of an IIR (order >= 1, coefficients normalised by a[0], padded to order+1):
 // warm-up length of the segment-parallel run and the float64 roundoff floor of the recursion.
+void analyse_iir_uncached(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
+                          double *noise_floor);
+
+// The analysis costs tens of milliseconds of host time (long-double simulations); decoders build a
+// new filter object per call with the same coefficients, so results are remembered per (b, a).
 void analyse_iir(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
                  double *noise_floor) {
+    static std::mutex mu;
+    static std::map<std::vector<double>, std::pair<long long, double>> cache;
+    std::vector<double> key(b);
+    key.insert(key.end(), a.begin(), a.end());
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) {
+            *warmup = it->second.first;
+            *noise_floor = it->second.second;
+            return;
+        }
+    }
+    analyse_iir_uncached(order, b, a, warmup, noise_floor);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() < 1024) cache[key] = std::make_pair(*warmup, *noise_floor);
+}
+
+void analyse_iir_uncached(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
+                          double *noise_floor) {
     // Warm-up length of the segment-parallel run: the zero-input response of the recursion,
     // started from each unit state vector, simulated in long double until every state has
     // fallen below 1e-30 (a zero-input run has no roundoff floor, it decays geometrically all
@@ -1155,13 +1182,14 @@ int ddm_lfilter_zi(const double *b, int nb, const double *a, int na, double *zi_
 int ddm_filter_destroy(ddm_filter *f) {
     if (!f) return DDM_OK;
     DeviceGuard guard(f->device);
-    cudaFree(f->d_state[0]);
-    cudaFree(f->d_state[1]);
-    cudaFree(f->d_zi_base);
-    cudaFree(f->d_taps);
-    cudaFree(f->d_H);
-    cudaFree(f->d_tw);
-    cudaFree(f->d_b);
+    cudaDeviceSynchronize();          // pooled blocks are recycled at once: nothing may still read them
+    pool_free(f->d_state[0]);
+    pool_free(f->d_state[1]);
+    pool_free(f->d_zi_base);
+    pool_free(f->d_taps);
+    pool_free(f->d_H);
+    pool_free(f->d_tw);
+    pool_free(f->d_b);
     cudaFree(f->d_tmp[0]);
     cudaFree(f->d_tmp[1]);
     delete f;
@@ -1201,7 +1229,7 @@ int ddm_filter_create(int device, const double *b, int nb, const double *a, int 
     if (rc == DDM_OK) {
         f->state_len_dev = f->fir ? std::max(f->order, 1) : f->P;
         for (int i = 0; i < 2 && rc == DDM_OK; ++i) {
-            cudaError_t e = cudaMalloc(&f->d_state[i], sizeof(double2) * f->state_len_dev);
+            cudaError_t e = pool_alloc_t(&f->d_state[i], sizeof(double2) * f->state_len_dev);
             if (e == cudaSuccess) e = cudaMemset(f->d_state[i], 0, sizeof(double2) * f->state_len_dev);
             if (e != cudaSuccess) {
                 set_error("ddm_filter_create: state allocation failed: %s", cudaGetErrorString(e));
