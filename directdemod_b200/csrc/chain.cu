@@ -387,7 +387,7 @@ __device__ __forceinline__ float2 chain_fetch(const void *x, const void *halo, i
     return i >= 0 ? static_cast<const float2 *>(x)[i] : static_cast<const float2 *>(halo)[H + i];
 }
 
-__global__ void chain_generic_y_kernel(const GenericParams P) {
+static __global__ void chain_generic_y_kernel(const GenericParams P) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx > P.M) return;
     const long long m = idx - 1;
@@ -412,7 +412,7 @@ __global__ void chain_generic_y_kernel(const GenericParams P) {
     P.y[idx] = make_double2(ax, ay);
 }
 
-__global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
+static __global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
                                          int out_mode) {
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (m >= M) return;
@@ -516,10 +516,30 @@ int launch_fused_moi(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st)
     return DDM_ERR_UNSUPPORTED;
 }
 
+}  // namespace
+
+// The kernel is instantiated for 10 values of Q x mixer x output mode x input format; the u8 half
+// lives in its own translation unit (chain_u8.cu includes this file with DDM_CHAIN_PART = 1) so that
+// the two halves compile in parallel.
+int ddm_chain_launch_u8(ddm_chain *c, int mix, int out_mode, int Q, const ddm::ChainParams &p, cudaStream_t st);
+
+#if defined(DDM_CHAIN_PART) && DDM_CHAIN_PART == 1
+int ddm_chain_launch_u8(ddm_chain *c, int mix, int out_mode, int Q, const ddm::ChainParams &p, cudaStream_t st) {
+    if (mix) {
+        return out_mode == DDM_CHAIN_OUT_FM ? launch_fused_moi<true, DDM_CHAIN_OUT_FM, DDM_IN_CU8>(c, Q, p, st)
+                                            : launch_fused_moi<true, DDM_CHAIN_OUT_IQ, DDM_IN_CU8>(c, Q, p, st);
+    }
+    return out_mode == DDM_CHAIN_OUT_FM ? launch_fused_moi<false, DDM_CHAIN_OUT_FM, DDM_IN_CU8>(c, Q, p, st)
+                                        : launch_fused_moi<false, DDM_CHAIN_OUT_IQ, DDM_IN_CU8>(c, Q, p, st);
+}
+#else
+
+namespace {
+
 template <bool MIX, int OUT>
 int launch_fused_mo(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
-    return c->in_format == DDM_IN_CU8 ? launch_fused_moi<MIX, OUT, DDM_IN_CU8>(c, Q, p, st)
-                                      : launch_fused_moi<MIX, OUT, DDM_IN_CF32>(c, Q, p, st);
+    if (c->in_format == DDM_IN_CU8) return ddm_chain_launch_u8(c, MIX ? 1 : 0, OUT, Q, p, st);
+    return launch_fused_moi<MIX, OUT, DDM_IN_CF32>(c, Q, p, st);
 }
 
 int launch_fused(ddm_chain *c, int Q, const ChainParams &p, cudaStream_t st) {
@@ -1096,3 +1116,5 @@ int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_
 }
 
 }  // extern "C"
+
+#endif  // DDM_CHAIN_PART
