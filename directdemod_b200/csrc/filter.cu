@@ -331,45 +331,244 @@ __device__ __forceinline__ void fftfir_4096(float2 (&v)[16], float2 *buf, const 
     __syncthreads();          // buf is reused by the next transform
 }
 
+// ---- packed single precision (Blackwell FADD2 / FMUL2 / FFMA2) ---------------------------------
+// A complex value is one 64-bit register pair (re low, im high): an addition is one FADD2 and a
+// multiplication by w is FMUL2(a, (wr, wr)) + FFMA2(swap(a), (-wi, wi)) -- ptxas folds the swap into
+// the operand's LO_HI selector and the broadcast into .F32 -- so a transform issues half the
+// instructions of the scalar form above (the kernel is issue/latency-bound, not FLOP-bound).
+typedef unsigned long long cpk;
+
+__device__ __forceinline__ cpk fsub2(cpk a, cpk b) {
+    cpk d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ cpk pk_swap(cpk a) {
+    const float2 t = unpack_f32x2(a);
+    return pack_f32x2(t.y, t.x);
+}
+struct PkW {
+    cpk rr, ii;             // (wr, wr) and (-wi, wi)
+};
+__device__ __forceinline__ PkW pk_w(float wr, float wi) { return PkW{pack_f32x2(wr, wr), pack_f32x2(-wi, wi)}; }
+__device__ __forceinline__ PkW pk_w(cpk w) {
+    const float2 t = unpack_f32x2(w);
+    return pk_w(t.x, t.y);
+}
+__device__ __forceinline__ cpk pk_mul(cpk a, PkW w) { return ffma2(pk_swap(a), w.ii, fmul2(a, w.rr)); }
+
+template <int DIR>
+__device__ __forceinline__ void pk_dft4(cpk &v0, cpk &v1, cpk &v2, cpk &v3) {
+    // -i d = swap(d) (1, -1) forward, +i d = swap(d) (-1, 1) inverse: folded into the last two sums
+    const cpk sp = DIR > 0 ? pack_f32x2(1.f, -1.f) : pack_f32x2(-1.f, 1.f);
+    const cpk sm = DIR > 0 ? pack_f32x2(-1.f, 1.f) : pack_f32x2(1.f, -1.f);
+    const cpk a0 = fadd2(v0, v2), a1 = fsub2(v0, v2), a2 = fadd2(v1, v3), d = pk_swap(fsub2(v1, v3));
+    v0 = fadd2(a0, a2);
+    v2 = fsub2(a0, a2);
+    v1 = ffma2(d, sp, a1);
+    v3 = ffma2(d, sm, a1);
+}
+
+// 16-point DFT in registers, same index maps as cf_dft16
+template <int DIR>
+__device__ __forceinline__ void pk_dft16(cpk (&v)[16]) {
+    constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    constexpr float wr[10] = {1.f, c1, h, s1, 0.f, -s1, -h, -c1, -1.f, -c1};
+    constexpr float wi[10] = {0.f, -s1, -h, -c1, -1.f, -c1, -h, -s1, 0.f, s1};      // forward
+    cpk a[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        cpk c[4] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2]};
+        pk_dft4<DIR>(c[0], c[1], c[2], c[3]);
+        a[0][n2] = c[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 4; ++k1) {
+            const int m = n2 * k1;
+            if (m == 0) a[k1][n2] = c[k1];
+            else if (m == 4) a[k1][n2] = fmul2(pk_swap(c[k1]), DIR > 0 ? pack_f32x2(1.f, -1.f) : pack_f32x2(-1.f, 1.f));
+            else a[k1][n2] = pk_mul(c[k1], pk_w(wr[m], DIR > 0 ? wi[m] : -wi[m]));
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        cpk r0 = a[k1][0], r1 = a[k1][1], r2 = a[k1][2], r3 = a[k1][3];
+        pk_dft4<DIR>(r0, r1, r2, r3);
+        v[k1] = r0;
+        v[k1 + 4] = r1;
+        v[k1 + 8] = r2;
+        v[k1 + 12] = r3;
+    }
+}
+
+// v[r] *= w^r, r = 1..15, from the four table entries w, w^2, w^4, w^8 (shared memory, T[p * S]):
+// w^3, w^5, w^6, w^7 by one product each; the upper half is multiplied by w^8 first and then by the
+// same eight factors as the lower half
+template <int DIR, int S>
+__device__ __forceinline__ void pk_twiddle(cpk (&v)[16], const float2 *T) {
+    float2 t1 = T[0], t2 = T[S], t4 = T[2 * S], t8 = T[3 * S];
+    if (DIR < 0) {
+        t1.y = -t1.y;
+        t2.y = -t2.y;
+        t4.y = -t4.y;
+        t8.y = -t8.y;
+    }
+    const PkW w1 = pk_w(t1.x, t1.y), w2 = pk_w(t2.x, t2.y), w4 = pk_w(t4.x, t4.y), w8 = pk_w(t8.x, t8.y);
+    const PkW w3 = pk_w(pk_mul(pack_f32x2(t2.x, t2.y), w1));
+    const PkW w5 = pk_w(pk_mul(pack_f32x2(t4.x, t4.y), w1));
+    const PkW w6 = pk_w(pk_mul(pack_f32x2(t4.x, t4.y), w2));
+    const PkW w7 = pk_w(pk_mul(pack_f32x2(t4.x, t4.y), w3));
+#pragma unroll
+    for (int r = 8; r < 16; ++r) v[r] = pk_mul(v[r], w8);
+    v[1] = pk_mul(v[1], w1);
+    v[9] = pk_mul(v[9], w1);
+    v[2] = pk_mul(v[2], w2);
+    v[10] = pk_mul(v[10], w2);
+    v[3] = pk_mul(v[3], w3);
+    v[11] = pk_mul(v[11], w3);
+    v[4] = pk_mul(v[4], w4);
+    v[12] = pk_mul(v[12], w4);
+    v[5] = pk_mul(v[5], w5);
+    v[13] = pk_mul(v[13], w5);
+    v[6] = pk_mul(v[6], w6);
+    v[14] = pk_mul(v[14], w6);
+    v[7] = pk_mul(v[7], w7);
+    v[15] = pk_mul(v[15], w7);
+}
+
+// shared-memory twiddle tables of the two twiddled passes, laid out so that a warp reads
+// consecutive entries: T3[p][j] = tw[j 2^p] (j < 256), T2[p][k] = tw[16 k 2^p] (k < 16)
+constexpr int kFftFirT3 = 4 * 256, kFftFirT2 = 4 * 16;
+
+// the 4096-point transform of fftfir_4096 on packed values
+template <int DIR>
+__device__ __forceinline__ void pkfft_4096(cpk (&v)[16], cpk *buf, const float2 *T3, const float2 *T2, int j) {
+    pk_dft16<DIR>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[fftfir_idx(16 * j + r)] = v[r];
+    __syncthreads();
+    {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf[fftfir_idx(j + 256 * r)];
+        const int k = j & 15;
+        pk_twiddle<DIR, 16>(v, T2 + k);
+        pk_dft16<DIR>(v);
+        __syncthreads();
+        const int base = (j - k) * 16 + k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) buf[fftfir_idx(base + 16 * r)] = v[r];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[fftfir_idx(j + 256 * r)];
+    pk_twiddle<DIR, 256>(v, T3 + j);
+    pk_dft16<DIR>(v);
+    __syncthreads();          // buf is reused by the next transform
+}
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gsrc, bool valid) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const int sz = valid ? BYTES : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(gsrc), "n"(BYTES), "r"(sz) : "memory");
+}
+
+constexpr size_t fft_fir_smem_bytes(bool cplx) {
+    return sizeof(float2) * (kFftFirN + kFftFirN / 16 + kFftFirT3 + kFftFirT2) +
+           (cplx ? sizeof(float2) : sizeof(float)) * kFftFirN;
+}
+
+// Persistent CTAs (2 per SM) walk the blocks of the signal.  The next block's 4096 input samples
+// are fetched with cp.async into thread-private slots of a staging buffer (thread j copies and later
+// reads elements j + 256 r: no barrier needed) while the current block is transformed; samples
+// before the start / behind the end of the signal are zero-filled by the copy itself.
 template <bool CPLX>
 __global__ void __launch_bounds__(kFftFirThreads, 2)
 fir_fft_kernel(const typename FirTraits<CPLX>::T *__restrict__ x, typename FirTraits<CPLX>::T *__restrict__ y,
                const float2 *__restrict__ H, const float2 *__restrict__ tw, const double2 *__restrict__ zi,
-               long long n, int K) {
-    __shared__ float2 buf[kFftFirN + kFftFirN / 16];
+               long long n, int K, long long blocks) {
+    using T = typename FirTraits<CPLX>::T;
+    extern __shared__ __align__(16) unsigned char fftfir_smem[];
+    cpk *buf = reinterpret_cast<cpk *>(fftfir_smem);
+    float2 *T3 = reinterpret_cast<float2 *>(buf + kFftFirN + kFftFirN / 16);
+    float2 *T2 = T3 + kFftFirT3;
+    T *stage = reinterpret_cast<T *>(T2 + kFftFirT2);
     const int j = threadIdx.x;
     const int V = kFftFirN - (K - 1);                      // valid outputs per block
-    const long long out0 = static_cast<long long>(blockIdx.x) * V;
-    const long long in0 = out0 - (K - 1);
-    float2 v[16];
+
+    auto prefetch = [&](long long blk) {
+        const long long in0 = blk * V - (K - 1);
+        if (in0 >= 0 && in0 + kFftFirN <= n) {              // interior block: no per-sample checks
+            const T *src = x + in0 + j;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const long long g = in0 + j + 256 * r;
-        float2 s = make_float2(0.f, 0.f);
-        if (g >= 0 && g < n) {
-            if constexpr (CPLX) s = x[g];
-            else s.x = x[g];
+            for (int r = 0; r < 16; ++r) cp_async_zfill<sizeof(T)>(&stage[j + 256 * r], src + 256 * r, true);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const long long g = in0 + j + 256 * r;
+                const bool ok = g >= 0 && g < n;
+                cp_async_zfill<sizeof(T)>(&stage[j + 256 * r], x + (ok ? g : 0), ok);
+            }
         }
-        v[r] = s;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    long long blk = blockIdx.x;
+    if (blk < blocks) prefetch(blk);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        T3[p * 256 + j] = __ldg(&tw[j << p]);
+        if (j < 16) T2[p * 16 + j] = __ldg(&tw[(16 * j) << p]);
     }
-    fftfir_4096<1>(v, buf, tw, j);
+    __syncthreads();
+
+    for (; blk < blocks; blk += gridDim.x) {
+        cpk v[16];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = cf_mul(v[r], __ldg(&H[j + 256 * r]));
-    fftfir_4096<-1>(v, buf, tw, j);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int i = j + 256 * r;                          // position inside the block
-        if (i < K - 1) continue;                            // circular wrap-around: discard
-        const long long o = out0 + (i - (K - 1));
-        if (o >= n) continue;
-        float2 s = v[r];
-        if (zi != nullptr && o < K - 1) {
-            const double2 z = zi[o];
-            s.x = static_cast<float>(static_cast<double>(s.x) + z.x);
-            s.y = static_cast<float>(static_cast<double>(s.y) + z.y);
+        for (int r = 0; r < 16; ++r) {
+            if constexpr (CPLX) {
+                const float2 s = stage[j + 256 * r];
+                v[r] = pack_f32x2(s.x, s.y);
+            } else {
+                v[r] = pack_f32x2(stage[j + 256 * r], 0.f);
+            }
         }
-        if constexpr (CPLX) y[o] = s;
-        else y[o] = s.x;
+        if (blk + gridDim.x < blocks) prefetch(blk + gridDim.x);
+        pkfft_4096<1>(v, buf, T3, T2, j);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float2 hh = __ldg(&H[j + 256 * r]);
+            v[r] = pk_mul(v[r], pk_w(hh.x, hh.y));
+        }
+        pkfft_4096<-1>(v, buf, T3, T2, j);
+        const long long out0 = blk * V;
+        if (out0 + V <= n && (zi == nullptr || out0 >= K - 1)) {
+            // interior block: only the circular wrap-around (i < K - 1) is discarded
+            T *dst = y + (out0 - (K - 1)) + j;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                if (j + 256 * r < K - 1) continue;
+                const float2 s = unpack_f32x2(v[r]);
+                if constexpr (CPLX) dst[256 * r] = s;
+                else dst[256 * r] = s.x;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int i = j + 256 * r;                      // position inside the block
+                if (i < K - 1) continue;
+                const long long o = out0 + (i - (K - 1));
+                if (o >= n) continue;
+                float2 s = unpack_f32x2(v[r]);
+                if (zi != nullptr && o < K - 1) {
+                    const double2 z = zi[o];
+                    s.x = static_cast<float>(static_cast<double>(s.x) + z.x);
+                    s.y = static_cast<float>(static_cast<double>(s.y) + z.y);
+                }
+                if constexpr (CPLX) y[o] = s;
+                else y[o] = s.x;
+            }
+        }
     }
 }
 
@@ -453,13 +652,32 @@ __device__ __forceinline__ void from_d2(double &d, double2 v) { d = v.x; }
 
 // one DF-II-T step in scipy's operation order:
 //   y = Z[0] + b[0] x;   Z[i] = (Z[i+1] + x b[i+1]) - y a[i+1];   Z[P-1] = x b[P] - y a[P]
-template <int P, typename V>
+//
+// EXACT = false (segment-parallel mode only): the same recursion with every multiply-add pair
+// contracted into one DFMA -- 2P+1 FP64 issues per real sample instead of 4P+2.  The result
+// differs from scipy's by the recursion's own roundoff floor, which this mode is only chosen
+// for when it is below 1e-7 (two orders under the parity tolerance), and the kernel goes from
+// FP64-pipe-bound to HBM-bound.
+__device__ __forceinline__ double2 vfma(double c, double2 x, double2 acc) {
+    return make_double2(fma(c, x.x, acc.x), fma(c, x.y, acc.y));
+}
+__device__ __forceinline__ double vfma(double c, double x, double acc) { return fma(c, x, acc); }
+
+template <int P, bool EXACT, typename V>
 __device__ __forceinline__ V iir_step(V (&z)[P], const V x, const IirCoef &c) {
-    const V y = vadd(z[0], vmul(c.b[0], x));
+    if constexpr (EXACT) {
+        const V y = vadd(z[0], vmul(c.b[0], x));
 #pragma unroll
-    for (int i = 0; i < P - 1; ++i) z[i] = vsub(vadd(z[i + 1], vmul(c.b[i + 1], x)), vmul(c.a[i + 1], y));
-    z[P - 1] = vsub(vmul(c.b[P], x), vmul(c.a[P], y));
-    return y;
+        for (int i = 0; i < P - 1; ++i) z[i] = vsub(vadd(z[i + 1], vmul(c.b[i + 1], x)), vmul(c.a[i + 1], y));
+        z[P - 1] = vsub(vmul(c.b[P], x), vmul(c.a[P], y));
+        return y;
+    } else {
+        const V y = vfma(c.b[0], x, z[0]);
+#pragma unroll
+        for (int i = 0; i < P - 1; ++i) z[i] = vfma(-c.a[i + 1], y, vfma(c.b[i + 1], x, z[i + 1]));
+        z[P - 1] = vfma(-c.a[P], y, vmul(c.b[P], x));
+        return y;
+    }
 }
 
 __device__ __forceinline__ double2 vload(double2 s) { return s; }
@@ -515,7 +733,7 @@ __device__ __forceinline__ void iir_store_block(S *__restrict__ y, long long pos
 }
 
 // SI / SO: sample types of input and output (float, float2, double, double2)
-template <int P, typename SI, typename SO>
+template <int P, bool EXACT, typename SI, typename SO>
 __global__ void __launch_bounds__(kIirThreads)
 iir_kernel(const IirParams prm) {
     constexpr bool CPLX = sizeof(SI) == 2 * (std::is_same<SI, float2>::value ? sizeof(float) : sizeof(double)) &&
@@ -558,16 +776,16 @@ iir_kernel(const IirParams prm) {
         const int cnt = left < B ? static_cast<int>(left) : B;
         if (warm) {
 #pragma unroll
-            for (int i = 0; i < B; ++i) iir_step<P, V>(z, vload(cur[i]), prm.c);
+            for (int i = 0; i < B; ++i) iir_step<P, EXACT, V>(z, vload(cur[i]), prm.c);
         } else if (cnt == B) {
             SO out[B];
 #pragma unroll
-            for (int i = 0; i < B; ++i) out[i] = vout<SO>(iir_step<P, V>(z, vload(cur[i]), prm.c));
+            for (int i = 0; i < B; ++i) out[i] = vout<SO>(iir_step<P, EXACT, V>(z, vload(cur[i]), prm.c));
             iir_store_block<SO, B>(y, pos, vec, out);
         } else {
 #pragma unroll
             for (int i = 0; i < B; ++i) {
-                if (i < cnt) y[pos + i] = vout<SO>(iir_step<P, V>(z, vload(cur[i]), prm.c));
+                if (i < cnt) y[pos + i] = vout<SO>(iir_step<P, EXACT, V>(z, vload(cur[i]), prm.c));
             }
         }
 #pragma unroll
@@ -575,6 +793,175 @@ iir_kernel(const IirParams prm) {
         pos = npos;
     }
     if (prm.zf != nullptr && s1 == prm.n) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) prm.zf[i] = to_d2(z[i]);
+    }
+}
+
+// ---- warp-staged variant ------------------------------------------------------------------------
+// In iir_kernel every lane streams its own segment, so one warp-wide 16-byte load touches 32
+// different cache lines: ncu showed the L1 data pipe at 75 % (11 wavefronts per request) and the
+// kernel bound there, not by FP64 or HBM.  Here a warp moves the 32 rows of a step cooperatively --
+// consecutive lanes copy consecutive 16-byte pieces of a row, so an instruction touches PI-times
+// fewer lines -- through shared memory: cp.async into a two-stage ring of padded rows (the next
+// step is in flight while this one is computed), each lane reads its own row with conflict-free
+// 128-bit accesses, and the outputs go back the same way.  Warps are autonomous (no CTA barrier).
+// DFMA form only (the separately rounded form is FP64-bound and gains nothing); needs 16-byte
+// aligned x and y; iir_kernel remains the general form.
+// general form of a step's copy: rows that have not reached position 0 yet or run past the end of
+// the signal are zero-filled by the copy itself (edge warps only; kept out of line so that its index
+// arithmetic does not weigh on the registers of the main loop)
+template <typename SI, int PI, int RI>
+__device__ __noinline__ void iir_copy_in_edge(const SI *__restrict__ x, uint4 *s_row0, long long p0, long long seg0,
+                                              long long L, long long n, int lane) {
+    constexpr int perI = 16 / sizeof(SI);
+#pragma unroll 1
+    for (int i = 0; i < PI; ++i) {
+        const int q = i * 32 + lane, row = q / PI, col = q % PI;
+        const long long pr = p0 + row * L;
+        long long end = (seg0 + row + 1) * L;
+        if (end > n) end = n;
+        const long long g0 = pr + col * perI;
+        long long valid = end - g0;
+        if (pr < 0 || valid < 0) valid = 0;
+        if (valid > perI) valid = perI;
+        const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(s_row0 + row * RI + col));
+        const int bytes = static_cast<int>(valid) * static_cast<int>(sizeof(SI));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(x + (valid > 0 ? g0 : 0)), "r"(bytes)
+                     : "memory");
+    }
+}
+
+template <int P, typename SI, typename SO>
+__global__ void __launch_bounds__(kIirThreads, 6)
+iir_warp_kernel(const IirParams prm) {
+    constexpr bool CPLX = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
+    using V = typename IirV<CPLX>::V;
+    constexpr int BI = 128 / sizeof(SI) > kIirBlock ? kIirBlock : 128 / sizeof(SI);
+    constexpr int BO = 128 / sizeof(SO) > kIirBlock ? kIirBlock : 128 / sizeof(SO);
+    constexpr int B = BI < BO ? BI : BO;                    // samples per lane and step
+    constexpr int PI = B * sizeof(SI) / 16, PO = B * sizeof(SO) / 16;      // 16-byte pieces per row
+    constexpr int RI = PI + 1, RO = PO + 1;                 // padded row lengths (in pieces)
+    constexpr int perI = 16 / sizeof(SI), perO = 16 / sizeof(SO);
+    constexpr int kWarps = kIirThreads / 32;
+    __shared__ uint4 s_in[kWarps][2][32 * RI];
+    __shared__ uint4 s_out[kWarps][32 * RO];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long seg0 = (blockIdx.x * static_cast<long long>(kWarps) + warp) * 32;    // lane 0's segment
+    if (seg0 * prm.L >= prm.n) return;
+    const SI *__restrict__ x = static_cast<const SI *>(prm.x);
+    SO *__restrict__ y = static_cast<SO *>(prm.y);
+    const long long L = prm.L, W = prm.W, n = prm.n;
+    const long long s0 = (seg0 + lane) * L;
+    long long s1 = s0 + L;
+    if (s1 > n) s1 = n;
+    const bool interior = (seg0 + 32) * L <= n;             // every segment of this warp is complete
+
+    V z[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        z[i] = vzero(V());
+        if (s0 - W <= 0 && prm.zi != nullptr) from_d2(z[i], prm.zi[i]);
+    }
+
+    // step t covers positions [s0 - W + t B, + B) of every lane's segment; p0 is lane 0's position.
+    // Piece i of a lane: row lane / PI + i (32 / PI), column lane % PI.
+    const unsigned in_base = static_cast<unsigned>(__cvta_generic_to_shared(&s_in[warp][0][(lane / PI) * RI + lane % PI]));
+    const long long in_off = (lane / PI) * L + (lane % PI) * perI;
+    const long long out_off = (lane / PO) * L + (lane % PO) * perO;
+    auto copy_in = [&](long long p0, int stage) {
+        if (interior && p0 >= 0) {
+            const SI *src = x + p0 + in_off;
+            unsigned d = in_base + stage * (32 * RI * 16);
+#pragma unroll
+            for (int i = 0; i < PI; ++i) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                d += (32 / PI) * RI * 16;
+                src += (32 / PI) * L;
+            }
+        } else {
+            iir_copy_in_edge<SI, PI, RI>(x, &s_in[warp][stage][0], p0, seg0, L, n, lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const long long steps = (W + L) / B;                    // L, W are multiples of kIirBlock >= B
+    const long long warm_steps = W / B;
+    long long p0 = seg0 * L - W;
+    copy_in(p0, 0);
+#pragma unroll 1
+    for (long long t = 0; t < steps; ++t, p0 += B) {
+        const int stage = static_cast<int>(t & 1);
+        if (t + 1 < steps) {
+            copy_in(p0 + B, stage ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const long long pos = p0 + lane * L;
+        long long left = s1 - pos;
+        if (pos < 0 || left < 0) left = 0;
+        const int cnt = left < B ? static_cast<int>(left) : B;
+        const bool warm = t < warm_steps;
+        const uint4 *my_in = &s_in[warp][stage][lane * RI];
+        // lanes with a whole block compute; lanes that have not reached position 0 yet or are past
+        // the end of their segment sit the step out; a partial block (once per launch, at the end of
+        // the signal) sends the warp through the scalar form
+        if (!__any_sync(0xffffffffu, cnt > 0 && cnt < B)) {
+            if (warm) {
+                if (cnt == B) {
+#pragma unroll
+                    for (int i = 0; i < PI; ++i) {
+                        SI cur[perI];
+                        const uint4 v = my_in[i];
+                        memcpy(cur, &v, 16);
+#pragma unroll
+                        for (int k = 0; k < perI; ++k) iir_step<P, false, V>(z, vload(cur[k]), prm.c);
+                    }
+                }
+            } else {
+                if (cnt == B) {
+                    SO out[B];
+#pragma unroll
+                    for (int i = 0; i < PI; ++i) {
+                        SI cur[perI];
+                        const uint4 v = my_in[i];
+                        memcpy(cur, &v, 16);
+#pragma unroll
+                        for (int k = 0; k < perI; ++k)
+                            out[i * perI + k] = vout<SO>(iir_step<P, false, V>(z, vload(cur[k]), prm.c));
+                    }
+#pragma unroll
+                    for (int i = 0; i < PO; ++i) {
+                        uint4 v;
+                        memcpy(&v, &out[i * perO], 16);
+                        s_out[warp][lane * RO + i] = v;
+                    }
+                }
+                __syncwarp();
+                SO *dst = y + p0 + out_off;
+                const uint4 *so = &s_out[warp][(lane / PO) * RO + lane % PO];
+#pragma unroll
+                for (int i = 0; i < PO; ++i) {
+                    // interior warps: every row holds a whole block in every output step
+                    const bool ok = interior || __shfl_sync(0xffffffffu, cnt, lane / PO + i * (32 / PO)) == B;
+                    if (ok) *reinterpret_cast<uint4 *>(dst) = so[i * (32 / PO) * RO];
+                    dst += (32 / PO) * L;
+                }
+            }
+        } else if (cnt > 0) {
+#pragma unroll 1
+            for (int i = 0; i < cnt; ++i) {
+                const SI xi = reinterpret_cast<const SI *>(my_in)[i];
+                const V r = iir_step<P, false, V>(z, vload(xi), prm.c);
+                if (!warm) y[pos + i] = vout<SO>(r);
+            }
+        }
+        __syncwarp();
+    }
+    if (prm.zf != nullptr && s1 == n && s0 < n) {
 #pragma unroll
         for (int i = 0; i < P; ++i) prm.zf[i] = to_d2(z[i]);
     }
@@ -726,7 +1113,7 @@ struct ddm_filter {
     int P = 0;
     long long warmup = -1;          // samples after which a zero-state run matches; -1 = never
     double noise_floor = 0.0;       // relative roundoff noise of the float64 recursion itself
-    int mode = 0;                   // DDM_IIR_AUTO / _PARALLEL / _SEQUENTIAL
+    int mode = 0;                   // DDM_IIR_AUTO / _PARALLEL / _SEQUENTIAL / _PARALLEL_EXACT
     int sms = 148;
     IirCoef coef;
     // scratch for filtfilt
@@ -939,16 +1326,21 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     // parity tolerance, in which case only the sequential replay reproduces the reference
     const bool sequential = f->warmup < 0 || f->mode == DDM_IIR_SEQUENTIAL ||
                             (f->mode == DDM_IIR_AUTO && f->noise_floor > 1e-7);
+    // the DFMA form goes through the warp-staged kernel when both pointers are 16-byte aligned
+    static const bool no_staging = std::getenv("DDM_IIR_NO_STAGING") != nullptr;
+    const bool staged = !sequential && f->mode != DDM_IIR_PARALLEL_EXACT && !no_staging &&
+                        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     if (sequential) {
         L = n;                                        // one thread replays scipy's loop
         prm.W = 0;
     } else {
-        // Two warps per SM sub-partition keep the FP64 pipe fed (one warp measured 55 % pipe
-        // activity: 8.07 -> 5.43 ms per 1.08 G samples with two; three and more are no faster);
-        // when that would make the segments shorter than twice the warm-up, one warp per
-        // sub-partition keeps the redundant warm-up work down instead.
+        // Warps per SM sub-partition (measured, 1.08 G cf32 samples through the 8th-order low-pass):
+        // separately rounded arithmetic is FP64-pipe-bound and two warps saturate it (8.07 -> 5.43 ms,
+        // more are no faster); the DFMA form through the warp-staged kernel is fastest with three
+        // (4.29 / 3.96 / 4.74 ms for 2 / 3 / 4).  When that would make the segments shorter than twice
+        // the warm-up, one warp per sub-partition keeps the redundant warm-up work down instead.
         const long long base = static_cast<long long>(f->sms) * 4 * 32;
-        long long wps = 2;
+        long long wps = staged ? 3 : 2;
         if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));
         L = (n + base * wps - 1) / (base * wps);
         if (wps > 1 && L < 2 * f->warmup) L = (n + base - 1) / base;
@@ -960,7 +1352,9 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     prm.W = (prm.W + kIirBlock - 1) / kIirBlock * kIirBlock;
     const long long segs = (n + L - 1) / L;
     const unsigned grid = static_cast<unsigned>((segs + kIirThreads - 1) / kIirThreads);
-    iir_kernel<P, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    if (sequential || f->mode == DDM_IIR_PARALLEL_EXACT) iir_kernel<P, true, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    else if (staged) iir_warp_kernel<P, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    else iir_kernel<P, false, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     DDM_CUDA(cudaGetLastError());
     count_launch();
     return DDM_OK;
@@ -1053,8 +1447,12 @@ int launch_fir(ddm_filter *f, const void *x, void *y, long long n, const double2
         if (rc != DDM_OK) return rc;
         const int V = kFftFirN - (f->nb - 1);
         const long long blocks = (n + V - 1) / V;
-        fir_fft_kernel<CPLX><<<static_cast<unsigned>(blocks), kFftFirThreads, 0, st>>>(
-            static_cast<const T *>(x), static_cast<T *>(y), f->d_H, f->d_tw, zi, n, f->nb);
+        constexpr size_t smem = fft_fir_smem_bytes(CPLX);
+        auto kern = fir_fft_kernel<CPLX>;
+        DDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const long long grid = std::min<long long>(blocks, 2LL * f->sms);
+        kern<<<static_cast<unsigned>(grid), kFftFirThreads, smem, st>>>(
+            static_cast<const T *>(x), static_cast<T *>(y), f->d_H, f->d_tw, zi, n, f->nb, blocks);
         DDM_CUDA(cudaGetLastError());
         count_launch();
         return DDM_OK;
@@ -1276,7 +1674,8 @@ int ddm_filter_set_fir_mode(ddm_filter *f, int mode) {
 
 int ddm_filter_set_iir_mode(ddm_filter *f, int mode) {
     DDM_REQUIRE(f != nullptr, "ddm_filter_set_iir_mode: NULL handle");
-    DDM_REQUIRE(mode == DDM_IIR_AUTO || mode == DDM_IIR_PARALLEL || mode == DDM_IIR_SEQUENTIAL,
+    DDM_REQUIRE(mode == DDM_IIR_AUTO || mode == DDM_IIR_PARALLEL || mode == DDM_IIR_SEQUENTIAL ||
+                    mode == DDM_IIR_PARALLEL_EXACT,
                 "ddm_filter_set_iir_mode: bad mode %d", mode);
     f->mode = mode;
     return DDM_OK;

@@ -95,7 +95,8 @@ class filter:
         self._owns_handle = True
 
     def setIIRMode(self, mode):
-        """0 auto (default), 1 segment-parallel, 2 sequential bit-exact replay (see ddemod.h)."""
+        """0 auto (default), 1 segment-parallel (DFMA-contracted), 2 sequential bit-exact replay,
+        3 segment-parallel with scipy's separately rounded operations (see ddemod.h)."""
         self._unshare()
         _lib.check(_lib.lib().ddm_filter_set_iir_mode(self._handle(), int(mode)), "ddm_filter_set_iir_mode")
         return self

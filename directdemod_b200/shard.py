@@ -118,9 +118,10 @@ class TimeShardedFilters:
     all of it is RAW input of the previous slab, so ONE neighbour exchange of
     ``halo_len = sum(lookbacks)`` samples (NCCL point-to-point) serves the whole cascade and does
     not wait for the neighbour's compute.  Rank 0 runs the filters statefully from the reference's
-    initial conditions (lfilter_zi); ranks > 0 run them from zero state over [halo ++ slab] and
-    drop the first halo_len outputs -- by then the zero-input response of every stage has decayed
-    below one ulp.  A filter that only runs as a sequential replay raises at construction."""
+    initial conditions (lfilter_zi); ranks > 0 run them from zero state over [halo ++ slab] -- every
+    stage statefully over the halo first, then over the slab, so the concatenation is never
+    materialised -- and keep the slab part: by then the zero-input response of every stage has
+    decayed below one ulp.  A filter that only runs as a sequential replay raises at construction."""
 
     def __init__(self, filts, n_samples, rank, world, group=None):
         self.filts = list(filts)
@@ -132,14 +133,16 @@ class TimeShardedFilters:
             if world > 1 and e - s < self.halo_len:
                 raise ValueError("slab of %d samples is shorter than the %d-sample halo" % (e - s, self.halo_len))
 
-    def run(self, x_slab):
-        import ctypes as C
+    def run(self, x_slab, halo=None):
+        """Filter this rank's slab.  ``halo`` (the last ``halo_len`` raw samples of the previous
+        slab, on the device) may be passed by a caller that moved it itself; otherwise it is
+        exchanged here over the process group."""
+        import numpy as np
         import torch
         from . import _dev, _lib
         if x_slab.numel() != self.end - self.start:
             raise ValueError("slab has %d samples, expected %d" % (x_slab.numel(), self.end - self.start))
-        halo = None
-        if self.world > 1:
+        if self.world > 1 and halo is None:
             send = x_slab[-self.halo_len:] if self.rank + 1 < self.world else \
                 torch.empty(self.halo_len, dtype=x_slab.dtype, device=x_slab.device)
             halo = exchange_halo(send.contiguous(), self.rank, self.world, self.group)
@@ -148,12 +151,22 @@ class TimeShardedFilters:
             for f in self.filts:
                 y = f._apply_dev(y)
             return y
-        y = torch.cat([halo, x_slab])
+        if halo.numel() != self.halo_len:
+            raise ValueError("halo has %d samples, expected %d" % (halo.numel(), self.halo_len))
+        # [halo ++ slab] from zero state without materialising the concatenation: every stage runs
+        # statefully over the halo first (outputs feed the next stage's warm-up and are then dropped)
+        # and carries its delay line / recursion state into the slab
         l = _lib.lib()
+        st = _dev.stream_ptr(x_slab.device.index)
+        y_h, y_s = halo.contiguous(), x_slab
         for f in self.filts:
-            out = torch.empty_like(y)
-            _lib.check(l.ddm_filter_apply_dev(f._handle(), _dev.ptr(y), y.numel(), int(y.is_complex()),
-                                              _dev.ptr(out), 0, _dev.stream_ptr(y.device.index)),
-                       "ddm_filter_apply_dev")
-            y = out
-        return y[self.halo_len:]
+            f._unshare()                      # the carried state below must be this cascade's own
+            f.setState(np.zeros(f._state_len(), dtype=np.complex128))
+            outs = []
+            for part in (y_h, y_s):
+                out = torch.empty_like(part)
+                _lib.check(l.ddm_filter_apply_dev(f._handle(), _dev.ptr(part), part.numel(), int(part.is_complex()),
+                                                  _dev.ptr(out), 1, st), "ddm_filter_apply_dev")
+                outs.append(out)
+            y_h, y_s = outs
+        return y_s

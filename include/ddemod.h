@@ -170,10 +170,13 @@ int ddm_filter_set_zi_base(ddm_filter *f, const double *zi_host);
  * decode_noaa.py:274); a run that is not the very same sequential loop cannot agree with it
  * better than that floor.  AUTO measures the floor at create time and replays the loop
  * sequentially (one thread, bit-exact float64) when it exceeds 1e-7, otherwise runs
- * segment-parallel. */
+ * segment-parallel.  The segment-parallel mode contracts every multiply-add pair of the recursion
+ * into one DFMA (half the FP64 issues: the kernel becomes HBM-bound); PARALLEL_EXACT keeps scipy's
+ * separately rounded operations in the segments as well. */
 #define DDM_IIR_AUTO 0
 #define DDM_IIR_PARALLEL 1
 #define DDM_IIR_SEQUENTIAL 2
+#define DDM_IIR_PARALLEL_EXACT 3
 int ddm_filter_set_iir_mode(ddm_filter *f, int mode);
 /* FIR execution path: direct register-tiled convolution (FP32-pipe bound, cost grows with the tap
  * count) or overlap-save through 4096-point FFTs in shared memory (HBM bound, up to 2049 taps).

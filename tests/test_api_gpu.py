@@ -173,6 +173,12 @@ def test_iir_roundoff_floor_and_execution_modes(golden):
     b8, a8 = O.taps_butter(2400000, 100000, n=8)
     ref8, _ = sps.lfilter(b8, a8, xl, zi=sps.lfilter_zi(b8, a8))
     assert O.rel_rms(f8.applyOn(xl), ref8) <= TOL
+    # the segment-parallel mode contracts the recursion into DFMAs: far below the tolerance, at the
+    # filter's own roundoff floor; mode 3 keeps scipy's separately rounded operations in the segments
+    y_fma = filters.butter(2400000, 100000, n=8).setIIRMode(1).applyOn(xl)
+    y_sep = filters.butter(2400000, 100000, n=8).setIIRMode(3).applyOn(xl)
+    assert O.rel_rms(y_fma, ref8) <= 1e-6 and O.rel_rms(y_sep, ref8) <= 1e-6
+    assert np.array_equal(y_sep[:64], ref8[:64].astype(np.float32).astype(np.float64))   # first segment: scipy's own bits
 
 
 def test_stateless_and_zero_phase_filters_match_reference(golden):
@@ -524,3 +530,39 @@ def test_empty_and_tiny_inputs_behave_like_the_reference():
     y = filters.rollingAverage(4).applyOn(np.arange(40)[::2])
     want, _ = O.filt_stateful([0.25] * 4, [1], np.arange(40)[::2].astype(float), O.initial_zi([0.25] * 4))
     assert O.rel_rms(y, want) <= TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_parallel_iir_ragged_lengths_and_chunk_carry(cplx):
+    """The segment-parallel IIR over awkward lengths (shorter than a block, not a multiple of 16,
+    shorter than the warm-up, several warps with a ragged last segment), chunk after chunk with the
+    carried state, and from a sample-misaligned device view (the kernel without shared-memory
+    staging): all equal scipy's lfilter on the whole stream."""
+    import scipy.signal as sps
+    import torch
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(11)
+    sizes = [1, 5, 15, 16, 17, 63, 64, 65, 1000, 4097, 70001, 300000, 1234567, 3, 2048]
+    n = sum(sizes)
+    x = rng.standard_normal(n).astype(np.float32)
+    if cplx:
+        x = (x + 1j * rng.standard_normal(n).astype(np.float32)).astype(np.complex64)
+    for make in (lambda: filters.butter(2400000, 100000, n=8), lambda: filters.butter(48000, 3000, n=3, typeFlt=constants.FLT_HP)):
+        f = make()
+        b, a = np.asarray(f.getB, dtype=np.float64), np.asarray(f.getA, dtype=np.float64)
+        want, _ = sps.lfilter(b, a, x.astype(np.complex128 if cplx else np.float64), zi=sps.lfilter_zi(b, a))
+        got, pos = [], 0
+        for m in sizes:
+            got.append(f.applyOn(x[pos:pos + m]))
+            pos += m
+        got = np.concatenate(got)
+        assert got.shape == want.shape
+        assert O.rel_rms(got, want) <= TOL
+        assert np.max(np.abs(got - want)) <= 1e-4 * np.max(np.abs(want))
+        # misaligned device input (one sample into an aligned buffer)
+        f2 = make()
+        xd = torch.from_numpy(x).cuda()
+        got2 = f2.applyOn(xd[1:200001])
+        got2 = got2.cpu().numpy() if hasattr(got2, "cpu") else np.asarray(got2)
+        want2, _ = sps.lfilter(b, a, x[1:200001].astype(np.complex128 if cplx else np.float64), zi=sps.lfilter_zi(b, a))
+        assert O.rel_rms(got2, want2) <= TOL
