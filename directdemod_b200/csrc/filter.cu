@@ -833,7 +833,7 @@ __device__ __noinline__ void iir_copy_in_edge(const SI *__restrict__ x, uint4 *s
 }
 
 template <int P, typename SI, typename SO>
-__global__ void __launch_bounds__(kIirThreads, 6)
+__global__ void __launch_bounds__(kIirThreads, P > 12 ? 4 : 6)
 iir_warp_kernel(const IirParams prm) {
     constexpr bool CPLX = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
     using V = typename IirV<CPLX>::V;
@@ -964,6 +964,81 @@ iir_warp_kernel(const IirParams prm) {
     if (prm.zf != nullptr && s1 == n && s0 < n) {
 #pragma unroll
         for (int i = 0; i < P; ++i) prm.zf[i] = to_d2(z[i]);
+    }
+}
+
+// ---- sequential replay across the lanes of one warp -------------------------------------------
+// The bit-exact replay is a serial dependency in time, but not across the delay line: given y[n],
+// the P updates Z[i] = (Z[i+1] + x b[i+1]) - y a[i+1] are independent.  Lane i keeps Z[i] (lanes
+// 16.. keep the imaginary recursion of a complex signal, which never mixes with the real one), lane 0
+// forms y = Z[0] + b[0] x and broadcasts it, every lane fetches its upper neighbour's Z by shuffle.
+// Same operations, same operands, same order as iir_step<EXACT> -- hence the same bits -- but a
+// sample costs one y-broadcast plus three dependent FP64 operations instead of a 4P+2 long
+// instruction sequence of one thread (order 12: 8.8 -> ~40 Msps).  Samples are staged through
+// shared memory in blocks of 128: converted to float64 on the way in, broadcast-read per sample,
+// collected and written back coalesced.
+constexpr int kIirSeqBlock = 128;
+
+__device__ __forceinline__ double shfl_f64(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src),
+                            __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+__device__ __forceinline__ double shfl_down_f64(double v) {
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), 1),
+                            __shfl_down_sync(0xffffffffu, __double2loint(v), 1));
+}
+
+template <int P, typename SI, typename SO>
+__global__ void __launch_bounds__(32)
+iir_seq_warp_kernel(const IirParams prm) {
+    static_assert(P <= 16, "one half-warp per recursion");
+    constexpr bool CPLX = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
+    constexpr int T = kIirSeqBlock;
+    __shared__ double2 xs[T];
+    __shared__ double2 ys[T];
+    const int lane = threadIdx.x;
+    const int i = lane & 15;                 // delay-line index of this lane
+    const bool upper = lane >= 16;           // imaginary recursion (complex signals only)
+    const SI *__restrict__ x = static_cast<const SI *>(prm.x);
+    SO *__restrict__ y = static_cast<SO *>(prm.y);
+    const long long n = prm.n;
+
+    const double b0 = prm.c.b[0];
+    const double bn = i < P ? prm.c.b[i + 1] : 0.0;
+    const double an = i < P ? prm.c.a[i + 1] : 0.0;
+    const bool last = i >= P - 1;            // Z[P-1] has no upper neighbour
+    double z = 0.0;
+    if (i < P && prm.zi != nullptr) z = upper ? prm.zi[i].y : prm.zi[i].x;
+
+    for (long long pos = 0; pos < n; pos += T) {
+        const int cnt = n - pos < T ? static_cast<int>(n - pos) : T;
+        for (int k = lane; k < cnt; k += 32) xs[k] = to_d2(vload(x[pos + k]));
+        __syncwarp();
+        for (int k = 0; k < cnt; ++k) {
+            const double2 xv = xs[k];
+            const double xk = upper ? xv.y : xv.x;
+            const double zn = shfl_down_f64(z);
+            const double bx = __dmul_rn(bn, xk);
+            const double t = last ? bx : __dadd_rn(zn, bx);
+            const double y0 = __dadd_rn(z, __dmul_rn(b0, xk));          // meaningful on lanes 0 and 16
+            const double yk = shfl_f64(y0, lane & 16);
+            z = __dsub_rn(t, __dmul_rn(an, yk));
+            if (i == 0) {
+                if (upper) ys[k].y = y0;
+                else ys[k].x = y0;
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < cnt; k += 32) {
+            if constexpr (CPLX) y[pos + k] = vout<SO>(ys[k]);
+            else y[pos + k] = vout<SO>(ys[k].x);
+        }
+        __syncwarp();
+    }
+    if (prm.zf != nullptr) {
+        // gather (re, im) of every Z[i] on the lower half-warp
+        const double zim = shfl_f64(z, (lane & 15) + 16);
+        if (!upper && i < P) prm.zf[i] = make_double2(z, CPLX ? zim : 0.0);
     }
 }
 
@@ -1352,7 +1427,9 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     prm.W = (prm.W + kIirBlock - 1) / kIirBlock * kIirBlock;
     const long long segs = (n + L - 1) / L;
     const unsigned grid = static_cast<unsigned>((segs + kIirThreads - 1) / kIirThreads);
-    if (sequential || f->mode == DDM_IIR_PARALLEL_EXACT) iir_kernel<P, true, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    static const bool seq_one_thread = std::getenv("DDM_IIR_SEQ_THREAD") != nullptr;
+    if (sequential && !seq_one_thread) iir_seq_warp_kernel<P, SI, SO><<<1, 32, 0, st>>>(prm);
+    else if (sequential || f->mode == DDM_IIR_PARALLEL_EXACT) iir_kernel<P, true, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     else if (staged) iir_warp_kernel<P, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     else iir_kernel<P, false, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     DDM_CUDA(cudaGetLastError());
