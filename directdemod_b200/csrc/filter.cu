@@ -811,12 +811,12 @@ iir_kernel(const IirParams prm) {
 // general form of a step's copy: rows that have not reached position 0 yet or run past the end of
 // the signal are zero-filled by the copy itself (edge warps only; kept out of line so that its index
 // arithmetic does not weigh on the registers of the main loop)
-template <typename SI, int PI, int RI>
+template <typename SI, int PI, int RI, int ROWS>
 __device__ __noinline__ void iir_copy_in_edge(const SI *__restrict__ x, uint4 *s_row0, long long p0, long long seg0,
                                               long long L, long long n, int lane) {
     constexpr int perI = 16 / sizeof(SI);
 #pragma unroll 1
-    for (int i = 0; i < PI; ++i) {
+    for (int i = 0; i < ROWS * PI / 32; ++i) {
         const int q = i * 32 + lane, row = q / PI, col = q % PI;
         const long long pr = p0 + row * L;
         long long end = (seg0 + row + 1) * L;
@@ -832,56 +832,79 @@ __device__ __noinline__ void iir_copy_in_edge(const SI *__restrict__ x, uint4 *s
     }
 }
 
-template <int P, typename SI, typename SO>
-__global__ void __launch_bounds__(kIirThreads, P > 12 ? 4 : 6)
+template <typename S>
+struct IirScalar { using T = S; };
+template <>
+struct IirScalar<float2> { using T = float; };
+template <>
+struct IirScalar<double2> { using T = double; };
+
+// A complex signal is two independent real recursions: lanes 2r and 2r+1 share row r and run its
+// real and imaginary part (SPLIT).  Half the state per lane (17 instead of 34 DFMA per sample and
+// lane, ~half the registers: more resident warps to cover the FP64 latency) and twice as many
+// samples per segment for the same number of threads, which halves the warm-up overhead of
+// chunk-sized signals.
+template <int P, bool SPLIT, typename SI, typename SO>
+__global__ void __launch_bounds__(kIirThreads, SPLIT ? (P > 12 ? 5 : (P > 8 ? 8 : 10)) : (P > 12 ? 4 : (P > 8 ? 6 : 8)))
 iir_warp_kernel(const IirParams prm) {
     constexpr bool CPLX = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
-    using V = typename IirV<CPLX>::V;
+    static_assert(CPLX || !SPLIT, "only complex signals split into two recursions");
+    // scalar types of one recursion: the components when SPLIT, the samples themselves otherwise
+    using XS = typename std::conditional<SPLIT, typename IirScalar<SI>::T, SI>::type;
+    using YS = typename std::conditional<SPLIT, typename IirScalar<SO>::T, SO>::type;
+    using V = typename std::conditional<SPLIT, double, typename IirV<CPLX>::V>::type;
+    constexpr int ROWS = SPLIT ? 16 : 32;                   // segments per warp
     constexpr int BI = 128 / sizeof(SI) > kIirBlock ? kIirBlock : 128 / sizeof(SI);
     constexpr int BO = 128 / sizeof(SO) > kIirBlock ? kIirBlock : 128 / sizeof(SO);
-    constexpr int B = BI < BO ? BI : BO;                    // samples per lane and step
+    constexpr int B = BI < BO ? BI : BO;                    // samples per row and step
     constexpr int PI = B * sizeof(SI) / 16, PO = B * sizeof(SO) / 16;      // 16-byte pieces per row
     constexpr int RI = PI + 1, RO = PO + 1;                 // padded row lengths (in pieces)
     constexpr int perI = 16 / sizeof(SI), perO = 16 / sizeof(SO);
+    constexpr int NI = ROWS * PI / 32, NO = ROWS * PO / 32; // copy instructions per lane and step
+    constexpr int CI = sizeof(SI) / sizeof(XS);             // scalars per sample (2 when SPLIT)
     constexpr int kWarps = kIirThreads / 32;
-    __shared__ uint4 s_in[kWarps][2][32 * RI];
-    __shared__ uint4 s_out[kWarps][32 * RO];
+    __shared__ uint4 s_in[kWarps][2][ROWS * RI];
+    __shared__ uint4 s_out[kWarps][ROWS * RO];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long seg0 = (blockIdx.x * static_cast<long long>(kWarps) + warp) * 32;    // lane 0's segment
+    const int row = SPLIT ? lane >> 1 : lane, half = SPLIT ? lane & 1 : 0;
+    const long long seg0 = (blockIdx.x * static_cast<long long>(kWarps) + warp) * ROWS;  // row 0's segment
     if (seg0 * prm.L >= prm.n) return;
     const SI *__restrict__ x = static_cast<const SI *>(prm.x);
     SO *__restrict__ y = static_cast<SO *>(prm.y);
     const long long L = prm.L, W = prm.W, n = prm.n;
-    const long long s0 = (seg0 + lane) * L;
+    const long long s0 = (seg0 + row) * L;
     long long s1 = s0 + L;
     if (s1 > n) s1 = n;
-    const bool interior = (seg0 + 32) * L <= n;             // every segment of this warp is complete
+    const bool interior = (seg0 + ROWS) * L <= n;           // every segment of this warp is complete
 
     V z[P];
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         z[i] = vzero(V());
-        if (s0 - W <= 0 && prm.zi != nullptr) from_d2(z[i], prm.zi[i]);
+        if (s0 - W <= 0 && prm.zi != nullptr) {
+            if constexpr (SPLIT) z[i] = half ? prm.zi[i].y : prm.zi[i].x;
+            else from_d2(z[i], prm.zi[i]);
+        }
     }
 
-    // step t covers positions [s0 - W + t B, + B) of every lane's segment; p0 is lane 0's position.
-    // Piece i of a lane: row lane / PI + i (32 / PI), column lane % PI.
+    // step t covers positions [s0 - W + t B, + B) of every row's segment; p0 is row 0's position.
+    // Copy piece i of a lane: row lane / PI + i (32 / PI), column lane % PI.
     const unsigned in_base = static_cast<unsigned>(__cvta_generic_to_shared(&s_in[warp][0][(lane / PI) * RI + lane % PI]));
     const long long in_off = (lane / PI) * L + (lane % PI) * perI;
     const long long out_off = (lane / PO) * L + (lane % PO) * perO;
     auto copy_in = [&](long long p0, int stage) {
         if (interior && p0 >= 0) {
             const SI *src = x + p0 + in_off;
-            unsigned d = in_base + stage * (32 * RI * 16);
+            unsigned d = in_base + stage * (ROWS * RI * 16);
 #pragma unroll
-            for (int i = 0; i < PI; ++i) {
+            for (int i = 0; i < NI; ++i) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
                 d += (32 / PI) * RI * 16;
                 src += (32 / PI) * L;
             }
         } else {
-            iir_copy_in_edge<SI, PI, RI>(x, &s_in[warp][stage][0], p0, seg0, L, n, lane);
+            iir_copy_in_edge<SI, PI, RI, ROWS>(x, &s_in[warp][stage][0], p0, seg0, L, n, lane);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -900,53 +923,41 @@ iir_warp_kernel(const IirParams prm) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
-        const long long pos = p0 + lane * L;
+        const long long pos = p0 + row * L;
         long long left = s1 - pos;
         if (pos < 0 || left < 0) left = 0;
         const int cnt = left < B ? static_cast<int>(left) : B;
         const bool warm = t < warm_steps;
-        const uint4 *my_in = &s_in[warp][stage][lane * RI];
-        // lanes with a whole block compute; lanes that have not reached position 0 yet or are past
+        const uint4 *my_in = &s_in[warp][stage][row * RI];
+        YS *my_out = reinterpret_cast<YS *>(&s_out[warp][row * RO]) + half;
+        // rows with a whole block compute; rows that have not reached position 0 yet or are past
         // the end of their segment sit the step out; a partial block (once per launch, at the end of
         // the signal) sends the warp through the scalar form
         if (!__any_sync(0xffffffffu, cnt > 0 && cnt < B)) {
-            if (warm) {
-                if (cnt == B) {
+            if (cnt == B) {
 #pragma unroll
-                    for (int i = 0; i < PI; ++i) {
-                        SI cur[perI];
-                        const uint4 v = my_in[i];
-                        memcpy(cur, &v, 16);
+                for (int i = 0; i < PI; ++i) {
+                    XS cur[perI * CI];
+                    const uint4 v = my_in[i];
+                    memcpy(cur, &v, 16);
 #pragma unroll
-                        for (int k = 0; k < perI; ++k) iir_step<P, false, V>(z, vload(cur[k]), prm.c);
+                    for (int k = 0; k < perI; ++k) {
+                        // (a select, not an index: a runtime index would put cur in local memory)
+                        const XS xk = CI == 2 ? (half ? cur[k * CI + CI - 1] : cur[k * CI]) : cur[k];
+                        const V r = iir_step<P, false, V>(z, vload(xk), prm.c);
+                        if (!warm) my_out[(i * perI + k) * CI] = vout<YS>(r);
                     }
                 }
-            } else {
-                if (cnt == B) {
-                    SO out[B];
-#pragma unroll
-                    for (int i = 0; i < PI; ++i) {
-                        SI cur[perI];
-                        const uint4 v = my_in[i];
-                        memcpy(cur, &v, 16);
-#pragma unroll
-                        for (int k = 0; k < perI; ++k)
-                            out[i * perI + k] = vout<SO>(iir_step<P, false, V>(z, vload(cur[k]), prm.c));
-                    }
-#pragma unroll
-                    for (int i = 0; i < PO; ++i) {
-                        uint4 v;
-                        memcpy(&v, &out[i * perO], 16);
-                        s_out[warp][lane * RO + i] = v;
-                    }
-                }
+            }
+            if (!warm) {
                 __syncwarp();
                 SO *dst = y + p0 + out_off;
                 const uint4 *so = &s_out[warp][(lane / PO) * RO + lane % PO];
 #pragma unroll
-                for (int i = 0; i < PO; ++i) {
+                for (int i = 0; i < NO; ++i) {
                     // interior warps: every row holds a whole block in every output step
-                    const bool ok = interior || __shfl_sync(0xffffffffu, cnt, lane / PO + i * (32 / PO)) == B;
+                    const int src_row = lane / PO + i * (32 / PO);
+                    const bool ok = interior || __shfl_sync(0xffffffffu, cnt, SPLIT ? 2 * src_row : src_row) == B;
                     if (ok) *reinterpret_cast<uint4 *>(dst) = so[i * (32 / PO) * RO];
                     dst += (32 / PO) * L;
                 }
@@ -954,16 +965,23 @@ iir_warp_kernel(const IirParams prm) {
         } else if (cnt > 0) {
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-                const SI xi = reinterpret_cast<const SI *>(my_in)[i];
+                const XS xi = reinterpret_cast<const XS *>(my_in)[i * CI + half];
                 const V r = iir_step<P, false, V>(z, vload(xi), prm.c);
-                if (!warm) y[pos + i] = vout<SO>(r);
+                if (!warm) reinterpret_cast<YS *>(y + pos + i)[half] = vout<YS>(r);
             }
         }
         __syncwarp();
     }
     if (prm.zf != nullptr && s1 == n && s0 < n) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) prm.zf[i] = to_d2(z[i]);
+        for (int i = 0; i < P; ++i) {
+            if constexpr (SPLIT) {
+                if (half) prm.zf[i].y = z[i];
+                else prm.zf[i].x = z[i];
+            } else {
+                prm.zf[i] = to_d2(z[i]);
+            }
+        }
     }
 }
 
@@ -1405,6 +1423,8 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     static const bool no_staging = std::getenv("DDM_IIR_NO_STAGING") != nullptr;
     const bool staged = !sequential && f->mode != DDM_IIR_PARALLEL_EXACT && !no_staging &&
                         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    constexpr bool cplx = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
+    bool split = false;
     if (sequential) {
         L = n;                                        // one thread replays scipy's loop
         prm.W = 0;
@@ -1412,13 +1432,18 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
         // Warps per SM sub-partition (measured, 1.08 G cf32 samples through the 8th-order low-pass):
         // separately rounded arithmetic is FP64-pipe-bound and two warps saturate it (8.07 -> 5.43 ms,
         // more are no faster); the DFMA form through the warp-staged kernel is fastest with three
-        // (4.29 / 3.96 / 4.74 ms for 2 / 3 / 4).  When that would make the segments shorter than twice
-        // the warm-up, one warp per sub-partition keeps the redundant warm-up work down instead.
-        const long long base = static_cast<long long>(f->sms) * 4 * 32;
-        long long wps = staged ? 3 : 2;
+        // (4.29 / 3.96 / 4.74 ms for 2 / 3 / 4).
+        // The staged kernel runs a complex signal either as one complex recursion per lane (fewest
+        // instructions per sample: 3.96 ms per 1.08 G samples with three warps per sub-partition) or
+        // split over lane pairs (half as many segments for the same number of threads: 4.23 ms there,
+        // but half the warm-up overhead once the segments get short -- 100 M samples 0.64 vs 0.73 ms).
+        // Warps per sub-partition: as many as keep the segments at least twice the warm-up long.
+        split = staged && cplx && n < 6 * f->warmup * (static_cast<long long>(f->sms) * 4 * 32 * 3);
+        const long long base = static_cast<long long>(f->sms) * 4 * 32 / (split ? 2 : 1);
+        long long wps = staged ? (split || !cplx ? 4 : 3) : 2;
         if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));
+        while (wps > 1 && (n + base * wps - 1) / (base * wps) < 2 * f->warmup) --wps;
         L = (n + base * wps - 1) / (base * wps);
-        if (wps > 1 && L < 2 * f->warmup) L = (n + base - 1) / base;
         if (L < 4 * kIirBlock) L = 4 * kIirBlock;
         prm.W = f->warmup;
     }
@@ -1426,11 +1451,16 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     prm.L = L;
     prm.W = (prm.W + kIirBlock - 1) / kIirBlock * kIirBlock;
     const long long segs = (n + L - 1) / L;
-    const unsigned grid = static_cast<unsigned>((segs + kIirThreads - 1) / kIirThreads);
+    unsigned grid = static_cast<unsigned>((segs + kIirThreads - 1) / kIirThreads);
+    if (staged) {
+        const long long rows_per_cta = (kIirThreads / 32) * (split ? 16 : 32);
+        grid = static_cast<unsigned>((segs + rows_per_cta - 1) / rows_per_cta);
+    }
     static const bool seq_one_thread = std::getenv("DDM_IIR_SEQ_THREAD") != nullptr;
     if (sequential && !seq_one_thread) iir_seq_warp_kernel<P, SI, SO><<<1, 32, 0, st>>>(prm);
     else if (sequential || f->mode == DDM_IIR_PARALLEL_EXACT) iir_kernel<P, true, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
-    else if (staged) iir_warp_kernel<P, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    else if (staged && split) iir_warp_kernel<P, cplx, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
+    else if (staged) iir_warp_kernel<P, false, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     else iir_kernel<P, false, SI, SO><<<grid, kIirThreads, 0, st>>>(prm);
     DDM_CUDA(cudaGetLastError());
     count_launch();
