@@ -937,8 +937,10 @@ iir_warp_kernel(const IirParams prm) {
             if (cnt == B) {
 #pragma unroll
                 for (int i = 0; i < PI; ++i) {
-                    XS cur[perI * CI];
+                    // (float -> double on the integer pipe instead of F2F, which occupies the FP64 pipe,
+                    // measured slower: 3.96 -> 5.33 ms -- the extra issue slots cost more than they free)
                     const uint4 v = my_in[i];
+                    XS cur[perI * CI];
                     memcpy(cur, &v, 16);
 #pragma unroll
                     for (int k = 0; k < perI; ++k) {
@@ -1205,6 +1207,7 @@ struct ddm_filter {
     // IIR
     int P = 0;
     long long warmup = -1;          // samples after which a zero-state run matches; -1 = never
+    long long warmup_fast = -1;     // ... matches to 1e-18: the warm-up of the DFMA modes
     double noise_floor = 0.0;       // relative roundoff noise of the float64 recursion itself
     int mode = 0;                   // DDM_IIR_AUTO / _PARALLEL / _SEQUENTIAL / _PARALLEL_EXACT
     int sms = 148;
@@ -1290,47 +1293,60 @@ int setup_fir(ddm_filter *f) {
 // Host-side analysis of an IIR (order >= 1, coefficients normalised by a[0], padded to order+1):
 // warm-up length of the segment-parallel run and the float64 roundoff floor of the recursion.
 void analyse_iir_uncached(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
-                          double *noise_floor);
+                          long long *warmup_fast, double *noise_floor);
 
 // The analysis costs tens of milliseconds of host time (long-double simulations); decoders build a
 // new filter object per call with the same coefficients, so results are remembered per (b, a).
+struct IirAnalysis {
+    long long warmup, warmup_fast;
+    double noise_floor;
+};
+
 void analyse_iir(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
-                 double *noise_floor) {
+                 long long *warmup_fast, double *noise_floor) {
     static std::mutex mu;
-    static std::map<std::vector<double>, std::pair<long long, double>> cache;
+    static std::map<std::vector<double>, IirAnalysis> cache;
     std::vector<double> key(b);
     key.insert(key.end(), a.begin(), a.end());
     {
         std::lock_guard<std::mutex> lk(mu);
         auto it = cache.find(key);
         if (it != cache.end()) {
-            *warmup = it->second.first;
-            *noise_floor = it->second.second;
+            *warmup = it->second.warmup;
+            if (warmup_fast) *warmup_fast = it->second.warmup_fast;
+            *noise_floor = it->second.noise_floor;
             return;
         }
     }
-    analyse_iir_uncached(order, b, a, warmup, noise_floor);
+    long long wf = -1;
+    analyse_iir_uncached(order, b, a, warmup, &wf, noise_floor);
+    if (warmup_fast) *warmup_fast = wf;
     std::lock_guard<std::mutex> lk(mu);
-    if (cache.size() < 1024) cache[key] = std::make_pair(*warmup, *noise_floor);
+    if (cache.size() < 1024) cache[key] = IirAnalysis{*warmup, wf, *noise_floor};
 }
 
 void analyse_iir_uncached(int order, const std::vector<double> &b, const std::vector<double> &a, long long *warmup,
-                          double *noise_floor) {
+                          long long *warmup_fast, double *noise_floor) {
     // Warm-up length of the segment-parallel run: the zero-input response of the recursion,
     // started from each unit state vector, simulated in long double until every state has
     // fallen below 1e-30 (a zero-input run has no roundoff floor, it decays geometrically all
     // the way).  Matrix powers of the companion form are useless here: for the reference's
     // clustered Butterworth poles they carry 1e20 transients and cancel catastrophically.
+    // The DFMA modes do not reproduce scipy's rounding history anyway and only need the discarded
+    // transient far below the parity tolerance: their warm-up ends where the response has fallen
+    // below 1e-18 (times a state discrepancy of at most ~1e9 signal units for the filters this mode
+    // accepts: 1e-9 relative, four orders under the tolerance) -- about 60 % of the full length.
     *warmup = -1;
+    *warmup_fast = -1;
     {
         const int p = order;
         const long long cap = 1LL << 22;
-        long long worst = 0;
+        long long worst = 0, worst_fast = 0;
         bool ok = true;
         for (int u = 0; u < p && ok; ++u) {
             std::vector<ld> z(p + 1, 0.0L);
             z[u] = 1.0L;
-            long long k = 0, quiet = 0;
+            long long k = 0, quiet = 0, quiet_fast = 0, k_fast = -1;
             while (k < cap) {
                 const ld y = z[0];
                 ld m = 0;
@@ -1343,13 +1359,19 @@ void analyse_iir_uncached(int order, const std::vector<double> &b, const std::ve
                     ok = false;
                     break;
                 }
+                quiet_fast = m < 1e-18L ? quiet_fast + 1 : 0;
+                if (k_fast < 0 && quiet_fast >= 2 * p + 2) k_fast = k;
                 quiet = m < 1e-30L ? quiet + 1 : 0;
                 if (quiet >= 2 * p + 2) break;
             }
             if (k >= cap) ok = false;
             worst = std::max(worst, k);
+            worst_fast = std::max(worst_fast, k_fast < 0 ? k : k_fast);
         }
-        if (ok) *warmup = worst + kIirBlock;
+        if (ok) {
+            *warmup = worst + kIirBlock;
+            *warmup_fast = worst_fast + kIirBlock;
+        }
     }
     // Roundoff noise floor of scipy's float64 recursion for THIS filter: run it on white noise
     // in double and in long double and compare.  Two float64 runs whose states ever differ by
@@ -1397,7 +1419,7 @@ int setup_iir(ddm_filter *f) {
         f->coef.b[i] = f->b[i];
         f->coef.a[i] = f->a[i];
     }
-    analyse_iir(f->order, f->b, f->a, &f->warmup, &f->noise_floor);
+    analyse_iir(f->order, f->b, f->a, &f->warmup, &f->warmup_fast, &f->noise_floor);
     return DDM_OK;
 }
 
@@ -1438,14 +1460,15 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
         // split over lane pairs (half as many segments for the same number of threads: 4.23 ms there,
         // but half the warm-up overhead once the segments get short -- 100 M samples 0.64 vs 0.73 ms).
         // Warps per sub-partition: as many as keep the segments at least twice the warm-up long.
-        split = staged && cplx && n < 6 * f->warmup * (static_cast<long long>(f->sms) * 4 * 32 * 3);
+        const long long W = f->mode == DDM_IIR_PARALLEL_EXACT ? f->warmup : f->warmup_fast;
+        split = staged && cplx && n < 6 * W * (static_cast<long long>(f->sms) * 4 * 32 * 3);
         const long long base = static_cast<long long>(f->sms) * 4 * 32 / (split ? 2 : 1);
         long long wps = staged ? (split || !cplx ? 4 : 3) : 2;
         if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));
-        while (wps > 1 && (n + base * wps - 1) / (base * wps) < 2 * f->warmup) --wps;
+        while (wps > 1 && (n + base * wps - 1) / (base * wps) < 2 * W) --wps;
         L = (n + base * wps - 1) / (base * wps);
         if (L < 4 * kIirBlock) L = 4 * kIirBlock;
-        prm.W = f->warmup;
+        prm.W = W;
     }
     L = (L + kIirBlock - 1) / kIirBlock * kIirBlock;
     prm.L = L;
@@ -1808,7 +1831,7 @@ int ddm_iir_analyse(const double *b, int nb, const double *a, int na, int64_t *w
     bool fir = true;
     for (int i = 1; i <= order; ++i)
         if (aa[i] != 0.0) fir = false;
-    if (!fir) analyse_iir(order, bb, aa, &w, &nf);
+    if (!fir) analyse_iir(order, bb, aa, &w, nullptr, &nf);
     if (warmup) *warmup = w;
     if (noise_floor) *noise_floor = nf;
     return DDM_OK;
