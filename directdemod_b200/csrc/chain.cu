@@ -128,8 +128,11 @@ chain_fused_kernel(const ChainParams P) {
     // thread 0: start the TMA copies that fill one stage with tile `tile`
     auto issue = [&](long long gtile, int stage) {
         unsigned char *dst = s_stage0 + stage * stage_bytes;
-        const long long cap = gtile / P.num_tiles;
-        const long long tile = gtile - cap * P.num_tiles;
+        long long cap = 0, tile = gtile;           // (a 64-bit division per tile is not free: only for batches)
+        if (P.batch > 1) {
+            cap = gtile / P.num_tiles;
+            tile = gtile - cap * P.num_tiles;
+        }
         const long long S0 = P.b0 + (tile * J - QH) * D;           // first sample (may be < 0)
         long long E = S0 + static_cast<long long>(NT) * D;
         if (E > end_all) E = end_all;
@@ -193,8 +196,11 @@ chain_fused_kernel(const ChainParams P) {
 
     for (int it = 0; gtile < total_tiles; gtile += gridDim.x, ++it) {
         const int stage = it % S;
-        const long long cap = gtile / P.num_tiles;
-        const long long tile = gtile - cap * P.num_tiles;
+        long long cap = 0, tile = gtile;
+        if (P.batch > 1) {
+            cap = gtile / P.num_tiles;
+            tile = gtile - cap * P.num_tiles;
+        }
         const long long nxt = gtile + static_cast<long long>(S - 1) * gridDim.x;
         if (tid == 0 && nxt < total_tiles) {
             // the stage being refilled was consumed in iteration it-1 (all threads are past
@@ -222,40 +228,6 @@ chain_fused_kernel(const ChainParams P) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
 
-            // two consecutive raw samples starting at block position a (a even) as packed pairs
-            const bool odd = (D & 1) != 0;       // blocks of odd threads are then only element aligned
-            auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
-                if (U8) {
-                    unsigned int w;
-                    if (odd) {
-                        const unsigned short *h = reinterpret_cast<const unsigned short *>(sp + 2 * a);
-                        w = static_cast<unsigned int>(h[0]) | (static_cast<unsigned int>(h[1]) << 16);
-                    } else {
-                        w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
-                    }
-                    const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
-                    X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
-                                          __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
-                    X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
-                                          __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
-                } else if (odd) {
-                    X0 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
-                    X1 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a + 8);
-                } else {
-                    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
-                    X0 = v.x;
-                    X1 = v.y;
-                }
-            };
-            auto load1 = [&](int a) -> unsigned long long {
-                if (U8) {
-                    const unsigned int w = *reinterpret_cast<const unsigned short *>(sp + 2 * a);
-                    return fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
-                                            __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))),
-                                 pack_f32x2(-8388736.f, -8388736.f));
-                }
-                return *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
-            };
             // raw pair -> mixed sample.  cf32: x rot.  u8: (v + 0.5 (1+j)) rot with v = b - 128.
             auto rotate = [&](unsigned long long X, float rx, float2 ry, float2 c) -> unsigned long long {
                 const float2 x = unpack_f32x2(X);
@@ -264,61 +236,125 @@ chain_fused_kernel(const ChainParams P) {
                                                 : fmul2(X, pack_f32x2(rx, rx));
                 return ffma2(pack_f32x2(x.y, x.x), pack_f32x2(ry.x, ry.y), m);
             };
-            const int D4 = D & ~3;
-            int a = 0;
-            // four samples against the first NQ partial sums
-            auto body4 = [&](auto nq_tag) {
-                constexpr int NQ = decltype(nq_tag)::value;
-                unsigned long long X0, X1, X2, X3;
-                load2(a, X0, X1);
-                load2(a + 2, X2, X3);
-                float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0, c0 = ry0, c1 = ry0;
-                if (MIX) {
-                    rx = *reinterpret_cast<const float4 *>(s_rx + a);
-                    ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
-                    ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
+            // The accumulation over the D samples of this thread's block.  ODD (odd D: the blocks of
+            // odd threads are only element aligned) is a compile-time tag of this lambda, chosen by
+            // one warp-uniform branch per tile, so that the even-D instruction stream carries none of
+            // the narrower loads (as a runtime flag inside the loads it cost D = 34 16 %).
+            auto accumulate = [&](auto odd_tag) {
+                constexpr bool ODD = decltype(odd_tag)::value;
+                // two consecutive raw samples starting at block position a (a even) as packed pairs
+                auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
                     if (U8) {
-                        c0 = *reinterpret_cast<const float4 *>(s_c + a);
-                        c1 = *reinterpret_cast<const float4 *>(s_c + a + 2);
+                        unsigned int w;
+                        if (ODD) {
+                            const unsigned short *h = reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                            w = static_cast<unsigned int>(h[0]) | (static_cast<unsigned int>(h[1]) << 16);
+                        } else {
+                            w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
+                        }
+                        const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
+                        X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                              __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
+                        X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
+                                              __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
+                    } else if (ODD) {
+                        X0 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
+                        X1 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a + 8);
+                    } else {
+                        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
+                        X0 = v.x;
+                        X1 = v.y;
+                    }
+                };
+                auto load1 = [&](int a) -> unsigned long long {
+                    if (U8) {
+                        const unsigned int w = *reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                        return fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                                __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))),
+                                     pack_f32x2(-8388736.f, -8388736.f));
+                    }
+                    return *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
+                };
+                const int D4 = D & ~3;
+                int a = 0;
+                // four samples against the first NQ partial sums
+                auto body4 = [&](auto nq_tag) {
+                    constexpr int NQ = decltype(nq_tag)::value;
+                    unsigned long long X0, X1, X2, X3;
+                    load2(a, X0, X1);
+                    load2(a + 2, X2, X3);
+                    float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
+                    float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0, c0 = ry0, c1 = ry0;
+                    if (MIX) {
+                        rx = *reinterpret_cast<const float4 *>(s_rx + a);
+                        ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                        ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
+                        if (U8) {
+                            c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                            c1 = *reinterpret_cast<const float4 *>(s_c + a + 2);
+                        }
+                    }
+                    const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+                    const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+                    const unsigned long long M2 = rotate(X2, rx.z, make_float2(ry1.x, ry1.y), make_float2(c1.x, c1.y));
+                    const unsigned long long M3 = rotate(X3, rx.w, make_float2(ry1.z, ry1.w), make_float2(c1.z, c1.w));
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
+                        acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                        acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                        acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
+                        acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
+                    }
+                };
+                // the last partial sum only sees the filter's tail: its taps are zero up to a_lastq
+                if (Q > 1) {
+#pragma unroll(kChainUnroll)
+                    for (; a < P.a_lastq; a += 4) body4(std::integral_constant<int, (Q > 1 ? Q - 1 : 1)>());
+                }
+#pragma unroll(kChainUnroll)
+                for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
+                if (!ODD) {
+                    if (a < D) {                                // D % 4 == 2: one aligned pair
+                        unsigned long long X0, X1;
+                        load2(a, X0, X1);
+                        float2 rx = make_float2(1.f, 1.f);
+                        float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = ry0;
+                        if (MIX) {
+                            rx = *reinterpret_cast<const float2 *>(s_rx + a);
+                            ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                            if (U8) c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                        }
+                        const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+                        const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
+                            acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                            acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                        }
+                    }
+                } else {
+                    for (; a < D; ++a) {                        // the D % 4 samples left over
+                        const unsigned long long X0 = load1(a);
+                        float rx = 1.f;
+                        float2 ry = make_float2(0.f, 0.f), c0 = ry;
+                        if (MIX) {
+                            rx = s_rx[a];
+                            ry = s_ry[a];
+                            if (U8) c0 = s_c[a];
+                        }
+                        const unsigned long long M0 = rotate(X0, rx, ry, c0);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const float t = s_taps[q * DP + a];
+                            acc[q] = ffma2(pack_f32x2(t, t), M0, acc[q]);
+                        }
                     }
                 }
-                const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
-                const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
-                const unsigned long long M2 = rotate(X2, rx.z, make_float2(ry1.x, ry1.y), make_float2(c1.x, c1.y));
-                const unsigned long long M3 = rotate(X3, rx.w, make_float2(ry1.z, ry1.w), make_float2(c1.z, c1.w));
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
-                    acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
-                    acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
-                    acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
-                    acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
-                }
             };
-            // the last partial sum only sees the filter's tail: its taps are zero up to a_lastq
-            if (Q > 1) {
-#pragma unroll(kChainUnroll)
-                for (; a < P.a_lastq; a += 4) body4(std::integral_constant<int, (Q > 1 ? Q - 1 : 1)>());
-            }
-#pragma unroll(kChainUnroll)
-            for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
-            for (; a < D; ++a) {                            // the D % 4 samples left over
-                const unsigned long long X0 = load1(a);
-                float rx = 1.f;
-                float2 ry = make_float2(0.f, 0.f), c0 = ry;
-                if (MIX) {
-                    rx = s_rx[a];
-                    ry = s_ry[a];
-                    if (U8) c0 = s_c[a];
-                }
-                const unsigned long long M0 = rotate(X0, rx, ry, c0);
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const float t = s_taps[q * DP + a];
-                    acc[q] = ffma2(pack_f32x2(t, t), M0, acc[q]);
-                }
-            }
+            if (D & 1) accumulate(std::true_type());
+            else accumulate(std::false_type());
             float2 w0 = make_float2(1.f, 0.f);
             if (MIX) {
                 const long long g = P.n0 + P.b0 + jblk * D;  // global index of the block start

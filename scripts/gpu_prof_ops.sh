@@ -7,5 +7,5 @@ timeout 1500 ncu --set full --clock-control none --import-source on \
 tail -n 2 gpurun_out/prof_ops2.log
 # the C4 kernels of the second half of round 1 (scripts/prof_c4.py)
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'fir_fft_kernel|iir_warp_kernel|iir_seq_warp' -s 3 -c 3 -o gpurun_out/prof_c4 -f python scripts/prof_c4.py > gpurun_out/prof_c4.log 2>&1
+    -k regex:'fir_fft_kernel|iir_warp_kernel|iir_seq_warp' -s 4 -c 4 -o gpurun_out/prof_c4 -f python scripts/prof_c4.py > gpurun_out/prof_c4.log 2>&1
 tail -n 2 gpurun_out/prof_c4.log
