@@ -570,3 +570,45 @@ def test_parallel_iir_ragged_lengths_and_chunk_carry(cplx):
         got2 = got2.cpu().numpy() if hasattr(got2, "cpu") else np.asarray(got2)
         want2, _ = sps.lfilter(b, a, x[1:200001].astype(np.complex128 if cplx else np.float64), zi=sps.lfilter_zi(b, a))
         assert O.rel_rms(got2, want2) <= TOL
+
+
+def test_c4_filters_at_slab_scale_chunk_invariance_and_windows():
+    """BASELINE config 4 at a size where the production code paths run (400 M cf32 samples: the
+    persistent overlap-save FIR; the warp-staged IIR with one complex recursion per lane, which small
+    inputs never reach).  Size-independent properties: the whole slab in one call equals the same slab
+    in 20 M-sample chunks with carried state (those take the lane-split IIR kernel), and windows of the
+    output equal scipy's lfilter started W samples early."""
+    import scipy.signal as sps
+    import torch
+    chunker, comm, constants, demod_fm, filters = _mods()
+    n, chunk = 400_000_000, 20_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.empty(n, dtype=torch.complex64, device="cuda")
+    torch.view_as_real(x).normal_(0, 40, generator=g)
+    t = torch.arange(n, device="cuda", dtype=torch.float32)
+    x += 300 * torch.polar(torch.ones_like(t), t * (2 * np.pi * 0.01))      # a carrier inside the pass band
+    del t
+    for make, lookback in ((lambda: filters.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023), 1022),
+                           (lambda: filters.butter(2400000, 100000, n=8), 4000)):
+        f_whole, f_chunks = make(), make()
+        y = f_whole._apply_dev(x)
+        worst = 0.0
+        for a in range(0, n, chunk):
+            yc = f_chunks._apply_dev(x[a:a + chunk])
+            ref = y[a:a + chunk]
+            worst = max(worst, float((yc - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt()))
+            del yc
+        assert worst <= 2e-6, worst                                       # same arithmetic up to fp32 block layout
+        b, a_ = np.asarray(f_whole.getB, dtype=np.float64), np.asarray(f_whole.getA, dtype=np.float64)
+        for start in (0, 123_456_789, n - 300_000):
+            lo = max(0, start - lookback)
+            seg = x[lo:start + 300_000].cpu().numpy().astype(np.complex128)
+            if lo == 0:
+                want, _ = sps.lfilter(b, a_, seg, zi=sps.lfilter_zi(b, a_))
+            else:
+                want = sps.lfilter(b, a_, seg)
+            want = want[start - lo:]
+            got = y[start:start + 300_000].cpu().numpy()
+            assert O.rel_rms(got, want) <= TOL, (start, O.rel_rms(got, want))
+        del y
