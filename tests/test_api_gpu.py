@@ -612,3 +612,31 @@ def test_c4_filters_at_slab_scale_chunk_invariance_and_windows():
             got = y[start:start + 300_000].cpu().numpy()
             assert O.rel_rms(got, want) <= TOL, (start, O.rel_rms(got, want))
         del y
+
+
+def test_constructor_snapshot_of_large_host_arrays():
+    """commSignal copies its input (comm.py:38).  Large float32 / complex64 host arrays are
+    snapshotted straight onto the device: later writes to the caller's array must not show, .signal
+    must hand back the same values in the same dtype while no operator has run, and operators must
+    see the snapshot."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(21)
+    n = 300000
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    keep = x.copy()
+    s = comm.commSignal(2048000, x)
+    x[:] = 0                                             # the caller reuses its buffer
+    assert s.length == n
+    got = s.signal
+    assert got.dtype == np.complex64 and np.array_equal(got, keep)
+    s2 = comm.commSignal(2048000, keep.copy())
+    y = s2.filter(filters.blackmanHarris(151)).bwLim(60000).signal
+    bh = filters.blackmanHarris(151)
+    want = comm.commSignal(2048000, [complex(v) for v in keep[:70000]]).filter(bh).bwLim(60000).signal   # small/list input: host path
+    assert y.dtype == np.complex128
+    assert O.rel_rms(y[:len(want)], want) <= TOL
+    xr = rng.standard_normal(n).astype(np.float32)
+    sr = comm.commSignal(48000, xr)
+    assert sr.signal.dtype == np.float32 and np.array_equal(sr.signal, xr)
+    with pytest.raises(TypeError):
+        comm.commSignal(48000, np.zeros((70000, 2), dtype=np.float32))
