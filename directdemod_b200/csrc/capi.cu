@@ -27,7 +27,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // steady-state calls do no cudaMalloc/cudaFree.  Calls that use the pool must be serialised per
 // device by the caller (the same rule as for handles).
 namespace {
-constexpr int kScratchSlots = 8;
+constexpr int kScratchSlots = 10;     // 0..6: ncc.cu, 8..9: filtfilt temporaries (filter.cu)
 constexpr int kScratchDevices = 64;
 struct ScratchSlot {
     void *p = nullptr;

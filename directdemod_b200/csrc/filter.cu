@@ -1212,9 +1212,6 @@ struct ddm_filter {
     int mode = 0;                   // DDM_IIR_AUTO / _PARALLEL / _SEQUENTIAL / _PARALLEL_EXACT
     int sms = 148;
     IirCoef coef;
-    // scratch for filtfilt
-    void *d_tmp[2] = {nullptr, nullptr};
-    size_t tmp_cap = 0;
 };
 
 namespace {
@@ -1662,17 +1659,10 @@ int ddm_filter_filtfilt_rows_dev(ddm_filter *f, const void *x_dev, int64_t rows,
     const long long m = n + 2LL * pad;
     const long long ls = hist + m;
     const size_t need = esz * static_cast<size_t>(ls) * rows;
-    if (need > f->tmp_cap) {
-        DDM_CUDA(cudaStreamSynchronize(st));
-        cudaFree(f->d_tmp[0]);
-        cudaFree(f->d_tmp[1]);
-        f->d_tmp[0] = f->d_tmp[1] = nullptr;
-        f->tmp_cap = 0;
-        DDM_CUDA(cudaMalloc(&f->d_tmp[0], need));
-        DDM_CUDA(cudaMalloc(&f->d_tmp[1], need));
-        f->tmp_cap = need;
-    }
-    void *t0 = f->d_tmp[0], *t1 = f->d_tmp[1];
+    // temporaries from the per-device scratch pool (decoders build a new filter object per call, and
+    // cudaMalloc / cudaFree of ~100 MB cost tens of milliseconds on a context that holds gigabytes)
+    void *t0 = scratch_get(f->device, 8, need), *t1 = scratch_get(f->device, 9, need);
+    if (!t0 || !t1) return DDM_ERR_NOMEM;
     const bool cplx = is_complex != 0;
     const int tb = 256;
     const dim3 grid(static_cast<unsigned>(std::min<long long>((ls + tb - 1) / tb, 1024)), static_cast<unsigned>(rows));
@@ -1718,8 +1708,6 @@ int ddm_filter_destroy(ddm_filter *f) {
     pool_free(f->d_H);
     pool_free(f->d_tw);
     pool_free(f->d_b);
-    cudaFree(f->d_tmp[0]);
-    cudaFree(f->d_tmp[1]);
     delete f;
     return DDM_OK;
 }
@@ -1917,17 +1905,8 @@ int ddm_filter_filtfilt_dev(ddm_filter *f, const void *x_dev, int64_t n, int is_
     const bool cplx = is_complex != 0;
     const size_t esz = (cplx ? sizeof(float2) : sizeof(float)) * (f->fir ? 1 : 2);
     const long long m = n + 2LL * pad;
-    if (esz * m > f->tmp_cap) {
-        DDM_CUDA(cudaStreamSynchronize(st));
-        cudaFree(f->d_tmp[0]);
-        cudaFree(f->d_tmp[1]);
-        f->d_tmp[0] = f->d_tmp[1] = nullptr;
-        f->tmp_cap = 0;
-        DDM_CUDA(cudaMalloc(&f->d_tmp[0], esz * m));
-        DDM_CUDA(cudaMalloc(&f->d_tmp[1], esz * m));
-        f->tmp_cap = esz * m;
-    }
-    void *t0 = f->d_tmp[0], *t1 = f->d_tmp[1];
+    void *t0 = scratch_get(f->device, 8, esz * m), *t1 = scratch_get(f->device, 9, esz * m);
+    if (!t0 || !t1) return DDM_ERR_NOMEM;
     // scratch state: the "next" slot, so the carried state is untouched
     double2 *seed = f->d_state[f->cur ^ 1];
     const int tb = 256;

@@ -36,6 +36,25 @@ def _row_medians(x, starts=None, rows=None, stride=0, length=1):
     return out.cpu().numpy()
 
 
+def _fifo_medians(chunks, fifo_len, device):
+    """Medians of a FIFO that keeps the last ``fifo_len`` values, read after every append of one of
+    ``chunks`` (float32-valued arrays): np.median(concatenate(chunks[:j+1])[-fifo_len:]) for every j.
+    Full-length states are equal-length windows of the concatenation -> one ddm_row_medians call."""
+    if not chunks:
+        return np.empty(0)
+    t = _dev.torch()
+    cat = np.concatenate(chunks)
+    ends = np.cumsum([c.size for c in chunks])
+    meds = np.empty(len(chunks))
+    for j in np.nonzero(ends < fifo_len)[0]:
+        meds[j] = np.median(cat[:ends[j]]) if ends[j] else np.nan
+    full = np.nonzero(ends >= fifo_len)[0]
+    if full.size:
+        catd = t.from_numpy(cat.astype(np.float32)).to(device)
+        meds[full] = _row_medians(catd, starts=ends[full] - fifo_len, length=fifo_len)
+    return meds
+
+
 def _resample_rows(x, starts, n, num):
     """signal.resample of the rows x[s:s+n] -> [rows][num] cuda float32 (ddm_resample_rows)."""
     t = _dev.torch()
@@ -206,16 +225,42 @@ class decode_noaa:
 
         # ---- host: colour-calibration state machine over the precomputed lines -------
         image, imageBuffer, backupImage = [], [], []
-        lowFifo, highFifo = np.zeros(0), np.zeros(0)
         low_rows = [j for j in range(len(constants.NOAA_SYNCA)) if constants.NOAA_SYNCA[j] == 0]
         high_rows = [j for j in range(len(constants.NOAA_SYNCA)) if constants.NOAA_SYNCA[j] != 0]
+        fifoLen = constants.NOAA_COLORCORRECT_FIFOLEN
+        # :358-366 two FIFOs of the last 10 000 samples seen under the low / high sync bits, read
+        # through their medians after every line with a real (not filled-in) sync.  All lines are
+        # known here, so a FIFO state is a window of one concatenated array: the full-length windows
+        # are equal-length rows of one ddm_row_medians call, the few partial ones at the start of the
+        # pass stay np.median (appending row by row and truncating each time == appending all,
+        # truncating once).
+        real_sync = set(ucsync)
+        upd = []
+        for li, (k, sA, eA, sB, eB) in enumerate(lines):
+            if pix.get((li, "A")) is None or pix.get((li, "B")) is None:
+                break                           # the loop below raises at this line
+            if csyncA[k] in real_sync:
+                upd.append(li)
+
+        def fifo_medians(rows_sel):
+            meds = _fifo_medians([sync_px[li][rows_sel].ravel() for li in upd], fifoLen, sig.device)
+            return dict(zip(upd, meds))
+        lowMed, highMed = fifo_medians(low_rows), fifo_medians(high_rows)
+
+        def median_small(vals):
+            """np.median of a short python list (the three-entry smoothing FIFOs)."""
+            for v in vals:
+                if v != v:
+                    return np.nan
+            s = sorted(vals)
+            m = len(s)
+            return float(s[m // 2]) if m % 2 else 0.5 * (s[m // 2 - 1] + s[m // 2])
         corrfifo, corrfifosig, corrfifosig2 = [], [], []
         ncorrfifo = 3
         lcorr = lcorrsig = None
         statecorr = 0
         valuesPixCorr, valuesSigCorr = [], []
         chidFifo1, chidFifo2 = [], []
-        fifoLen = constants.NOAA_COLORCORRECT_FIFOLEN
 
         def quantise(v):
             v = np.round(v)
@@ -226,22 +271,17 @@ class decode_noaa:
         for li, (k, sA, eA, sB, eB) in enumerate(lines):
             if pix.get((li, "A")) is None or pix.get((li, "B")) is None:
                 raise ValueError("cannot reshape array of size 0 into shape (%d,0)" % half)
-            if csyncA[k] in ucsync:
-                # :358-366 two FIFOs of the last 10 000 samples seen under the low / high sync bits
-                # (appending row by row and truncating each time == appending all, truncating once)
-                pxA = sync_px[li]
-                lowFifo = np.concatenate([lowFifo, pxA[low_rows].ravel()])[-fifoLen:]
-                highFifo = np.concatenate([highFifo, pxA[high_rows].ravel()])[-fifoLen:]
-                val11, val244 = np.median(lowFifo), np.median(highFifo)
+            if li in lowMed:
+                val11, val244 = lowMed[li], highMed[li]
                 self._low = val11 - (val244 - val11) * (11 - 0) / (244 - 11)
                 self._high = val11 - (val244 - val11) * (11 - 255) / (244 - 11)
             stripVal = stripA[li]
             corrfifo = (corrfifo + [255 * (stripVal - self._low) / (self._high - self._low)])[-ncorrfifo:]
-            outcorr = np.median(corrfifo)
+            outcorr = median_small(corrfifo)
             corrfifosig = (corrfifosig + [stripVal])[-ncorrfifo:]
-            outcorrsig = np.median(corrfifosig)
+            outcorrsig = median_small(corrfifosig)
             corrfifosig2 = (corrfifosig2 + [stripB[li]])[-ncorrfifo:]
-            outcorrsig2 = np.median(corrfifosig2)
+            outcorrsig2 = median_small(corrfifosig2)
             chidFifo1 = (chidFifo1 + [outcorrsig2])[-100:]
             chidFifo2 = (chidFifo2 + [outcorrsig])[-100:]
             # telemetry wedge tracker (:386-425): eight rising steps then a big drop = one frame

@@ -277,3 +277,19 @@ def test_device_group_scan_equals_sequential_scan():
     cor[::500] += 3.0
     got, _ = sync.pick_peaks(torch.from_numpy(cor).cuda(), fs, 40)
     assert np.array_equal(got, O.pick_sync_peaks(cor, fs, 40))
+
+
+def test_fifo_medians_equal_the_appending_loop():
+    """getImage reads two 10 000-sample FIFOs through their medians after every line
+    (decode_noaa.py:358-366); the batched form must equal the append-truncate-median loop."""
+    from directdemod_b200 import decode_noaa as dn
+    rng = np.random.default_rng(17)
+    fifo_len = 1000
+    chunks = [rng.standard_normal(int(k)).astype(np.float32).astype(np.float64) for k in rng.integers(1, 140, 60)]
+    chunks[7] = np.repeat(chunks[7][:1], 50)                       # ties
+    got = dn._fifo_medians(chunks, fifo_len, "cuda")
+    fifo = np.zeros(0)
+    for j, c in enumerate(chunks):
+        fifo = np.concatenate([fifo, c])[-fifo_len:]
+        assert got[j] == np.median(fifo), j
+    assert dn._fifo_medians([], fifo_len, "cuda").size == 0
