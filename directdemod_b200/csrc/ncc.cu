@@ -18,6 +18,7 @@
 // sequential group-maximum scan of :731-746 runs over that short list on the host, bit for bit.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -360,40 +361,68 @@ __global__ void compact_write_kernel(const double *__restrict__ x, long long n, 
 // of two loads per peak.  A noisy pass has millions of candidates; none of them leaves the device.
 constexpr int kWmThreads = 256;
 
-// F[j] = max(x[block start .. j]), B[j] = max(x[j .. block end]) for blocks of `w` samples
+// F[j] = max(x[block start .. j]), B[j] = max(x[j .. block end]) for blocks of `w` samples.
+// One CTA per block walks it in tiles of 256 consecutive samples (coalesced), left to right for F
+// and right to left for B: warp-shuffle inclusive max-scan, warp totals through shared memory, and a
+// running carry from the tiles before.
+__device__ __forceinline__ double shfl_up_f64(double v, int d) {
+    return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d),
+                            __shfl_up_sync(0xffffffffu, __double2loint(v), d));
+}
+__device__ __forceinline__ double shfl_down_f64(double v, int d) {
+    return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), d),
+                            __shfl_down_sync(0xffffffffu, __double2loint(v), d));
+}
+
 __global__ void __launch_bounds__(kWmThreads)
 winmax_blocks_kernel(const double *__restrict__ x, long long n, long long w, double *__restrict__ F,
                      double *__restrict__ B) {
-    __shared__ double pm[kWmThreads], sm[kWmThreads];
+    __shared__ double wt[kWmThreads / 32];
     const long long b0 = static_cast<long long>(blockIdx.x) * w;
     const long long b1 = b0 + w < n ? b0 + w : n;
-    const long long len = b1 - b0;
-    const long long per = (len + kWmThreads - 1) / kWmThreads;
-    const long long c0 = b0 + static_cast<long long>(threadIdx.x) * per;
-    const long long c1 = c0 + per < b1 ? c0 + per : b1;
-    double m = -INFINITY;
-    for (long long i = c0; i < c1; ++i) m = fmax(m, x[i]);
-    pm[threadIdx.x] = m;
-    sm[threadIdx.x] = m;
-    __syncthreads();
-    for (int off = 1; off < kWmThreads; off <<= 1) {
-        double a = -INFINITY, c = -INFINITY;
-        if (threadIdx.x >= off) a = pm[threadIdx.x - off];
-        if (threadIdx.x + off < kWmThreads) c = sm[threadIdx.x + off];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = kWmThreads / 32;
+    // prefix maxima
+    double carry = -INFINITY;
+    for (long long t0 = b0; t0 < b1; t0 += kWmThreads) {
+        const long long i = t0 + threadIdx.x;
+        double v = i < b1 ? x[i] : -INFINITY;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = shfl_up_f64(v, d);
+            if (lane >= d) v = fmax(v, o);
+        }
+        if (lane == 31) wt[wid] = v;
         __syncthreads();
-        pm[threadIdx.x] = fmax(pm[threadIdx.x], a);
-        sm[threadIdx.x] = fmax(sm[threadIdx.x], c);
+        double pre = carry;
+        for (int k = 0; k < wid; ++k) pre = fmax(pre, wt[k]);
+        double tot = carry;
+        for (int k = 0; k < NW; ++k) tot = fmax(tot, wt[k]);
+        v = fmax(v, pre);
+        if (i < b1) F[i] = v;
+        carry = tot;
         __syncthreads();
     }
-    double run = threadIdx.x > 0 ? pm[threadIdx.x - 1] : -INFINITY;
-    for (long long i = c0; i < c1; ++i) {
-        run = fmax(run, x[i]);
-        F[i] = run;
-    }
-    run = threadIdx.x + 1 < kWmThreads ? sm[threadIdx.x + 1] : -INFINITY;
-    for (long long i = c1 - 1; i >= c0; --i) {
-        run = fmax(run, x[i]);
-        B[i] = run;
+    // suffix maxima: tiles from the right end of the block
+    carry = -INFINITY;
+    for (long long t1 = b1; t1 > b0; t1 -= kWmThreads) {
+        const long long i = t1 - kWmThreads + threadIdx.x;          // may lie before b0 in the last tile
+        double v = i >= b0 ? x[i] : -INFINITY;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = shfl_down_f64(v, d);
+            if (lane + d < 32) v = fmax(v, o);
+        }
+        if (lane == 0) wt[wid] = v;
+        __syncthreads();
+        double post = carry;
+        for (int k = wid + 1; k < NW; ++k) post = fmax(post, wt[k]);
+        double tot = carry;
+        for (int k = 0; k < NW; ++k) tot = fmax(tot, wt[k]);
+        v = fmax(v, post);
+        if (i >= b0) B[i] = v;
+        carry = tot;
+        __syncthreads();
     }
 }
 
@@ -455,6 +484,42 @@ peak_flags_kernel(const double *__restrict__ x, const double *__restrict__ F, co
     if (threadIdx.x == 0) {
         first_cand[blockIdx.x] = sc[0];
         first_dom[blockIdx.x] = sd[0];
+    }
+}
+
+// The walk only ever needs the dominant candidates: a dominant index is a candidate, so "first
+// dominant >= first candidate >= q" is "first dominant >= q", and a candidate >= q exists exactly
+// when a dominant one does (the largest of them).  Hence peak[k+1] = first dominant >= peak[k] +
+// ceil(minPkDist), peak[0] = the first dominant -- and dominants are sparse (no two within a window
+// unless the values tie), so they are appended to a short list here, unordered, and sorted and walked
+// on the host.  The table kernels above remain the form for inputs with more than `cap` dominants
+// (long plateaus above the threshold).
+__global__ void __launch_bounds__(256)
+dominant_append_kernel(const double *__restrict__ x, const double *__restrict__ F, const double *__restrict__ B,
+                       long long n, long long w, double thr, long long *__restrict__ list, long long cap,
+                       unsigned long long *__restrict__ count) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const double v = x[i];
+        if (!(v > thr)) continue;
+        double mx = -HUGE_VAL;
+        const long long a = i + 1;
+        long long b = i + w;
+        if (b > n - 1) b = n - 1;
+        if (a <= b) {
+            const long long ba = a / w, bb = b / w;
+            if (ba != bb) {
+                mx = fmax(B[a], F[b]);
+            } else if (b == n - 1 || (b + 1) % w == 0) {
+                mx = B[a];
+            } else {
+                for (long long k = a; k <= b; ++k) mx = fmax(mx, x[k]);
+            }
+        }
+        if (!(mx > v)) {
+            const unsigned long long slot = atomicAdd(count, 1ULL);
+            if (slot < static_cast<unsigned long long>(cap)) list[slot] = i;
+        }
     }
 }
 
@@ -831,13 +896,57 @@ int ddm_pick_peaks(int device, const void *x_f64_dev, int64_t n, double threshol
     DevBuf F, B, nc, nd, fc, fd, out;
     if ((rc = F.alloc(device, 0, sizeof(double) * n)) != DDM_OK) return rc;
     if ((rc = B.alloc(device, 1, sizeof(double) * n)) != DDM_OK) return rc;
+    winmax_blocks_kernel<<<static_cast<unsigned>(wblocks), kWmThreads, 0, st>>>(x, n, w, static_cast<double *>(F.p),
+                                                                                static_cast<double *>(B.p));
+    count_launch();
+    // sparse path: the dominant candidates as a short unordered list, sorted and walked on the host
+    // (DDM_PEAKS_DENSE=1 forces the table path below: used by the tests to cross-check the two)
+    if (std::getenv("DDM_PEAKS_DENSE") == nullptr) {
+        const long long dcap = 1 << 20;
+        if ((rc = out.alloc(device, 6, sizeof(long long) * (dcap + 1))) != DDM_OK) return rc;
+        long long *list = static_cast<long long *>(out.p);
+        DDM_CUDA(cudaMemsetAsync(list, 0, sizeof(long long), st));
+        dominant_append_kernel<<<static_cast<unsigned>(sm_count(device)) * 8, 256, 0, st>>>(
+            x, static_cast<const double *>(F.p), static_cast<const double *>(B.p), n, w, threshold, list + 1, dcap,
+            reinterpret_cast<unsigned long long *>(list));
+        count_launch();
+        DDM_CUDA(cudaGetLastError());
+        long long nd_found = 0;
+        DDM_CUDA(cudaMemcpyAsync(&nd_found, list, sizeof(nd_found), cudaMemcpyDeviceToHost, st));
+        DDM_CUDA(cudaStreamSynchronize(st));
+        if (nd_found <= dcap) {
+            std::vector<long long> dom(static_cast<size_t>(nd_found));
+            if (nd_found > 0) {
+                DDM_CUDA(cudaMemcpyAsync(dom.data(), list + 1, sizeof(long long) * nd_found, cudaMemcpyDeviceToHost, st));
+                DDM_CUDA(cudaStreamSynchronize(st));
+            }
+            std::sort(dom.begin(), dom.end());
+            long long np = 0;
+            auto it = dom.begin();
+            while (it != dom.end()) {
+                if (np < capacity) {
+                    DDM_REQUIRE(peaks_host != nullptr, "ddm_pick_peaks: NULL output");
+                    peaks_host[np] = *it;
+                }
+                ++np;
+                const long long p = *it + close_dist;
+                if (p >= n) break;
+                it = std::lower_bound(it, dom.end(), p);
+            }
+            *n_peaks = np;
+            if (np > capacity) {
+                set_error("ddm_pick_peaks: %lld peaks, capacity %lld", np, static_cast<long long>(capacity));
+                return DDM_ERR_CAPACITY;
+            }
+            return DDM_OK;
+        }
+    }
+    // dense path (more than 2^20 dominant candidates: plateaus): next-index tables and a device walk
     if ((rc = nc.alloc(device, 2, sizeof(long long) * n)) != DDM_OK) return rc;
     if ((rc = nd.alloc(device, 3, sizeof(long long) * n)) != DDM_OK) return rc;
     if ((rc = fc.alloc(device, 4, sizeof(long long) * nblk)) != DDM_OK) return rc;
     if ((rc = fd.alloc(device, 5, sizeof(long long) * nblk)) != DDM_OK) return rc;
     if ((rc = out.alloc(device, 6, sizeof(long long) * (capacity + 1))) != DDM_OK) return rc;
-    winmax_blocks_kernel<<<static_cast<unsigned>(wblocks), kWmThreads, 0, st>>>(x, n, w, static_cast<double *>(F.p),
-                                                                                static_cast<double *>(B.p));
     peak_flags_kernel<<<static_cast<unsigned>(nblk), kFlagBlock, 0, st>>>(
         x, static_cast<const double *>(F.p), static_cast<const double *>(B.p), n, w, threshold,
         static_cast<long long *>(nc.p), static_cast<long long *>(nd.p), static_cast<long long *>(fc.p),
@@ -847,7 +956,7 @@ int ddm_pick_peaks(int device, const void *x_f64_dev, int64_t n, double threshol
     peak_walk_kernel<<<1, 1, 0, st>>>(static_cast<const long long *>(nc.p), static_cast<const long long *>(nd.p),
                                      static_cast<const long long *>(fc.p), static_cast<const long long *>(fd.p), n, nblk,
                                      close_dist, peaks_dev + 1, capacity, peaks_dev);
-    count_launch(4);
+    count_launch(3);
     DDM_CUDA(cudaGetLastError());
     long long cnt = 0;
     DDM_CUDA(cudaMemcpyAsync(&cnt, peaks_dev, sizeof(cnt), cudaMemcpyDeviceToHost, st));

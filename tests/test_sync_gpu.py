@@ -1,6 +1,8 @@
 """GPU parity of the sync path: normalised correlation, threshold selection, peak picking,
 decode_noaa.getCrudeSync / getAccurateSync (positions bit-exact), and the AFSK correlator bank."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -262,6 +264,16 @@ def test_device_group_scan_equals_sequential_scan():
         cnt = C.c_int64()
         _lib.check(l.ddm_pick_peaks(0, _dev.ptr(xd), n, thr, dist, got.ctypes.data_as(C.POINTER(C.c_int64)), n,
                                     C.byref(cnt), _dev.stream_ptr(0)), "ddm_pick_peaks")
+        # the same through the table walk kept for inputs with more than 2^20 dominant candidates
+        got2 = np.empty(n, dtype=np.int64)
+        cnt2 = C.c_int64()
+        os.environ["DDM_PEAKS_DENSE"] = "1"
+        try:
+            _lib.check(l.ddm_pick_peaks(0, _dev.ptr(xd), n, thr, dist, got2.ctypes.data_as(C.POINTER(C.c_int64)), n,
+                                        C.byref(cnt2), _dev.stream_ptr(0)), "ddm_pick_peaks")
+        finally:
+            del os.environ["DDM_PEAKS_DENSE"]
+        assert cnt2.value == cnt.value and np.array_equal(got[:cnt.value], got2[:cnt.value]), trial
         # sequential reference scan over the candidate list
         cand = np.argwhere(x > thr).ravel().astype(np.int64)
         want = np.empty(len(cand), dtype=np.int64)
