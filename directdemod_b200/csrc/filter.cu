@@ -591,7 +591,9 @@ fir_fft_kernel(const typename FirTraits<CPLX>::T *__restrict__ x, typename FirTr
 // unit circle) is run by a single thread sequentially.  No inter-thread communication.
 constexpr int kIirThreads = 64;
 constexpr int kIirMaxOrder = 16;
-constexpr int kIirBlock = 16;                          // samples per register-staged block
+constexpr int kIirBlock = 16;                          // samples per register-staged block (iir_kernel)
+constexpr int kIirRowBytes = 256;                      // bytes per row and step of the staged kernel
+constexpr int kIirAlign = 64;                          // L and W are multiples of this many samples
 
 struct IirCoef {
     double b[kIirMaxOrder + 1];
@@ -845,7 +847,8 @@ struct IirScalar<double2> { using T = double; };
 // samples per segment for the same number of threads, which halves the warm-up overhead of
 // chunk-sized signals.
 template <int P, bool SPLIT, typename SI, typename SO>
-__global__ void __launch_bounds__(kIirThreads, SPLIT ? (P > 12 ? 5 : (P > 8 ? 8 : 10)) : (P > 12 ? 4 : (P > 8 ? 6 : 8)))
+__global__ void __launch_bounds__(kIirThreads, SPLIT ? (P > 12 ? 5 : (P > 8 ? 8 : 10))
+                                                    : (P > 12 ? 4 : (P > 8 || sizeof(SI) >= 8 ? 6 : 8)))
 iir_warp_kernel(const IirParams prm) {
     constexpr bool CPLX = std::is_same<SI, float2>::value || std::is_same<SI, double2>::value;
     static_assert(CPLX || !SPLIT, "only complex signals split into two recursions");
@@ -854,8 +857,11 @@ iir_warp_kernel(const IirParams prm) {
     using YS = typename std::conditional<SPLIT, typename IirScalar<SO>::T, SO>::type;
     using V = typename std::conditional<SPLIT, double, typename IirV<CPLX>::V>::type;
     constexpr int ROWS = SPLIT ? 16 : 32;                   // segments per warp
-    constexpr int BI = 128 / sizeof(SI) > kIirBlock ? kIirBlock : 128 / sizeof(SI);
-    constexpr int BO = 128 / sizeof(SO) > kIirBlock ? kIirBlock : 128 / sizeof(SO);
+    // 256-byte rows for complex samples (DRAM sees 57 k concurrent streams: longer bursts per stream
+    // measured 3.91 -> 3.75 ms), 128-byte rows for real ones (longer rows measured slower there)
+    constexpr int kRow = sizeof(SI) >= 8 ? kIirRowBytes : kIirRowBytes / 2;
+    constexpr int BI = kRow / sizeof(SI) > kIirAlign ? kIirAlign : kRow / sizeof(SI);
+    constexpr int BO = kRow / sizeof(SO) > kIirAlign ? kIirAlign : kRow / sizeof(SO);
     constexpr int B = BI < BO ? BI : BO;                    // samples per row and step
     constexpr int PI = B * sizeof(SI) / 16, PO = B * sizeof(SO) / 16;      // 16-byte pieces per row
     constexpr int RI = PI + 1, RO = PO + 1;                 // padded row lengths (in pieces)
@@ -863,8 +869,13 @@ iir_warp_kernel(const IirParams prm) {
     constexpr int NI = ROWS * PI / 32, NO = ROWS * PO / 32; // copy instructions per lane and step
     constexpr int CI = sizeof(SI) / sizeof(XS);             // scalars per sample (2 when SPLIT)
     constexpr int kWarps = kIirThreads / 32;
-    __shared__ uint4 s_in[kWarps][2][ROWS * RI];
-    __shared__ uint4 s_out[kWarps][ROWS * RO];
+    // Two-stage input ring (a third stage, two steps in flight, measured no faster: 3.91 -> 4.04 ms).
+    // Outputs of the same sample size overwrite the input row they were computed from, so longer
+    // rows cost no more shared memory than a separate output buffer did.
+    constexpr int NS = 2;
+    constexpr bool ALIAS = sizeof(SO) == sizeof(SI);
+    __shared__ uint4 s_in[kWarps][NS][ROWS * RI];
+    __shared__ uint4 s_out[kWarps][ALIAS ? 1 : ROWS * RO];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = SPLIT ? lane >> 1 : lane, half = SPLIT ? lane & 1 : 0;
@@ -909,13 +920,13 @@ iir_warp_kernel(const IirParams prm) {
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const long long steps = (W + L) / B;                    // L, W are multiples of kIirBlock >= B
+    const long long steps = (W + L) / B;                    // L, W are multiples of kIirAlign >= B
     const long long warm_steps = W / B;
     long long p0 = seg0 * L - W;
     copy_in(p0, 0);
+    int stage = 0;
 #pragma unroll 1
-    for (long long t = 0; t < steps; ++t, p0 += B) {
-        const int stage = static_cast<int>(t & 1);
+    for (long long t = 0; t < steps; ++t, p0 += B, stage ^= 1) {
         if (t + 1 < steps) {
             copy_in(p0 + B, stage ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -928,8 +939,8 @@ iir_warp_kernel(const IirParams prm) {
         if (pos < 0 || left < 0) left = 0;
         const int cnt = left < B ? static_cast<int>(left) : B;
         const bool warm = t < warm_steps;
-        const uint4 *my_in = &s_in[warp][stage][row * RI];
-        YS *my_out = reinterpret_cast<YS *>(&s_out[warp][row * RO]) + half;
+        uint4 *my_in = &s_in[warp][stage][row * RI];
+        YS *my_out = reinterpret_cast<YS *>(ALIAS ? my_in : &s_out[warp][row * RO]) + half;
         // rows with a whole block compute; rows that have not reached position 0 yet or are past
         // the end of their segment sit the step out; a partial block (once per launch, at the end of
         // the signal) sends the warp through the scalar form
@@ -954,7 +965,8 @@ iir_warp_kernel(const IirParams prm) {
             if (!warm) {
                 __syncwarp();
                 SO *dst = y + p0 + out_off;
-                const uint4 *so = &s_out[warp][(lane / PO) * RO + lane % PO];
+                const uint4 *so = ALIAS ? &s_in[warp][stage][(lane / PO) * RO + lane % PO]
+                                        : &s_out[warp][(lane / PO) * RO + lane % PO];
 #pragma unroll
                 for (int i = 0; i < NO; ++i) {
                     // interior warps: every row holds a whole block in every output step
@@ -1464,12 +1476,12 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
         if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));
         while (wps > 1 && (n + base * wps - 1) / (base * wps) < 2 * W) --wps;
         L = (n + base * wps - 1) / (base * wps);
-        if (L < 4 * kIirBlock) L = 4 * kIirBlock;
+        if (L < 4 * kIirAlign) L = 4 * kIirAlign;
         prm.W = W;
     }
-    L = (L + kIirBlock - 1) / kIirBlock * kIirBlock;
+    L = (L + kIirAlign - 1) / kIirAlign * kIirAlign;
     prm.L = L;
-    prm.W = (prm.W + kIirBlock - 1) / kIirBlock * kIirBlock;
+    prm.W = (prm.W + kIirAlign - 1) / kIirAlign * kIirAlign;
     const long long segs = (n + L - 1) / L;
     unsigned grid = static_cast<unsigned>((segs + kIirThreads - 1) / kIirThreads);
     if (staged) {
