@@ -573,7 +573,7 @@ def test_parallel_iir_ragged_lengths_and_chunk_carry(cplx):
 
 
 def test_c4_filters_at_slab_scale_chunk_invariance_and_windows():
-    """BASELINE config 4 at a size where the production code paths run (400 M cf32 samples: the
+    """BASELINE config 4 at a size where the production code paths run (480 M cf32 samples: the
     persistent overlap-save FIR; the warp-staged IIR with one complex recursion per lane, which small
     inputs never reach).  Size-independent properties: the whole slab in one call equals the same slab
     in 20 M-sample chunks with carried state (those take the lane-split IIR kernel), and windows of the
@@ -581,7 +581,7 @@ def test_c4_filters_at_slab_scale_chunk_invariance_and_windows():
     import scipy.signal as sps
     import torch
     chunker, comm, constants, demod_fm, filters = _mods()
-    n, chunk = 400_000_000, 20_000_000
+    n, chunk = 480_000_000, 20_000_000        # well above the size where the IIR stops splitting re/im
     g = torch.Generator(device="cuda")
     g.manual_seed(5)
     x = torch.empty(n, dtype=torch.complex64, device="cuda")
@@ -640,3 +640,26 @@ def test_constructor_snapshot_of_large_host_arrays():
     assert sr.signal.dtype == np.float32 and np.array_equal(sr.signal, xr)
     with pytest.raises(TypeError):
         comm.commSignal(48000, np.zeros((70000, 2), dtype=np.float32))
+
+
+def test_zero_phase_iir_on_complex_and_float64_inputs():
+    """filtfilt through the segment-parallel IIR for the sample formats the golden fixtures do not
+    cover: complex input (float2 -> double2 forward pass, double2 -> double2 backward pass) and a
+    well-conditioned low-pass, against scipy.signal.filtfilt."""
+    import scipy.signal as sps
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(33)
+    n = 300000
+    xc = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 10).astype(np.complex64)
+    xr = rng.standard_normal(n).astype(np.float32)
+    for make in (lambda **kw: filters.butter(2400000, 100000, n=8, **kw), lambda **kw: filters.butter(20800, 1200, **kw)):
+        f = make(zeroPhase=True)
+        b, a = np.asarray(f.getB, dtype=np.float64), np.asarray(f.getA, dtype=np.float64)
+        for x in (xc, xr):
+            want = sps.filtfilt(b, a, x.astype(np.complex128 if np.iscomplexobj(x) else np.float64))
+            got = make(zeroPhase=True).applyOn(x)
+            assert got.shape == want.shape and np.iscomplexobj(got) == np.iscomplexobj(want)
+            assert O.rel_rms(got, want) <= TOL, O.rel_rms(got, want)
+        # stateless lfilter on complex input
+        want = sps.lfilter(b, a, xc.astype(np.complex128))
+        assert O.rel_rms(make(storeState=False).applyOn(xc), want) <= TOL
