@@ -229,7 +229,9 @@ int ddm_group_peaks(const int64_t *idx, const double *val, int64_t count, double
 /* decode_noaa.py:723-746 in one call, on the device: candidates x > threshold, group-maximum scan
  * with groups closed at distance >= min_dist from the running maximum (strict '<': the first of
  * equal maxima wins).  Equals ddm_compact_above + ddm_group_peaks, but no candidate leaves the
- * device (a noisy pass has millions).  peaks_host receives the ascending peak indices. */
+ * device (a noisy pass has millions): only the "dominant" candidates -- those no later sample within
+ * the window exceeds, a few thousand -- are listed, and the walk over them runs on the host.
+ * peaks_host receives the ascending peak indices. */
 int ddm_pick_peaks(int device, const void *x_f64_dev, int64_t n, double threshold, double min_dist,
                    int64_t *peaks_host, int64_t capacity, int64_t *n_peaks, void *stream);
 /* decode_afsk1200.py:106-142: four nbuf-tap correlators over a real signal (taps4_host =
