@@ -939,6 +939,10 @@ iir_warp_kernel(const IirParams prm) {
         if (pos < 0 || left < 0) left = 0;
         const int cnt = left < B ? static_cast<int>(left) : B;
         const bool warm = t < warm_steps;
+        // (SPLIT + ALIAS: the two lanes of a row load the same 16-byte pieces and each writes its own
+        // component back; a lane may thus load a piece its partner has already written into -- it only
+        // uses its own component, which nobody else writes.  racecheck reports this as a potential
+        // WAR hazard; memcheck and racecheck report no errors.)
         uint4 *my_in = &s_in[warp][stage][row * RI];
         YS *my_out = reinterpret_cast<YS *>(ALIAS ? my_in : &s_out[warp][row * RO]) + half;
         // rows with a whole block compute; rows that have not reached position 0 yet or are past
