@@ -212,130 +212,20 @@ constexpr int kFftFirN = 4096;
 constexpr int kFftFirThreads = 256;
 constexpr int kFftFirMaxTaps = 2049;       // keeps at least half of every block valid
 
-__device__ __forceinline__ float2 cf_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 cf_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cf_mul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-// multiply by -i (forward, DIR > 0) or +i (inverse)
-template <int DIR>
-__device__ __forceinline__ float2 cf_mul_mi(float2 a) {
-    return DIR > 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
-}
-// twiddle from the forward table, conjugated for the inverse transform
-template <int DIR>
-__device__ __forceinline__ float2 cf_tw(float2 a, float2 w) {
-    if (DIR < 0) w.y = -w.y;
-    return cf_mul(a, w);
-}
-
-template <int DIR>
-__device__ __forceinline__ void cf_dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3) {
-    const float2 a0 = cf_add(v0, v2), a1 = cf_sub(v0, v2);
-    const float2 a2 = cf_add(v1, v3), a3 = cf_mul_mi<DIR>(cf_sub(v1, v3));
-    v0 = cf_add(a0, a2);
-    v1 = cf_add(a1, a3);
-    v2 = cf_sub(a0, a2);
-    v3 = cf_sub(a1, a3);
-}
-
-// 16-point DFT in registers: 4 x 4 Cooley-Tukey, input n = 4 n1 + n2, output k = k1 + 4 k2
-template <int DIR>
-__device__ __forceinline__ void cf_dft16(float2 (&v)[16]) {
-    // exp(-2 pi i m / 16), m = 0..9 (largest n2 k1 = 3 * 3)
-    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
-    const float2 w[10] = {{1.f, 0.f}, {c1, -s1}, {h, -h}, {s1, -c1}, {0.f, -1.f},
-                          {-s1, -c1}, {-h, -h}, {-c1, -s1}, {-1.f, 0.f}, {-c1, s1}};
-    float2 a[4][4];
-#pragma unroll
-    for (int n2 = 0; n2 < 4; ++n2) {
-        float2 c0 = v[n2], c1v = v[4 + n2], c2 = v[8 + n2], c3 = v[12 + n2];
-        cf_dft4<DIR>(c0, c1v, c2, c3);
-        a[0][n2] = c0;
-        a[1][n2] = n2 ? cf_tw<DIR>(c1v, w[n2]) : c1v;
-        a[2][n2] = n2 ? cf_tw<DIR>(c2, w[2 * n2]) : c2;
-        a[3][n2] = n2 ? cf_tw<DIR>(c3, w[3 * n2]) : c3;
-    }
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1) {
-        float2 r0 = a[k1][0], r1 = a[k1][1], r2 = a[k1][2], r3 = a[k1][3];
-        cf_dft4<DIR>(r0, r1, r2, r3);
-        v[k1] = r0;
-        v[k1 + 4] = r1;
-        v[k1 + 8] = r2;
-        v[k1 + 12] = r3;
-    }
-}
-
 // padded index into the exchange buffer: one float2 of padding per 16 keeps the stride-16
 // accesses of the passes conflict free
 __device__ __forceinline__ int fftfir_idx(int i) { return i + (i >> 4); }
 
-// 4096-point transform of the 16 values per thread.  In: v[r] = element (j + 256 r); out: v[r] =
-// bin (j + 256 r).  (Stockham autosort: pass Ns = 1, 16, 256; after the last pass the natural
-// output index of (j, r) is again j + 256 r, so nothing has to go back through shared memory.)
-// v[r] *= w^r, r = 1..15, w = tw[t0]: four table loads (w, w^2, w^4, w^8), the other powers by at
-// most three multiplications each -- a quarter of the load instructions of reading all fifteen
-template <int DIR>
-__device__ __forceinline__ void fftfir_twiddle(float2 (&v)[16], const float2 *__restrict__ tw, int t0) {
-    float2 w1 = __ldg(&tw[t0]), w2 = __ldg(&tw[2 * t0]), w4 = __ldg(&tw[4 * t0]), w8 = __ldg(&tw[8 * t0]);
-    if (DIR < 0) {
-        w1.y = -w1.y;
-        w2.y = -w2.y;
-        w4.y = -w4.y;
-        w8.y = -w8.y;
-    }
-    const float2 w3 = cf_mul(w2, w1), w5 = cf_mul(w4, w1), w6 = cf_mul(w4, w2), w7 = cf_mul(w4, w3);
-    v[1] = cf_mul(v[1], w1);
-    v[2] = cf_mul(v[2], w2);
-    v[3] = cf_mul(v[3], w3);
-    v[4] = cf_mul(v[4], w4);
-    v[5] = cf_mul(v[5], w5);
-    v[6] = cf_mul(v[6], w6);
-    v[7] = cf_mul(v[7], w7);
-    v[8] = cf_mul(v[8], w8);
-    v[9] = cf_mul(v[9], cf_mul(w8, w1));
-    v[10] = cf_mul(v[10], cf_mul(w8, w2));
-    v[11] = cf_mul(v[11], cf_mul(w8, w3));
-    v[12] = cf_mul(v[12], cf_mul(w8, w4));
-    v[13] = cf_mul(v[13], cf_mul(w8, w5));
-    v[14] = cf_mul(v[14], cf_mul(w8, w6));
-    v[15] = cf_mul(v[15], cf_mul(w8, w7));
-}
-
-template <int DIR>
-__device__ __forceinline__ void fftfir_4096(float2 (&v)[16], float2 *buf, const float2 *__restrict__ tw, int j) {
-    // pass Ns = 1 (no twiddles): out[16 j + r]
-    cf_dft16<DIR>(v);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) buf[fftfir_idx(16 * j + r)] = v[r];
-    __syncthreads();
-    // pass Ns = 16: in[j + 256 r], twiddle exp(-2 pi i k r / 256) = tw[16 k r], out[(j - k) 16 + k + 16 r]
-    {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = buf[fftfir_idx(j + 256 * r)];
-        const int k = j & 15;
-        fftfir_twiddle<DIR>(v, tw, 16 * k);
-        cf_dft16<DIR>(v);
-        __syncthreads();
-        const int base = (j - k) * 16 + k;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) buf[fftfir_idx(base + 16 * r)] = v[r];
-        __syncthreads();
-    }
-    // pass Ns = 256: in[j + 256 r], k = j, twiddle exp(-2 pi i j r / 4096) = tw[j r], out index j + 256 r
-#pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = buf[fftfir_idx(j + 256 * r)];
-    fftfir_twiddle<DIR>(v, tw, j);
-    cf_dft16<DIR>(v);
-    __syncthreads();          // buf is reused by the next transform
-}
+// The transform (pkfft_4096 below): 16 values per thread, in: v[r] = element (j + 256 r); out: v[r] =
+// bin (j + 256 r).  Stockham autosort, passes Ns = 1, 16, 256; after the last pass the natural
+// output index of (j, r) is again j + 256 r, so nothing has to go back through shared memory.
 
 // ---- packed single precision (Blackwell FADD2 / FMUL2 / FFMA2) ---------------------------------
 // A complex value is one 64-bit register pair (re low, im high): an addition is one FADD2 and a
 // multiplication by w is FMUL2(a, (wr, wr)) + FFMA2(swap(a), (-wi, wi)) -- ptxas folds the swap into
 // the operand's LO_HI selector and the broadcast into .F32 -- so a transform issues half the
-// instructions of the scalar form above (the kernel is issue/latency-bound, not FLOP-bound).
+// instructions of a scalar formulation (1241 instead of 2064 per block and warp; the kernel is
+// issue/latency-bound, not FLOP-bound).
 typedef unsigned long long cpk;
 
 __device__ __forceinline__ cpk fsub2(cpk a, cpk b) {
@@ -369,7 +259,7 @@ __device__ __forceinline__ void pk_dft4(cpk &v0, cpk &v1, cpk &v2, cpk &v3) {
     v3 = ffma2(d, sm, a1);
 }
 
-// 16-point DFT in registers, same index maps as cf_dft16
+// 16-point DFT in registers: 4 x 4 Cooley-Tukey, input n = 4 n1 + n2, output k = k1 + 4 k2
 template <int DIR>
 __device__ __forceinline__ void pk_dft16(cpk (&v)[16]) {
     constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
@@ -439,7 +329,7 @@ __device__ __forceinline__ void pk_twiddle(cpk (&v)[16], const float2 *T) {
 // consecutive entries: T3[p][j] = tw[j 2^p] (j < 256), T2[p][k] = tw[16 k 2^p] (k < 16)
 constexpr int kFftFirT3 = 4 * 256, kFftFirT2 = 4 * 16;
 
-// the 4096-point transform of fftfir_4096 on packed values
+// the 4096-point transform on packed values
 template <int DIR>
 __device__ __forceinline__ void pkfft_4096(cpk (&v)[16], cpk *buf, const float2 *T3, const float2 *T2, int j) {
     pk_dft16<DIR>(v);
