@@ -407,6 +407,7 @@ struct GenericParams {
     const void *halo;
     double2 *y;            // y[m+1] for m = -1..M-1
     const double *taps;    // K taps
+    const double2 *ctaps;  // K taps times exp(+j 2 pi r k) (mixer folded in), nullptr without mixer
     long long n, n0, M, off;
     long long virt_before; // chunk-relative index below which history is virtual: the mixed value
                            // is 1.0 there (the all-ones history behind lfilter_zi, filters.py:45)
@@ -423,6 +424,23 @@ __device__ __forceinline__ float2 chain_fetch(const void *x, const void *halo, i
     return i >= 0 ? static_cast<const float2 *>(x)[i] : static_cast<const float2 *>(halo)[H + i];
 }
 
+// exp(-j 2 pi r g) in float64 (the general path rotates float64 sums)
+__device__ __forceinline__ double2 phase_rotator_f64(double r_hi, double r_lo, long long g) {
+    const double gd = static_cast<double>(g);
+    const double p = r_hi * gd;
+    const double e = fma(r_hi, gd, -p);
+    double fr = p - rint(p);
+    fr += e + r_lo * gd;
+    double s, c;
+    sincospi(2.0 * fr, &s, &c);
+    return make_double2(c, -s);
+}
+
+// The mixer commutes into the taps: x'[pos-k] = x[pos-k] rot(n0+pos) exp(+j 2 pi r k), so
+//   y[m] = rot(n0 + pos) * sum_k (taps[k] exp(+j 2 pi r k)) x[pos-k]
+// with complex taps precomputed in float64 on the host and ONE rotator per output (the first version
+// evaluated a double-double reduced sincos per tap and sample: 151 per output at 151 taps).  Virtual
+// history (mixed value 1.0) is summed separately and added after the rotation.
 static __global__ void chain_generic_y_kernel(const GenericParams P) {
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx > P.M) return;
@@ -430,22 +448,33 @@ static __global__ void chain_generic_y_kernel(const GenericParams P) {
     const long long pos = P.off + m * P.D;          // chunk coordinates, may be negative
     // fp64 accumulation: at D = 1 consecutive outputs differ by a tiny rotation, so the
     // discriminator needs more than fp32's ~1e-7 rad floor to stay within 1e-5 relative
-    double ax = 0.0, ay = 0.0;
+    double ax = 0.0, ay = 0.0, vr = 0.0;
     for (int k = 0; k < P.K; ++k) {
         const long long i = pos - k;
         if (i < -static_cast<long long>(P.H)) break;
-        float2 v;
         if (i < P.virt_before) {
-            v = make_float2(1.f, 0.f);
-        } else {
-            v = chain_fetch(P.x, P.halo, P.H, i, P.in_format);
-            if (P.mix) v = cmul(v, phase_rotator(P.r_hi, P.r_lo, P.n0 + i));
+            vr += P.taps[k];
+            continue;
         }
-        const double t = P.taps[k];
-        ax = fma(t, static_cast<double>(v.x), ax);
-        ay = fma(t, static_cast<double>(v.y), ay);
+        const float2 v = chain_fetch(P.x, P.halo, P.H, i, P.in_format);
+        const double vx = static_cast<double>(v.x), vy = static_cast<double>(v.y);
+        if (P.mix) {
+            const double2 c = P.ctaps[k];
+            ax = fma(c.x, vx, fma(-c.y, vy, ax));
+            ay = fma(c.x, vy, fma(c.y, vx, ay));
+        } else {
+            const double t = P.taps[k];
+            ax = fma(t, vx, ax);
+            ay = fma(t, vy, ay);
+        }
     }
-    P.y[idx] = make_double2(ax, ay);
+    if (P.mix) {
+        const double2 w = phase_rotator_f64(P.r_hi, P.r_lo, P.n0 + pos);
+        const double rx = fma(w.x, ax, -w.y * ay), ry = fma(w.x, ay, w.y * ax);
+        ax = rx;
+        ay = ry;
+    }
+    P.y[idx] = make_double2(ax + vr, ay);
 }
 
 static __global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
@@ -483,6 +512,7 @@ struct ddm_chain {
     int per_sm[2] = {0, 0};                  // resident CTAs per SM of the fused kernel, per s
     float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
     double *d_taps_lin = nullptr;            // K
+    double2 *d_ctaps = nullptr;              // K: taps[k] exp(+j 2 pi r k), general path with mixer
     float2 *d_rot = nullptr;                 // DP
     void *d_halo[2] = {nullptr, nullptr};    // H samples of raw input in the handle's input format
     void *d_halo_init = nullptr;             // the reference's initial condition as raw history (cf32)
@@ -703,6 +733,23 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
             return fail(DDM_ERR_CUDA);
         }
     }
+    if (c->mix) {
+        // complex taps of the general path (chain_generic_y_kernel), phases in long double
+        std::vector<double2> ct(K);
+        const long double r = static_cast<long double>(freq_offset) / static_cast<long double>(samp_rate);
+        for (int k = 0; k < K; ++k) {
+            long double ph = r * k;
+            ph -= std::floor(ph);
+            const long double ang = 2.0L * 3.14159265358979323846264338327950288L * ph;
+            ct[k] = make_double2(static_cast<double>(taps[k] * std::cos(ang)), static_cast<double>(taps[k] * std::sin(ang)));
+        }
+        e = pool_alloc_t(&c->d_ctaps, sizeof(double2) * K);
+        if (e == cudaSuccess) e = cudaMemcpy(c->d_ctaps, ct.data(), sizeof(double2) * K, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("tap upload failed: %s", cudaGetErrorString(e));
+            return fail(DDM_ERR_CUDA);
+        }
+    }
     if (c->fast) {
         for (int s = 0; s < 2; ++s) {
             const int Q = (K + s + D - 1) / D;
@@ -763,6 +810,7 @@ int ddm_chain_destroy(ddm_chain *c) {
     }
     pool_free(c->d_halo_init);
     pool_free(c->d_taps_lin);
+    pool_free(c->d_ctaps);
     pool_free(c->d_rot);
     cudaFree(c->d_ytmp);
     cudaFree(c->d_in);
@@ -996,6 +1044,7 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             g.halo = c->d_halo[c->cur];
             g.y = c->d_ytmp;
             g.taps = c->d_taps_lin;
+            g.ctaps = c->d_ctaps;
             g.n = n;
             g.n0 = c->n0;
             g.M = M;
