@@ -477,6 +477,66 @@ static __global__ void chain_generic_y_kernel(const GenericParams P) {
     P.y[idx] = make_double2(ax + vr, ay);
 }
 
+// Tiled form of chain_generic_y_kernel for launches without virtual history: a CTA produces 128
+// consecutive outputs from one staged tile of 127 D + K input samples, converted to float64 once
+// (the per-thread form converts every sample K / D times, and F2F shares the FP64 pipe with the
+// DFMAs) and stored transposed -- sample s' of the tile at [s' mod D][s' div D] -- so that the 32
+// lanes of a warp, whose samples are D apart, read consecutive shared-memory words.
+constexpr int kGenTile = 128;
+
+static __global__ void __launch_bounds__(kGenTile)
+chain_generic_tile_kernel(const GenericParams P, int row_len) {
+    extern __shared__ double2 s_tile[];                  // [D][row_len]
+    const int j = threadIdx.x;
+    const long long idx0 = static_cast<long long>(blockIdx.x) * kGenTile;
+    const int D = P.D, K = P.K;
+    const long long lo = P.off + (idx0 - 1) * D - (K - 1);          // chunk coordinate of tile sample 0
+    const int count = (kGenTile - 1) * D + K;
+    for (int sp = j; sp < count; sp += kGenTile) {
+        const long long i = lo + sp;
+        double2 v = make_double2(0.0, 0.0);
+        if (i >= -static_cast<long long>(P.H) && i < P.n) {
+            const float2 f = chain_fetch(P.x, P.halo, P.H, i, P.in_format);
+            v = make_double2(static_cast<double>(f.x), static_cast<double>(f.y));
+        }
+        s_tile[(sp % D) * row_len + sp / D] = v;
+    }
+    __syncthreads();
+    const long long idx = idx0 + j;
+    if (idx > P.M) return;
+    // sample of tap k: s' = j D + e, e = K - 1 - k  ->  row e mod D, column j + e div D
+    int r = (K - 1) % D, a = (K - 1) / D;
+    double ax = 0.0, ay = 0.0;
+    if (P.mix) {
+        for (int k = 0; k < K; ++k) {
+            const double2 v = s_tile[r * row_len + j + a];
+            const double2 c = P.ctaps[k];
+            ax = fma(c.x, v.x, fma(-c.y, v.y, ax));
+            ay = fma(c.x, v.y, fma(c.y, v.x, ay));
+            if (--r < 0) {
+                r = D - 1;
+                --a;
+            }
+        }
+        const double2 w = phase_rotator_f64(P.r_hi, P.r_lo, P.n0 + P.off + (idx - 1) * D);
+        const double rx = fma(w.x, ax, -w.y * ay), ry = fma(w.x, ay, w.y * ax);
+        ax = rx;
+        ay = ry;
+    } else {
+        for (int k = 0; k < K; ++k) {
+            const double2 v = s_tile[r * row_len + j + a];
+            const double t = P.taps[k];
+            ax = fma(t, v.x, ax);
+            ay = fma(t, v.y, ay);
+            if (--r < 0) {
+                r = D - 1;
+                --a;
+            }
+        }
+    }
+    P.y[idx] = make_double2(ax, ay);
+}
+
 static __global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
                                          int out_mode) {
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -1058,7 +1118,17 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             g.in_format = c->in_format;
             g.virt_before = c->in_format == DDM_IN_CU8 ? -c->n_real : -static_cast<long long>(c->H) - 1;
             const int tb = 128;
-            chain_generic_y_kernel<<<static_cast<unsigned>((M + 1 + tb - 1) / tb), tb, 0, st>>>(g);
+            const int row_len = kGenTile + (c->K - 1) / D + 1;
+            const size_t tile_bytes = sizeof(double2) * static_cast<size_t>(D) * row_len;
+            const bool has_virtual = c->in_format == DDM_IN_CU8 && c->n_real < c->H;
+            if (!has_virtual && tile_bytes <= 200 * 1024) {
+                DDM_CUDA(cudaFuncSetAttribute(chain_generic_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(tile_bytes)));
+                chain_generic_tile_kernel<<<static_cast<unsigned>((M + 1 + kGenTile - 1) / kGenTile), kGenTile,
+                                            tile_bytes, st>>>(g, row_len);
+            } else {
+                chain_generic_y_kernel<<<static_cast<unsigned>((M + 1 + tb - 1) / tb), tb, 0, st>>>(g);
+            }
             DDM_CUDA(cudaGetLastError());
             chain_generic_out_kernel<<<static_cast<unsigned>((M + tb - 1) / tb), tb, 0, st>>>(
                 c->d_ytmp, out_dev, M, c->has_prev, c->out_mode);
