@@ -537,6 +537,76 @@ chain_generic_tile_kernel(const GenericParams P, int row_len) {
     P.y[idx] = make_double2(ax, ay);
 }
 
+// D = 1 (filter + discriminator without decimation): consecutive outputs share all but one of their
+// samples, so a thread produces four consecutive outputs from a sliding register window -- one
+// shared-memory load and one tap load per tap for four outputs instead of one each per output.
+// Tile layout: sample s' at [s' mod 4][s' div 4] (the lanes' windows start 4 samples apart).
+constexpr int kGen1Outs = 4;
+
+static __global__ void __launch_bounds__(kGenTile)
+chain_generic_tile1_kernel(const GenericParams P, int row_len) {
+    extern __shared__ double2 s_tile[];                  // [4][row_len]
+    constexpr int R = kGen1Outs;
+    const int j = threadIdx.x;
+    const int K = P.K;
+    const long long idx0 = static_cast<long long>(blockIdx.x) * (kGenTile * R);
+    const long long lo = P.off + (idx0 - 1) - (K - 1);
+    const int count = kGenTile * R - 1 + K;
+    for (int sp = j; sp < count; sp += kGenTile) {
+        const long long i = lo + sp;
+        double2 v = make_double2(0.0, 0.0);
+        if (i >= -static_cast<long long>(P.H) && i < P.n) {
+            const float2 f = chain_fetch(P.x, P.halo, P.H, i, P.in_format);
+            v = make_double2(static_cast<double>(f.x), static_cast<double>(f.y));
+        }
+        s_tile[(sp & 3) * row_len + (sp >> 2)] = v;
+    }
+    __syncthreads();
+    const long long idx = idx0 + static_cast<long long>(j) * R;
+    if (idx > P.M) return;
+    // output c of this thread, tap k: s' = 4 j + c + e, e = K - 1 - k
+    auto tile_at = [&](int sp) { return s_tile[(sp & 3) * row_len + (sp >> 2)]; };
+    double2 w[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) w[c] = tile_at(4 * j + c + K - 1);
+    double ax[R], ay[R];
+#pragma unroll
+    for (int c = 0; c < R; ++c) ax[c] = ay[c] = 0.0;
+    for (int k = 0; k < K; ++k) {
+        if (P.mix) {
+            const double2 t = P.ctaps[k];
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                ax[c] = fma(t.x, w[c].x, fma(-t.y, w[c].y, ax[c]));
+                ay[c] = fma(t.x, w[c].y, fma(t.y, w[c].x, ay[c]));
+            }
+        } else {
+            const double t = P.taps[k];
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                ax[c] = fma(t, w[c].x, ax[c]);
+                ay[c] = fma(t, w[c].y, ay[c]);
+            }
+        }
+        // slide: next tap looks one sample earlier
+#pragma unroll
+        for (int c = R - 1; c > 0; --c) w[c] = w[c - 1];
+        const int e = K - 2 - k;
+        if (e >= 0) w[0] = tile_at(4 * j + e);
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+        if (idx + c > P.M) break;
+        double rx = ax[c], ry = ay[c];
+        if (P.mix) {
+            const double2 r = phase_rotator_f64(P.r_hi, P.r_lo, P.n0 + P.off + (idx + c - 1));
+            rx = fma(r.x, ax[c], -r.y * ay[c]);
+            ry = fma(r.x, ay[c], r.y * ax[c]);
+        }
+        P.y[idx + c] = make_double2(rx, ry);
+    }
+}
+
 static __global__ void chain_generic_out_kernel(const double2 *y, void *out, long long M, int has_prev,
                                          int out_mode) {
     const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -1121,7 +1191,15 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             const int row_len = kGenTile + (c->K - 1) / D + 1;
             const size_t tile_bytes = sizeof(double2) * static_cast<size_t>(D) * row_len;
             const bool has_virtual = c->in_format == DDM_IN_CU8 && c->n_real < c->H;
-            if (!has_virtual && tile_bytes <= 200 * 1024) {
+            if (!has_virtual && D == 1 && c->K <= 4096) {
+                const int rl = (kGenTile * kGen1Outs - 1 + c->K + 3) / 4 + 1;
+                const size_t bytes = sizeof(double2) * 4 * static_cast<size_t>(rl);
+                DDM_CUDA(cudaFuncSetAttribute(chain_generic_tile1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(bytes)));
+                const int per_cta = kGenTile * kGen1Outs;
+                chain_generic_tile1_kernel<<<static_cast<unsigned>((M + 1 + per_cta - 1) / per_cta), kGenTile, bytes, st>>>(
+                    g, rl);
+            } else if (!has_virtual && tile_bytes <= 200 * 1024) {
                 DDM_CUDA(cudaFuncSetAttribute(chain_generic_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(tile_bytes)));
                 chain_generic_tile_kernel<<<static_cast<unsigned>((M + 1 + kGenTile - 1) / kGenTile), kGenTile,

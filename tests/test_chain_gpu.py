@@ -56,7 +56,10 @@ CASES = [
     (151, 17, 1024000, 30000.0, 90000, 6),     # 1.024 Msps recordings: D = 17, Q = 9
     (151, 35, 2100000, -20000.0, 90000, 4),
     (101, 25, 1500000, 12000.0, 90000, 7),
-    (151, 1, 60235, 500.0, 20000, 4),          # no decimation -> general path
+    (151, 1, 60235, 500.0, 20000, 4),          # no decimation -> general path (sliding-window tile)
+    (151, 1, 60235, 0.0, 5000, 3),             # ... without mixer
+    (1, 1, 1000, 10.0, 3000, 3),               # ... single tap
+    (40, 3, 48000, 1000.0, 30000, 5),          # general path, odd D, tile kernel
     (600, 8, 2048000, 30000.0, 30000, 3),      # Q > 10 -> general path
 ]
 
