@@ -140,6 +140,22 @@ def test_argument_validation_needs_no_gpu():
     assert not filters.butter(48000, 1000).isFIR
 
 
+def test_constructor_copy_semantics_without_a_device():
+    """Large float32 / complex64 inputs take the straight-to-device snapshot only when a device is
+    present; without one the constructor keeps the reference's host copy (comm.py:38) and .signal
+    works, while any operator still refuses to run on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from directdemod_b200 import comm, filters
+    x = np.arange(1 << 17, dtype=np.float32)
+    s = comm.commSignal(48000, x)
+    x[:] = -1
+    assert s.length == 1 << 17 and s.signal.dtype == np.float32 and s.signal[5] == 5.0
+    with pytest.raises(RuntimeError):
+        s.filter(filters.rollingAverage(3)).signal
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():
