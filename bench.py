@@ -222,6 +222,28 @@ def workload_config(n_gpus, mode):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def _cpus_near_gpu(torch, dev_index):
+    """CPUs of the NUMA node the GPU hangs off (sysfs), or None when that cannot be told."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(path) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return (node, cpus) if cpus else None
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -297,6 +319,19 @@ def run_ours(args):
     if world > 1 and args.e2e_samples == N_PASS:
         args.e2e_samples = N_PASS // 4
     n_e2e = min(n, args.e2e_samples)
+    # several ranks stream from host memory at once: keep each rank's pinned staging buffers (first
+    # touch) and its copy-issuing thread on the NUMA node of its GPU for the duration of this leg
+    numa_note = None
+    old_affinity = None
+    if world > 1 and not args.no_numa_bind:
+        near = _cpus_near_gpu(torch, local)
+        if near is not None:
+            try:
+                old_affinity = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, near[1])
+                numa_note = "rank bound to NUMA node %d (%d cpus) for the end-to-end leg" % (near[0], len(near[1]))
+            except Exception:
+                old_affinity = None
     try:
         host = torch.empty(n_e2e, dtype=torch.complex64, pin_memory=True)
         host.copy_(x[:n_e2e])
@@ -331,6 +366,12 @@ def run_ours(args):
                "h2d": int(h2d), "d2h": int(d2h)}
     except Exception as exc:  # pinned allocation can fail on a small host
         e2e = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    finally:
+        if old_affinity is not None:
+            try:
+                os.sched_setaffinity(0, old_affinity)
+            except Exception:
+                pass
     # ---- extra (not the headline): the same pass fed with raw unsigned 8-bit I/Q, the format the
     # reference's sources actually read (source.py:117-118); 2 B/sample instead of 8 ----
     u8 = None
@@ -432,6 +473,8 @@ def run_ours(args):
                            "ms_per_step": round(e2e_ms, 3), "steps": e2e["steps"],
                            "samples_per_step": e2e["samples_per_step"],
                            "path": "ddm_chain_apply_host per %d-sample chunk, pinned host buffers" % CHUNK}
+            if numa_note:
+                line["e2e"]["numa"] = numa_note
         else:
             line["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                            "note": str(e2e)}
@@ -453,6 +496,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=N_PASS, help="samples per GPU per step")
     ap.add_argument("--e2e-samples", type=int, default=N_PASS)
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="multi-rank runs: do not bind ranks to their GPU's NUMA node for the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
