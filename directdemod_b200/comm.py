@@ -410,7 +410,7 @@ class commSignal:
                                                op[2], _dev.stream_ptr(x.device.index)), "ddm_mix_cf32")
             return x
         if kind == "filter":
-            return op[1]._apply_dev(x)
+            return op[1]._apply_dev(x, _queued=True)
         if kind == "decim":
             jump, off = op[1], op[2]
             n = x.numel()

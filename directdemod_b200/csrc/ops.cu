@@ -82,22 +82,25 @@ __global__ void fm_kernel(const float2 *x, const float2 *prev, float *out, long 
 // in the difference, so every output only needs its own two angles:
 //   d = a[i] - a[i-1];  dd = mod(d + pi, 2 pi) - pi;  if (dd == -pi && d > 0) dd = pi;
 //   out = |d| < pi ? d : dd                       (numpy/lib/function_base.py unwrap)
-__global__ void fm_ad_kernel(const float2 *x, const float *prev_angle, float *out, float *last_angle,
+// The carried state is the last complex SAMPLE, not its angle rounded to float32: a[i-1] is then
+// evaluated in float64 from the same bits whether i-1 lies in this chunk or in the previous one, so
+// the result does not depend on where the stream was cut (the reference carries a float64 angle).
+__global__ void fm_ad_kernel(const float2 *x, const float2 *prev_sample, float *out, float2 *last_sample,
                              long long n) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    const long long first = prev_angle ? 0 : 1;
+    const long long first = prev_sample ? 0 : 1;
     const double pi = 3.14159265358979323846;
     for (long long i = first + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += stride) {
         const double a1 = atan2(static_cast<double>(x[i].y), static_cast<double>(x[i].x));
         const double a0 = i > 0 ? atan2(static_cast<double>(x[i - 1].y), static_cast<double>(x[i - 1].x))
-                                : static_cast<double>(*prev_angle);
+                                : atan2(static_cast<double>(prev_sample->y), static_cast<double>(prev_sample->x));
         const double d = a1 - a0;
         double dd = d + pi;
         dd = dd - floor(dd / (2 * pi)) * (2 * pi) - pi;
         if (dd == -pi && d > 0) dd = pi;
         out[i - first] = static_cast<float>(fabs(d) < pi ? d : dd);
-        if (i == n - 1 && last_angle) *last_angle = static_cast<float>(a1);
+        if (i == n - 1 && last_sample) *last_sample = x[i];
     }
 }
 
@@ -408,10 +411,10 @@ int ddm_fm_demod(int device, const void *x_dev, int64_t n, const void *prev_dev,
     return DDM_OK;
 }
 
-int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_angle_dev,
-                      void *out_dev, void *last_angle_dev, int64_t *n_out, void *stream) {
+int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_sample_dev,
+                      void *out_dev, void *last_sample_dev, int64_t *n_out, void *stream) {
     DDM_REQUIRE(n >= 0, "ddm_fm_angle_diff: negative length");
-    const int64_t m = prev_angle_dev ? n : (n > 0 ? n - 1 : 0);
+    const int64_t m = prev_sample_dev ? n : (n > 0 ? n - 1 : 0);
     if (n_out) *n_out = m;
     if (n == 0) return DDM_OK;
     DDM_REQUIRE(x_dev != nullptr, "ddm_fm_angle_diff: NULL argument");
@@ -421,18 +424,13 @@ int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev
     if (m > 0) {
         DDM_REQUIRE(out_dev != nullptr, "ddm_fm_angle_diff: NULL output");
         fm_ad_kernel<<<ops_grid(device, m), kOpsThreads, 0, st>>>(
-            static_cast<const float2 *>(x_dev), static_cast<const float *>(prev_angle_dev),
-            static_cast<float *>(out_dev), static_cast<float *>(last_angle_dev), n);
+            static_cast<const float2 *>(x_dev), static_cast<const float2 *>(prev_sample_dev),
+            static_cast<float *>(out_dev), static_cast<float2 *>(last_sample_dev), n);
         DDM_CUDA(cudaGetLastError());
         count_launch();
-    } else if (last_angle_dev) {
-        // a single sample and no predecessor: only the carried angle is produced
-        float2 h;
-        DDM_CUDA(cudaMemcpyAsync(&h, x_dev, sizeof(h), cudaMemcpyDeviceToHost, st));
-        DDM_CUDA(cudaStreamSynchronize(st));
-        const float a = static_cast<float>(std::atan2(static_cast<double>(h.y), static_cast<double>(h.x)));
-        DDM_CUDA(cudaMemcpyAsync(last_angle_dev, &a, sizeof(a), cudaMemcpyHostToDevice, st));
-        DDM_CUDA(cudaStreamSynchronize(st));
+    } else if (last_sample_dev) {
+        // a single sample and no predecessor: only the carried sample is produced
+        DDM_CUDA(cudaMemcpyAsync(last_sample_dev, x_dev, sizeof(float2), cudaMemcpyDeviceToDevice, st));
     }
     return DDM_OK;
 }

@@ -167,8 +167,13 @@ class decode_noaa:
         half = numPixels // 2
         # :317-320 first guess of the black / white levels from the whole pass
         seg = n // numPixels
-        (self._low, self._high) = np.percentile(_row_medians(sig, rows=numPixels, stride=seg, length=seg),
-                                                (0.5, 99.5))
+        if seg < 1:
+            # a pass shorter than one line: the reference takes medians of empty rows (NaN, with numpy's
+            # "Mean of empty slice" warning) and percentiles of those
+            self._low = self._high = float("nan")
+        else:
+            (self._low, self._high) = np.percentile(_row_medians(sig, rows=numPixels, stride=seg, length=seg),
+                                                    (0.5, 99.5))
 
         # ---- geometry of every line, then all GPU work in batches --------------------
         lines = []

@@ -67,7 +67,7 @@ class demod_fmAD:
 
     def __init__(self, storeState=True):
         self._storeState = bool(storeState)
-        self._last = None       # 1-element cuda float32 tensor (the carried angle)
+        self._last = None       # 1-element cuda complex64 tensor (the sample whose angle is carried)
 
     def demod(self, sig):
         if _dev.is_tensor(sig) and sig.is_cuda:
@@ -84,7 +84,7 @@ class demod_fmAD:
         prev = self._last if self._storeState else None
         m = n if prev is not None else max(n - 1, 0)
         out = _dev.empty_like_kind(m, False, xd.device.index)
-        new_last = t.empty(1, dtype=t.float32, device=xd.device) if self._storeState else None
+        new_last = t.empty(1, dtype=t.complex64, device=xd.device) if self._storeState else None
         got = C.c_int64()
         _lib.check(_lib.lib().ddm_fm_angle_diff(
             xd.device.index, _dev.ptr(xd), n, _dev.ptr(prev) if prev is not None else C.c_void_p(0),

@@ -53,26 +53,42 @@ class filter:
     # device allocations and coefficient uploads every time.
     _shared_handles = {}
 
-    def _handle(self):
-        if self._h is None and not self._storeState and not getattr(self, "_private", False):
+    def _handle(self, dev=None):
+        """The native handle on device ``dev`` (the device of the tensor being filtered; torch's
+        current device when no tensor is involved yet).  Filters without carried state follow their
+        input from device to device (shared handles are per device); a filter that carries a delay
+        line lives on the device it first ran on and refuses tensors from another one."""
+        if dev is None:
+            dev = self._dev_index if self._h is not None else _dev.device_index()
+        dev = int(dev)
+        if self._h is not None and dev != self._dev_index:
+            if self._storeState and self._used:
+                raise ValueError("this filter carries state on cuda:%d and was handed a tensor on cuda:%d"
+                                 % (self._dev_index, dev))
+            if getattr(self, "_owns_handle", True):
+                _lib.lib().ddm_filter_destroy(self._h)
+            self._h = None
+        shared = not self._storeState and not getattr(self, "_private", False)
+        key = (dev, self._zeroPhase, self._bd.tobytes(), self._ad.tobytes())
+        if self._h is None and shared:
             _dev.require_cuda()
-            key = (_dev.device_index(), self._bd.tobytes(), self._ad.tobytes())
             cached = filter._shared_handles.get(key)
             if cached is not None:
                 self._h = cached
                 self._owns_handle = False
-                self._dev_index = key[0]
+                self._dev_index = dev
                 return self._h
         if self._h is None:
             _dev.require_cuda()
             l = _lib.lib()
             h = C.c_void_p()
             _lib.check(l.ddm_filter_create(
-                _dev.device_index(), self._bd.ctypes.data_as(C.POINTER(C.c_double)), self._bd.size,
+                dev, self._bd.ctypes.data_as(C.POINTER(C.c_double)), self._bd.size,
                 self._ad.ctypes.data_as(C.POINTER(C.c_double)), self._ad.size, C.byref(h)),
                 "ddm_filter_create")
             self._h = h
-            self._dev_index = _dev.device_index()
+            self._dev_index = dev
+            self._owns_handle = True
             if self._state_len() > 0 and (self._storeState or self._zeroPhase):
                 # scipy's own lfilter_zi, so even ill-conditioned filters start from the very
                 # bits the reference starts from (filters.py:45)
@@ -80,12 +96,20 @@ class filter:
                 _lib.check(l.ddm_filter_set_zi_base(h, zi.ctypes.data_as(C.POINTER(C.c_double))),
                            "ddm_filter_set_zi_base")
             if self._storeState and not self._needs_lfiltic:
-                _lib.check(l.ddm_filter_reset(h, _dev.stream_ptr()), "ddm_filter_reset")
-            if not self._storeState and not getattr(self, "_private", False):
-                if len(filter._shared_handles) < 256:
-                    filter._shared_handles[(self._dev_index, self._bd.tobytes(), self._ad.tobytes())] = h
-                    self._owns_handle = False
+                _lib.check(l.ddm_filter_reset(h, _dev.stream_ptr(dev)), "ddm_filter_reset")
+            if shared and len(filter._shared_handles) < 256:
+                # one stream at a time: the handle's seed slot and the filtfilt scratch are shared too
+                filter._shared_handles[key] = h
+                self._owns_handle = False
         return self._h
+
+    def _sync_pending(self):
+        """commSignal.filter() only queues a stateful filter; anything that reads or advances the
+        delay line directly must first let that queue run, so state is consumed in call order like
+        in the reference (which executes eagerly)."""
+        owner = getattr(self, "_pending_owner", None)
+        if owner is not None:
+            owner._flush()
 
     def _unshare(self):
         """Execution modes are per-handle settings: a filter that changes one gets its own handle."""
@@ -158,6 +182,7 @@ class filter:
 
     def getState(self):
         """The carried delay line as complex128 (what the reference keeps in filter.__zi)."""
+        self._sync_pending()
         self._release_chain()
         z = np.zeros(2 * max(self._state_len(), 1))
         _lib.check(_lib.lib().ddm_filter_get_state(self._handle(), z.ctypes.data_as(C.POINTER(C.c_double)),
@@ -171,6 +196,7 @@ class filter:
         z = np.zeros(2 * max(zi.size, 1))
         z[0:2 * zi.size:2] = zi.real
         z[1:2 * zi.size:2] = zi.imag
+        self._sync_pending()
         self._chain = None
         _lib.check(_lib.lib().ddm_filter_set_state(self._handle(), z.ctypes.data_as(C.POINTER(C.c_double)),
                                                    _dev.stream_ptr()), "ddm_filter_set_state")
@@ -193,9 +219,11 @@ class filter:
         xd = _dev.to_device(x)
         return _dev.to_host(self._apply_dev(xd, host_x=x))
 
-    def _apply_dev(self, xd, host_x=None):
+    def _apply_dev(self, xd, host_x=None, _queued=False):
+        if not _queued:
+            self._sync_pending()
         l = _lib.lib()
-        h = self._handle()
+        h = self._handle(xd.device.index)
         self._release_chain()
         n = xd.numel()
         cplx = xd.is_complex()

@@ -126,9 +126,11 @@ int ddm_mix_var_cf32(int device, void *x_dev, const double *freq_dev, int64_t n,
  * on the device) or NULL for the first chunk (then n-1 outputs).  *n_out = outputs written. */
 int ddm_fm_demod(int device, const void *x_dev, int64_t n, const void *prev_dev, void *out_dev,
                  int64_t *n_out, void *stream);
-/* demod_fm.py:74-96  diff(unwrap(angle(x))); prev_angle_dev / last_angle_dev: one f32 each */
-int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_angle_dev,
-                      void *out_dev, void *last_angle_dev, int64_t *n_out, void *stream);
+/* demod_fm.py:74-96  diff(unwrap(angle(x))); prev_sample_dev / last_sample_dev: one cf32 each
+ * (the reference carries the last ANGLE in float64; carrying the sample and re-evaluating its angle
+ * in float64 gives the same value whatever the chunking) */
+int ddm_fm_angle_diff(int device, const void *x_dev, int64_t n, const void *prev_sample_dev,
+                      void *out_dev, void *last_sample_dev, int64_t *n_out, void *stream);
 /* np.abs of a cf32 (is_complex) or f32 array -> f32   (demod_am.py:29,62) */
 int ddm_abs(int device, const void *x_dev, int64_t n, int is_complex, void *out_dev, void *stream);
 /* np.sign of an f32 array (decode_afsk1200.py:157) */

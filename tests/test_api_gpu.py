@@ -663,3 +663,62 @@ def test_zero_phase_iir_on_complex_and_float64_inputs():
         # stateless lfilter on complex input
         want = sps.lfilter(b, a, xc.astype(np.complex128))
         assert O.rel_rms(make(storeState=False).applyOn(xc), want) <= TOL
+
+
+def test_queued_filter_then_direct_use_keeps_call_order():
+    """commSignal.filter() only queues a stateful filter (it may fuse with a following bwLim); using
+    the same filter object directly before the signal is read must still consume the delay line in
+    call order, as the eagerly executing reference does (comm.py:91, filters.py:69)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal(6000) + 1j * rng.standard_normal(6000)).astype(np.complex64)
+    b = sps.windows.blackmanharris(151)
+    zi = sps.lfilter_zi(b, [1.0])
+    w1, z1 = sps.lfilter(b, [1.0], x[:2000].astype(np.complex128), zi=zi)
+    w2, z2 = sps.lfilter(b, [1.0], x[2000:4000].astype(np.complex128), zi=z1)
+    w3, z3 = sps.lfilter(b, [1.0], x[4000:].astype(np.complex128), zi=z2)
+    bh = filters.blackmanHarris(151)
+    s = comm.commSignal(2048000, x[:2000]).filter(bh)          # queued, not yet run
+    got2 = bh.applyOn(x[2000:4000])                            # must see the state AFTER the queued chunk
+    assert O.rel_rms(got2, w2) <= TOL
+    assert O.rel_rms(s.signal, w1) <= TOL
+    s3 = comm.commSignal(2048000, x[4000:]).filter(bh)         # queued again ...
+    st = bh.getState()                                         # ... reading the state runs it first
+    assert O.rel_rms(st, z3) <= TOL
+    assert O.rel_rms(s3.signal, w3) <= TOL
+
+
+def test_fmad_result_does_not_depend_on_the_chunking():
+    """demod_fmAD carries the last angle (demod_fm.py:88-94); cut anywhere, the stream must give the
+    same samples (the carried value is re-evaluated in float64 from the last sample)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    rng = np.random.default_rng(22)
+    x = (rng.standard_normal(9000) + 1j * rng.standard_normal(9000)).astype(np.complex64)
+    whole = demod_fm.demod_fmAD().demod(x)
+    want, _ = O.fm_angle_diff(x, None)
+    assert wrap_rel_rms(whole, want) <= TOL
+    for cuts in ([0, 1, 2, 4500, 9000], [0, 3333, 3334, 8999, 9000]):
+        ad = demod_fm.demod_fmAD()
+        got = np.concatenate([ad.demod(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert np.array_equal(got, whole)
+
+
+def test_filter_follows_the_device_of_its_input():
+    """The native handle is created on the device of the tensor being filtered, not torch's
+    current device; a filter with carried state refuses tensors from another device."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal(5000).astype(np.float32)
+    want = filters.hamming(31, storeState=False).applyOn(torch.from_numpy(x).cuda(0)).cpu().numpy()
+    f = filters.hamming(31, storeState=False)
+    with torch.cuda.device(0):
+        got = f.applyOn(torch.from_numpy(x).to("cuda:1"))
+    assert got.device.index == 1 and np.array_equal(got.cpu().numpy(), want)
+    g = filters.hamming(31)
+    g.applyOn(torch.from_numpy(x).cuda(0))
+    with pytest.raises(ValueError):
+        g.applyOn(torch.from_numpy(x).to("cuda:1"))
