@@ -41,6 +41,7 @@ class FusedChain:
         taps = np.ascontiguousarray(np.asarray(taps, dtype=np.float64))
         if taps.ndim != 1 or taps.size < 1:
             raise ValueError("taps must be a non-empty 1-D array")
+        self._taps = taps
         self.ntaps = int(taps.size)
         self.decim = int(decim)
         self.freq_offset = float(freq_offset)

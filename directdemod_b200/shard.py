@@ -50,8 +50,9 @@ def decim_offset_at(start, decim, stream_offset=0):
 
 def exchange_halo(tail, rank, world, group=None):
     """Ring shift g -> g+1 of the slab tails.  ``tail``: this rank's last halo_len input
-    samples (tensor on the device of the process group's backend).  Returns the tensor received
-    from rank-1, or None on rank 0 (which starts from the reference's initial condition)."""
+    samples (tensor on the device of the process group's backend; every rank passes the same
+    shape and dtype).  Returns the tensor received from rank-1, or None on rank 0 (which starts
+    from the reference's initial condition)."""
     import torch
     import torch.distributed as dist
     if world == 1:
@@ -107,6 +108,40 @@ class TimeShardedChain:
         else:
             self.chain.set_position(self.start, off, True, halo)
         return self.chain.apply(x_slab)
+
+    def boundary_check(self, x_slab, y_slab, width=2000):
+        """Self-check of the seam between rank-1 and this rank: the ``width`` outputs either side of
+        the slab start are recomputed by ONE chain on this rank alone -- from ``width*decim`` (+ halo)
+        raw samples of the previous slab, fetched with a second ring shift, and the head of this slab
+        -- and compared with what the two ranks produced (previous rank's output tail ++ this rank's
+        output head).  Returns {"max_abs_err", "bit_equal", "samples"} (rank 0: nothing to compare,
+        zeros).  Collective: every rank must call it."""
+        import torch
+        from .fused import FusedChain
+        w_in = width * self.decim
+        need = w_in + self.halo_len
+        for s, e in self.bounds:
+            if e - s < need + self.decim:
+                raise ValueError("slabs are too short for a %d-output boundary check" % width)
+        tail_in = exchange_halo(x_slab[-need:].contiguous(), self.rank, self.world, self.group)
+        tail_out = exchange_halo(y_slab[-width:].contiguous(), self.rank, self.world, self.group)
+        if self.rank == 0:
+            return {"max_abs_err": 0.0, "bit_equal": True, "samples": 0}
+        c = self.chain
+        chk = FusedChain(c._taps, self.decim, c.freq_offset, c.samp_rate, demod=c.demod, device=c.device)
+        g0 = self.start - w_in
+        chk.set_position(g0, decim_offset_at(g0, self.decim), True, tail_in[:self.halo_len].contiguous())
+        win = torch.cat([tail_in[self.halo_len:], x_slab[:w_in]])
+        got = chk.apply(win)
+        want = torch.cat([tail_out, y_slab[:width]])
+        if got.numel() != want.numel():
+            raise RuntimeError("boundary window produced %d samples, expected %d" % (got.numel(), want.numel()))
+        if c.demod:                    # phases: compare modulo 2 pi
+            d = got.double() - want.double()
+            err = torch.atan2(torch.sin(d), torch.cos(d)).abs().max()
+        else:
+            err = (got - want).abs().max()
+        return {"max_abs_err": float(err), "bit_equal": bool(torch.equal(got, want)), "samples": int(got.numel())}
 
 
 class TimeShardedFilters:
@@ -170,3 +205,40 @@ class TimeShardedFilters:
                 outs.append(out)
             y_h, y_s = outs
         return y_s
+
+    def boundary_check(self, x_slab, y_slab, make_filters, width=2000):
+        """Self-check of the seam between rank-1 and this rank: a fresh copy of the cascade
+        (``make_filters()``) runs on this rank alone from zero state over
+        [halo_len + width raw samples of the previous slab ++ width samples of this slab] and its last
+        2*width outputs are compared with (previous rank's output tail ++ this rank's output head).
+        Returns {"max_rel_err", "samples"}: maximum absolute difference over the RMS of the window
+        (the segment-parallel IIR cuts its segments differently in the two runs, so this is equality
+        to the recursion's roundoff, not bit equality).  Collective: every rank must call it."""
+        import torch
+        need = self.halo_len + width
+        for s, e in self.bounds:
+            if e - s < need:
+                raise ValueError("slabs are too short for a %d-sample boundary check" % width)
+        tail_in = exchange_halo(x_slab[-need:].contiguous(), self.rank, self.world, self.group)
+        tail_out = exchange_halo(y_slab[-width:].contiguous(), self.rank, self.world, self.group)
+        if self.rank == 0 or self.world == 1:
+            return {"max_rel_err": 0.0, "samples": 0}
+        chk = TimeShardedFilters(make_filters(), self.bounds[-1][1], self.rank, self.world, self.group)
+        win = torch.cat([tail_in[self.halo_len:], x_slab[:width]])
+        got = chk.run_window(win, tail_in[:self.halo_len].contiguous())
+        want = torch.cat([tail_out, y_slab[:width]])
+        rms = float(want.abs().double().pow(2).mean().sqrt())
+        err = float((got - want).abs().max())
+        return {"max_rel_err": err / rms if rms > 0 else err, "samples": int(got.numel())}
+
+    def run_window(self, x, halo):
+        """The cascade from zero state over [halo ++ x], keeping the x part (what ``run`` does on ranks
+        > 0, for an arbitrary window)."""
+        keep_rank, keep_bounds = self.rank, (self.start, self.end)
+        try:
+            self.rank = max(self.rank, 1)
+            self.start, self.end = 0, x.numel()
+            return self.run(x, halo=halo)
+        finally:
+            self.rank = keep_rank
+            self.start, self.end = keep_bounds

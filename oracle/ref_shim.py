@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference (/root/reference) under modern numpy/scipy.
+"""Import the UNMODIFIED reference under modern numpy/scipy.
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py and by the differential tests
-that run in the build container; /root/reference does not exist on the GPU box, so
-everything that imports this must skip when ``available()`` is False.  No reference code
-is copied: this only patches renamed third-party symbols before importing it.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by oracle/gen_golden.py, by the differential tests and
+by the CPU arm of bench.py.  The reference is looked for at /root/reference (the build container)
+and, failing that, at oracle/_ref/ -- unmodified module files staged there by oracle/stage_ref.py
+(git-ignored, shipped to the GPU box by gpurun like a built binary).  Everything that imports this
+must cope with ``available()`` being False.  This file only patches renamed third-party symbols
+before importing the reference.
 """
 
 from __future__ import annotations
@@ -12,11 +14,28 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("DDM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.environ.get("DDM_REFERENCE_ROOT", "/root/reference"), os.path.join(_HERE, "_ref")]
+
+
+def _root():
+    for cand in _CANDIDATES:
+        if os.path.isfile(os.path.join(cand, "directdemod", "comm.py")):
+            return cand
+    return None
+
+
+REF_ROOT = _root() or _CANDIDATES[0]
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "directdemod"))
+    return _root() is not None
+
+
+def where() -> str:
+    """"checkout" (/root/reference), "staged" (oracle/_ref) or "absent"."""
+    r = _root()
+    return "absent" if r is None else ("staged" if os.path.abspath(r) == os.path.join(_HERE, "_ref") else "checkout")
 
 
 def _stub(name):
@@ -27,8 +46,9 @@ def _stub(name):
 
 def load():
     """Return the reference's ``directdemod`` package (importing it on first use)."""
-    if not available():
-        raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
+    ref_root = _root()
+    if ref_root is None:
+        raise RuntimeError("reference not present (neither %s nor %s)" % tuple(_CANDIDATES))
     if "directdemod" in sys.modules and getattr(sys.modules["directdemod"], "__ddm_ref__", False):
         return sys.modules["directdemod"]
 
@@ -69,11 +89,11 @@ def load():
     if not hasattr(scipy, "misc"):
         scipy.misc = sys.modules.get("scipy.misc")
 
-    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, ref_root)
     try:
         import directdemod  # noqa: F401  (the reference package)
         from directdemod import chunker, comm, constants, demod_am, demod_fm, filters  # noqa: F401
     finally:
-        sys.path.remove(REF_ROOT)
+        sys.path.remove(ref_root)
     sys.modules["directdemod"].__ddm_ref__ = True
     return sys.modules["directdemod"]

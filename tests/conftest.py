@@ -15,6 +15,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: a minute or more (long synthetic passes against the CPU oracle)")
 
 
 def pytest_collection_modifyitems(config, items):

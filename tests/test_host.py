@@ -206,3 +206,42 @@ def test_sources_read_like_the_reference(tmp_path):
     assert source.IQdat(str(dat)).sourceType == constants.SOURCE_IQDAT
     assert source.IQdat(str(dat)).sampFreq == constants.IQ_SDRSAMPRATE
     assert source.IQwav(str(wav), 1000000).sampFreq == 1000000
+
+
+def test_reference_arm_runs_the_staged_unmodified_reference(tmp_path):
+    """bench.py's CPU arm must drive the reference itself (oracle/stage_ref.py -> oracle/_ref, the copy
+    that travels to the GPU box), chunk loop as decode_noaa.py:613-627, and both arms must print the
+    same `config` dict."""
+    import filecmp
+    import bench
+    from oracle import ref_shim, stage_ref
+    if not ref_shim.available():
+        pytest.skip("no reference checkout and nothing staged")
+    if os.path.isdir(os.path.join(stage_ref.SRC_ROOT, "directdemod")):
+        staged = stage_ref.stage()
+        assert staged, "nothing staged"
+        for path in staged:                                   # byte-for-byte copies, no edits
+            assert filecmp.cmp(path, os.path.join(stage_ref.SRC_ROOT, "directdemod", os.path.basename(path)),
+                               shallow=False)
+    assert bench._cpu_kind() == "reference"
+    assert bench.workload_config(4) == bench.workload_config(4) and "mode" not in bench.workload_config(1)
+    # one small pass through the reference arm's worker against the oracle port of the same chain
+    from oracle import ddoracle as O
+    n = 300000
+    bench._CPU.clear()
+    bench._CPU.update(x=bench._cpu_chunk_input(5, n), n=n, kind="reference")
+    ref_shim.load()
+    from directdemod import chunker, comm, demod_fm, filters
+    src = bench._LoopSource(bench._CPU["x"], 2)
+    ck = chunker.chunker(src, n)
+    bh, fm = filters.blackmanHarris(bench.NTAPS), demod_fm.demod_fm()
+    got = comm.commSignal(bench.CRUDE_RATE)
+    for i in ck.getChunks:
+        got.extend(comm.commSignal(src.sampFreq, src.read(*i), ck).offsetFreq(bench.F_OFF).filter(bh)
+                   .bwLim(bench.BW, uniq="First").funcApply(fm.demod).bwLim(bench.CRUDE_RATE, False))
+    st = O.ChainState(bench.taps_bh151())
+    want = np.concatenate([O.chain_chunk(bench._CPU["x"], bench.FS, bench.F_OFF, bench.taps_bh151(), bench.BW, st)[0]
+                           for _ in range(2)])
+    assert got.signal.shape == want.shape and np.array_equal(got.signal, want)
+    assert bench._cpu_step(1) > 0
+    bench._CPU.clear()

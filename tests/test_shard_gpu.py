@@ -36,6 +36,8 @@ def _worker(rank, world, port, n, out_dir):
     ts = shard.TimeShardedChain(taps, decim, f, fs, n, rank, world, device=rank)
     slab = torch.from_numpy(x[ts.start:ts.end].copy()).cuda()
     y = ts.run(slab)
+    chk = ts.boundary_check(slab, y, width=300)          # the self-check bench.py reports
+    assert chk["bit_equal"] and chk["samples"] == (600 if rank else 0), chk
     np.save(os.path.join(out_dir, "part%d.npy" % rank), y.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -43,12 +45,12 @@ def _worker(rank, world, port, n, out_dir):
 
 def test_time_sharded_chain_over_nccl(tmp_path):
     import torch
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
     from directdemod_b200.fused import FusedChain
-    n = 3000000
+    n = 6000000
     mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / ("part%d.npy" % r)) for r in range(world)])
     fs, f, decim = 2048000, 30000.0, 34
@@ -74,7 +76,11 @@ def _worker_filters(rank, world, port, n, out_dir):
     fir = filters.remez(2400000, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023)
     iir = filters.butter(2400000, 100000, n=8)
     ts = shard.TimeShardedFilters([fir, iir], n, rank, world)
-    y = ts.run(torch.from_numpy(x[ts.start:ts.end].copy()).cuda())
+    slab = torch.from_numpy(x[ts.start:ts.end].copy()).cuda()
+    y = ts.run(slab)
+    b1, b2, a2 = np.asarray(fir.getB), np.asarray(iir.getB), np.asarray(iir.getA)
+    chk = ts.boundary_check(slab, y, lambda: [filters.filter(b1, [1]), filters.filter(b2, a2)], width=500)
+    assert chk["max_rel_err"] <= 1e-5 and chk["samples"] == (1000 if rank else 0), chk
     np.save(os.path.join(out_dir, "fpart%d.npy" % rank), y.cpu().numpy())
     dist.barrier()
     dist.destroy_process_group()
@@ -85,11 +91,11 @@ def test_time_sharded_c4_cascade_over_nccl(tmp_path):
     time across GPUs, halo moved by NCCL; equals the oracle's whole-stream result."""
     import scipy.signal as sps
     import torch
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
-    n = 2000000
+    n = 4000000
     mp.spawn(_worker_filters, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     got = np.concatenate([np.load(tmp_path / ("fpart%d.npy" % r)) for r in range(world)])
     rng = np.random.default_rng(9)

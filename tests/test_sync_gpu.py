@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import ddoracle as O
-from tests.util import TOL, ArraySource, apt_iq
+from tests.util import TOL, ArraySource, apt_iq, oracle_chain
 
 pytestmark = pytest.mark.gpu
 
@@ -136,6 +136,68 @@ def test_accurate_sync_positions_bit_exact(apt_pass):
         assert list(map(int, got[:len(want)])) == list(map(int, want))
 
 
+def test_accurate_sync_32_windows_per_sync_word_bit_exact():
+    """getAccurateSync on a 17.5 s pass: the first 32 windows of EACH sync word against the oracle
+    (decode_noaa.py:826-856 restated), the CPU windows computed by a pool of processes."""
+    import multiprocessing as mp
+    from directdemod_b200 import decode_noaa
+    from tests.util import oracle_accurate_window
+    fs = 2048000
+    x = apt_iq(17, 17.5, fs=fs)
+    dec = decode_noaa.decode_noaa(ArraySource(x, fs), 30000.0)
+    res = dec.getAccurateSync()
+    asyncA, asyncB = res[0], res[4]
+    taps = O.taps_blackman_harris(151)[0]
+    parts = oracle_chain(x, fs, 30000.0, taps, 60000, list(range(0, len(x), 20000000)) + [len(x)])
+    audio, rate = parts
+    am = O.am_envelope_chunked(audio)
+    width = int(3 * O.NOAA_T * 40 * fs)
+    jobs, owner = [], []
+    for bits, tag in ((O.NOAA_SYNCA, "A"), (O.NOAA_SYNCB, "B")):
+        crude, _ = O.find_syncs(am, rate, bits)
+        cnt = 0
+        for c in crude / rate * fs:
+            a, b = int(c) - width, int(c) + width
+            if a < 0 or b > len(x):
+                continue
+            if cnt == 32:
+                break
+            jobs.append((x[a:b].copy(), a, fs, bits))
+            owner.append(tag)
+            cnt += 1
+        assert cnt == 32, (tag, cnt)
+    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
+        want = pool.map(oracle_accurate_window, jobs, chunksize=2)
+    wantA = [w for w, t in zip(want, owner) if t == "A"]
+    wantB = [w for w, t in zip(want, owner) if t == "B"]
+    assert list(map(int, asyncA[:32])) == wantA
+    assert list(map(int, asyncB[:32])) == wantB
+
+
+@pytest.mark.slow
+def test_crude_sync_of_a_120_second_pass_bit_exact():
+    """A long pass (120 s = 245.76 M samples, 13 PROC_CHUNKSIZE chunks, 240 lines): crude sync
+    positions of both sync words against the oracle run chunk by chunk like the reference."""
+    from directdemod_b200 import decode_noaa
+    from tests.util import apt_iq_long
+    fs = 2048000
+    x = apt_iq_long(23, 120.0, fs=fs)
+    dec = decode_noaa.decode_noaa(ArraySource(x, fs), 30000.0)
+    syncA, syncB = dec.getCrudeSync()
+    assert dec.useful == 1
+    taps = O.taps_blackman_harris(151)[0]
+    audio, rate = oracle_chain(x, fs, 30000.0, taps, 60000, list(range(0, len(x), 20000000)) + [len(x)])
+    assert rate == 60235
+    from tests.util import wrap_rel_rms
+    assert wrap_rel_rms(dec._audOut.signal, audio) <= TOL
+    am = O.am_envelope_chunked(audio)
+    wantA, _ = O.find_syncs(am, rate, O.NOAA_SYNCA)
+    wantB, _ = O.find_syncs(am, rate, O.NOAA_SYNCB)
+    assert len(wantA) >= 238 and len(wantB) >= 238
+    assert np.array_equal(np.asarray(syncA), wantA)
+    assert np.array_equal(np.asarray(syncB), wantB)
+
+
 def test_batched_accurate_sync_equals_per_window_path(apt_pass):
     """The row-batched accurate sync (one launch sequence per 256 windows) against the per-window
     operator-by-operator path: identical positions, peak heights and time-sync means."""
@@ -190,10 +252,19 @@ def test_noaa_pass_matches_unmodified_reference(golden):
     assert frac >= 0.999, (frac, int(diff.max()))
 
 
-def test_afsk_front_end_matches_oracle():
+@pytest.mark.parametrize("exact_iir", [False, True], ids=["default-segment-parallel", "exact-replay"])
+def test_afsk_front_end_matches_oracle(exact_iir):
     """decode_afsk1200.getMsg up to the bit-edge correlation (decode_afsk1200.py:62-158) on a
     synthetic FM-modulated AFSK stream at 960 kHz IQ with bw = 48000 (at a literal
-    48 kHz IQ rate the reference's own 151-tap filter wipes the packet out)."""
+    48 kHz IQ rate the reference's own 151-tap filter wipes the packet out).
+
+    Both execution modes of the 12th-order band-pass are tested -- the DEFAULT (segment-parallel DFMA,
+    the one the benchmarks time) and the bit-exact replay.  The bound is the same for both and is the
+    reference's own: scipy's float64 tf-form recursion for this filter has a measured roundoff floor
+    of ~4e-5 relative (ddm_iir_analyse: float64 vs long double on white noise), i.e. two float64 runs
+    of scipy itself whose inputs differ in the last bit stay that far apart; the filter's input here
+    already differs from the float64 oracle's by the fp32 rounding of the FM stage.  What the decoder
+    consumes are the SIGNS of the bank output and the edge positions, asserted exactly below."""
     import scipy.signal as sps
     from directdemod_b200 import afsk
     rng = np.random.default_rng(6)
@@ -204,7 +275,7 @@ def test_afsk_front_end_matches_oracle():
     audio = np.sin(2 * np.pi * np.cumsum(tone) / fs)
     x = (50 * np.exp(1j * 2 * np.pi * 3000 * np.cumsum(audio) / fs)
          + 1.0 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
-    sig, bf, changes = afsk.front_end(ArraySource(x, fs), 0.0, bw, exact_iir=True)
+    sig, bf, changes = afsk.front_end(ArraySource(x, fs), 0.0, bw, exact_iir=exact_iir)
     # oracle
     taps = O.taps_blackman_harris(151)[0]
     iq, rate = O.chain_stream(x, fs, 0.0, taps, bw, demod=False)
@@ -230,6 +301,16 @@ def test_afsk_front_end_matches_oracle():
     assert np.mean(np.abs(got_ch - want_ch) < 1e-9) >= 0.999
     strong = np.abs(want_ch) > 0.5
     assert np.array_equal(np.sign(got_ch[strong]), np.sign(want_ch[strong]))
+    # downstream decisions (decode_afsk1200.py:157-170): the sign of the bank output wherever it is not
+    # within the filter's floor of zero, and the bit-edge positions = local extrema of `changes`
+    clear = np.abs(want_bf) > 20 * floor * np.sqrt(np.mean(want_bf ** 2))
+    assert np.mean(clear) > 0.95
+    assert np.array_equal(np.sign(got_bf[clear]), np.sign(want_bf[clear]))
+
+    def edges(c):
+        mid = c[1:-1]
+        return np.nonzero((np.abs(mid) > 0.9) & (np.abs(mid) >= np.abs(c[:-2])) & (np.abs(mid) > np.abs(c[2:])))[0]
+    assert np.array_equal(edges(got_ch), edges(want_ch))
 
 
 def b_floor(b, a):
