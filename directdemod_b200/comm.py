@@ -132,7 +132,12 @@ class commSignal:
             self._parts = []
             if any(p.is_complex() for p in parts):
                 parts = [p.to(t.complex64) for p in parts]
-            self._dev = parts[0] if len(parts) == 1 else t.cat(parts)
+            if len(parts) == 1:
+                self._dev = parts[0]
+                self._shared = True      # still the tensor of the signal it was taken from
+            else:
+                self._dev = t.cat(parts)
+                self._shared = False
             self._host = None
         elif self._dev is None:
             self._dev = _dev.to_device(self._host)
@@ -246,7 +251,10 @@ class commSignal:
         # bytes); here the pieces stay on the device and are joined once, when first read
         self._flush()
         sig._flush()
-        piece = sig._device_array().clone()      # must not alias a tensor its owner may still write to
+        # the piece is shared, not copied: `sig` is told that its tensor now has a second owner, so the
+        # one operator that writes in place (the stand-alone mixer) copies first
+        piece = sig._device_array()
+        sig._shared = True
         if self._len == 0:
             self._parts = [piece]
             self._complex = bool(piece.is_complex())
@@ -372,7 +380,7 @@ class commSignal:
         if ch is not None:
             if getattr(ch, "_key", None) != key or ch.device != dev_index:
                 return 0, None
-            pos_n0, pos_off, pos_prev = ch.position
+            pos_n0, pos_off, pos_prev = ch.position_cached
             if (n0 is not None and n0 != pos_n0) or off != pos_off:
                 return 0, None
             if fm is not None and not (fm._chain is ch or (fm._fresh and not pos_prev)):

@@ -68,8 +68,155 @@ struct ChainParams {
     // batch of independent captures (ddm_chain_apply_batch_dev): capture k reads x + k*x_stride
     // samples and writes out + k*out_stride elements; every capture starts from the same state
     long long batch, x_stride, out_stride;
-    int J;                 // outputs per tile (see the kernel)
+    int J;                 // outputs per tile (CTA-tiled kernel)
+    long long stream_warps;   // warps that share the work (warp-autonomous kernel)
+    int stages;               // ring depth per warp (warp-autonomous kernel)
 };
+
+// ------------------------------------------------------------------------------------
+// The accumulation over the D samples of one block (both fused kernels): Q partial sums
+//   P_q = sum_a T[q][a] * mix(x[B + a])
+// from the block's raw samples at `sp` in shared memory.
+// ------------------------------------------------------------------------------------
+template <int Q, bool MIX, bool U8>
+__device__ __forceinline__ void chain_accumulate(const unsigned char *sp, const int D, const int DP, const int a_lastq,
+                                                 const float *s_taps, const float *s_rx, const float2 *s_ry,
+                                                 const float2 *s_c, unsigned long long (&acc)[Q]) {
+    // Packed single precision (FFMA2): accumulators are (re, im) pairs, a tap is a
+    // broadcast scalar operand, and the complex rotation is
+    //   m = x * cos + swap(x) * (sin, -sin)        (swap = the LO_HI operand selector)
+    // so a sample costs 2 + Q issue slots instead of 4 + 2Q.
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
+
+    // raw pair -> mixed sample.  cf32: x rot.  u8: (v + 0.5 (1+j)) rot with v = b - 128.
+    auto rotate = [&](unsigned long long X, float rx, float2 ry, float2 c) -> unsigned long long {
+        const float2 x = unpack_f32x2(X);
+        if (!MIX) return U8 ? fadd2(X, pack_f32x2(0.5f, 0.5f)) : X;
+        const unsigned long long m = U8 ? ffma2(X, pack_f32x2(rx, rx), pack_f32x2(c.x, c.y))
+                                        : fmul2(X, pack_f32x2(rx, rx));
+        return ffma2(pack_f32x2(x.y, x.x), pack_f32x2(ry.x, ry.y), m);
+    };
+    // The accumulation over the D samples of this thread's block.  ODD (odd D: the blocks of
+    // odd threads are only element aligned) is a compile-time tag of this lambda, chosen by
+    // one warp-uniform branch per tile, so that the even-D instruction stream carries none of
+    // the narrower loads (as a runtime flag inside the loads it cost D = 34 16 %).
+    auto accumulate = [&](auto odd_tag) {
+        constexpr bool ODD = decltype(odd_tag)::value;
+        // two consecutive raw samples starting at block position a (a even) as packed pairs
+        auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
+            if (U8) {
+                unsigned int w;
+                if (ODD) {
+                    const unsigned short *h = reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                    w = static_cast<unsigned int>(h[0]) | (static_cast<unsigned int>(h[1]) << 16);
+                } else {
+                    w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
+                }
+                const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
+                X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
+                X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
+                                      __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
+            } else if (ODD) {
+                X0 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
+                X1 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a + 8);
+            } else {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
+                X0 = v.x;
+                X1 = v.y;
+            }
+        };
+        auto load1 = [&](int a) -> unsigned long long {
+            if (U8) {
+                const unsigned int w = *reinterpret_cast<const unsigned short *>(sp + 2 * a);
+                return fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
+                                        __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))),
+                             pack_f32x2(-8388736.f, -8388736.f));
+            }
+            return *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
+        };
+        const int D4 = D & ~3;
+        int a = 0;
+        // four samples against the first NQ partial sums
+        auto body4 = [&](auto nq_tag) {
+            constexpr int NQ = decltype(nq_tag)::value;
+            unsigned long long X0, X1, X2, X3;
+            load2(a, X0, X1);
+            load2(a + 2, X2, X3);
+            float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
+            float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0, c0 = ry0, c1 = ry0;
+            if (MIX) {
+                rx = *reinterpret_cast<const float4 *>(s_rx + a);
+                ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
+                if (U8) {
+                    c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                    c1 = *reinterpret_cast<const float4 *>(s_c + a + 2);
+                }
+            }
+            const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+            const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+            const unsigned long long M2 = rotate(X2, rx.z, make_float2(ry1.x, ry1.y), make_float2(c1.x, c1.y));
+            const unsigned long long M3 = rotate(X3, rx.w, make_float2(ry1.z, ry1.w), make_float2(c1.z, c1.w));
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
+                acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
+                acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
+            }
+        };
+        // the last partial sum only sees the filter's tail: its taps are zero up to a_lastq
+        if (Q > 1) {
+#pragma unroll(kChainUnroll)
+            for (; a < a_lastq; a += 4) body4(std::integral_constant<int, (Q > 1 ? Q - 1 : 1)>());
+        }
+#pragma unroll(kChainUnroll)
+        for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
+        if (!ODD) {
+            if (a < D) {                                // D % 4 == 2: one aligned pair
+                unsigned long long X0, X1;
+                load2(a, X0, X1);
+                float2 rx = make_float2(1.f, 1.f);
+                float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = ry0;
+                if (MIX) {
+                    rx = *reinterpret_cast<const float2 *>(s_rx + a);
+                    ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
+                    if (U8) c0 = *reinterpret_cast<const float4 *>(s_c + a);
+                }
+                const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
+                const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
+                    acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
+                    acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
+                }
+            }
+        } else {
+            for (; a < D; ++a) {                        // the D % 4 samples left over
+                const unsigned long long X0 = load1(a);
+                float rx = 1.f;
+                float2 ry = make_float2(0.f, 0.f), c0 = ry;
+                if (MIX) {
+                    rx = s_rx[a];
+                    ry = s_ry[a];
+                    if (U8) c0 = s_c[a];
+                }
+                const unsigned long long M0 = rotate(X0, rx, ry, c0);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float t = s_taps[q * DP + a];
+                    acc[q] = ffma2(pack_f32x2(t, t), M0, acc[q]);
+                }
+            }
+        }
+    };
+    if (D & 1) accumulate(std::true_type());
+    else accumulate(std::false_type());
+}
 
 // ------------------------------------------------------------------------------------
 // fast path: D >= 2, Q <= 8
@@ -220,141 +367,8 @@ chain_fused_kernel(const ChainParams P) {
                 sp_off += static_cast<size_t>(S0 - S0a) * 2;         // shift of the aligned copy (even)
             }
             const unsigned char *sp = s_stage0 + stage * stage_bytes + sp_off;
-            // Packed single precision (FFMA2): accumulators are (re, im) pairs, a tap is a
-            // broadcast scalar operand, and the complex rotation is
-            //   m = x * cos + swap(x) * (sin, -sin)        (swap = the LO_HI operand selector)
-            // so a sample costs 2 + Q issue slots instead of 4 + 2Q.
             unsigned long long acc[Q];
-#pragma unroll
-            for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
-
-            // raw pair -> mixed sample.  cf32: x rot.  u8: (v + 0.5 (1+j)) rot with v = b - 128.
-            auto rotate = [&](unsigned long long X, float rx, float2 ry, float2 c) -> unsigned long long {
-                const float2 x = unpack_f32x2(X);
-                if (!MIX) return U8 ? fadd2(X, pack_f32x2(0.5f, 0.5f)) : X;
-                const unsigned long long m = U8 ? ffma2(X, pack_f32x2(rx, rx), pack_f32x2(c.x, c.y))
-                                                : fmul2(X, pack_f32x2(rx, rx));
-                return ffma2(pack_f32x2(x.y, x.x), pack_f32x2(ry.x, ry.y), m);
-            };
-            // The accumulation over the D samples of this thread's block.  ODD (odd D: the blocks of
-            // odd threads are only element aligned) is a compile-time tag of this lambda, chosen by
-            // one warp-uniform branch per tile, so that the even-D instruction stream carries none of
-            // the narrower loads (as a runtime flag inside the loads it cost D = 34 16 %).
-            auto accumulate = [&](auto odd_tag) {
-                constexpr bool ODD = decltype(odd_tag)::value;
-                // two consecutive raw samples starting at block position a (a even) as packed pairs
-                auto load2 = [&](int a, unsigned long long &X0, unsigned long long &X1) {
-                    if (U8) {
-                        unsigned int w;
-                        if (ODD) {
-                            const unsigned short *h = reinterpret_cast<const unsigned short *>(sp + 2 * a);
-                            w = static_cast<unsigned int>(h[0]) | (static_cast<unsigned int>(h[1]) << 16);
-                        } else {
-                            w = *reinterpret_cast<const unsigned int *>(sp + 2 * a);
-                        }
-                        const unsigned long long bias = pack_f32x2(-8388736.f, -8388736.f);     // -(2^23 + 128)
-                        X0 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
-                                              __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))), bias);
-                        X1 = fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)),
-                                              __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543))), bias);
-                    } else if (ODD) {
-                        X0 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
-                        X1 = *reinterpret_cast<const unsigned long long *>(sp + 8 * a + 8);
-                    } else {
-                        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(sp + 8 * a);
-                        X0 = v.x;
-                        X1 = v.y;
-                    }
-                };
-                auto load1 = [&](int a) -> unsigned long long {
-                    if (U8) {
-                        const unsigned int w = *reinterpret_cast<const unsigned short *>(sp + 2 * a);
-                        return fadd2(pack_f32x2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)),
-                                                __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541))),
-                                     pack_f32x2(-8388736.f, -8388736.f));
-                    }
-                    return *reinterpret_cast<const unsigned long long *>(sp + 8 * a);
-                };
-                const int D4 = D & ~3;
-                int a = 0;
-                // four samples against the first NQ partial sums
-                auto body4 = [&](auto nq_tag) {
-                    constexpr int NQ = decltype(nq_tag)::value;
-                    unsigned long long X0, X1, X2, X3;
-                    load2(a, X0, X1);
-                    load2(a + 2, X2, X3);
-                    float4 rx = make_float4(1.f, 1.f, 1.f, 1.f);
-                    float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), ry1 = ry0, c0 = ry0, c1 = ry0;
-                    if (MIX) {
-                        rx = *reinterpret_cast<const float4 *>(s_rx + a);
-                        ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
-                        ry1 = *reinterpret_cast<const float4 *>(s_ry + a + 2);
-                        if (U8) {
-                            c0 = *reinterpret_cast<const float4 *>(s_c + a);
-                            c1 = *reinterpret_cast<const float4 *>(s_c + a + 2);
-                        }
-                    }
-                    const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
-                    const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
-                    const unsigned long long M2 = rotate(X2, rx.z, make_float2(ry1.x, ry1.y), make_float2(c1.x, c1.y));
-                    const unsigned long long M3 = rotate(X3, rx.w, make_float2(ry1.z, ry1.w), make_float2(c1.z, c1.w));
-#pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const float4 t = *reinterpret_cast<const float4 *>(s_taps + q * DP + a);
-                        acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
-                        acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
-                        acc[q] = ffma2(pack_f32x2(t.z, t.z), M2, acc[q]);
-                        acc[q] = ffma2(pack_f32x2(t.w, t.w), M3, acc[q]);
-                    }
-                };
-                // the last partial sum only sees the filter's tail: its taps are zero up to a_lastq
-                if (Q > 1) {
-#pragma unroll(kChainUnroll)
-                    for (; a < P.a_lastq; a += 4) body4(std::integral_constant<int, (Q > 1 ? Q - 1 : 1)>());
-                }
-#pragma unroll(kChainUnroll)
-                for (; a < D4; a += 4) body4(std::integral_constant<int, Q>());
-                if (!ODD) {
-                    if (a < D) {                                // D % 4 == 2: one aligned pair
-                        unsigned long long X0, X1;
-                        load2(a, X0, X1);
-                        float2 rx = make_float2(1.f, 1.f);
-                        float4 ry0 = make_float4(0.f, 0.f, 0.f, 0.f), c0 = ry0;
-                        if (MIX) {
-                            rx = *reinterpret_cast<const float2 *>(s_rx + a);
-                            ry0 = *reinterpret_cast<const float4 *>(s_ry + a);
-                            if (U8) c0 = *reinterpret_cast<const float4 *>(s_c + a);
-                        }
-                        const unsigned long long M0 = rotate(X0, rx.x, make_float2(ry0.x, ry0.y), make_float2(c0.x, c0.y));
-                        const unsigned long long M1 = rotate(X1, rx.y, make_float2(ry0.z, ry0.w), make_float2(c0.z, c0.w));
-#pragma unroll
-                        for (int q = 0; q < Q; ++q) {
-                            const float2 t = *reinterpret_cast<const float2 *>(s_taps + q * DP + a);
-                            acc[q] = ffma2(pack_f32x2(t.x, t.x), M0, acc[q]);
-                            acc[q] = ffma2(pack_f32x2(t.y, t.y), M1, acc[q]);
-                        }
-                    }
-                } else {
-                    for (; a < D; ++a) {                        // the D % 4 samples left over
-                        const unsigned long long X0 = load1(a);
-                        float rx = 1.f;
-                        float2 ry = make_float2(0.f, 0.f), c0 = ry;
-                        if (MIX) {
-                            rx = s_rx[a];
-                            ry = s_ry[a];
-                            if (U8) c0 = s_c[a];
-                        }
-                        const unsigned long long M0 = rotate(X0, rx, ry, c0);
-#pragma unroll
-                        for (int q = 0; q < Q; ++q) {
-                            const float t = s_taps[q * DP + a];
-                            acc[q] = ffma2(pack_f32x2(t, t), M0, acc[q]);
-                        }
-                    }
-                }
-            };
-            if (D & 1) accumulate(std::true_type());
-            else accumulate(std::false_type());
+            chain_accumulate<Q, MIX, U8>(sp, D, DP, P.a_lastq, s_taps, s_rx, s_ry, s_c, acc);
             float2 w0 = make_float2(1.f, 0.f);
             if (MIX) {
                 const long long g = P.n0 + P.b0 + jblk * D;  // global index of the block start
@@ -395,6 +409,241 @@ chain_fused_kernel(const ChainParams P) {
             }
         }
         if (kChainEBufs == 1) __syncthreads();        // e_buf is reused by the next tile
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// fast path, second generation: warp-autonomous streams.
+//
+// ncu on chain_fused_kernel (profiles/r02_chain_fused_v1_warpstates.csv) showed the CTA-tiled kernel
+// waiting, not issuing: half of its executed instructions are the mbarrier spin, a CTA holds one
+// 34.8 KB tile in flight while it works on the other, and the per-tile CTA barrier plus the
+// thread-0 address arithmetic sit between "tile consumed" and "next copy issued".  Here the unit
+// of scheduling is the WARP:
+//   * every warp owns a contiguous range of 32-block tiles of the stream and a private ring of
+//     kStreamStages stages with its own mbarriers; lane 0 re-arms a stage with the tile S steps
+//     ahead as soon as the warp has read it (one __syncwarp, no CTA barrier anywhere in the loop),
+//     so a warp keeps S-1 .. S tiles in flight and an SM with 8 warps ~ 200 KB;
+//   * the partial sums never touch shared memory: lane l needs P_q of lane l-q -- one shuffle --
+//     and the first q lanes take it from the previous tile of the same warp, which every lane
+//     still holds in registers (source lane s hands out its current sum when s < 32-q, else its
+//     previous one).  Consecutive tiles of a warp are consecutive in the stream, so there is no
+//     halo block to recompute (the CTA-tiled kernel re-read and re-accumulated Q of every 128
+//     blocks); a range starts with one warm-up tile whose outputs are dropped.
+// Block geometry, tap tables, accumulation (chain_accumulate) and summation order are those of
+// the first kernel, so the results are bit-identical to it.
+// Tile t of a capture holds blocks 32 (t-1) .. 32 t - 1: tile 0 is the capture's own warm-up tile
+// (history from the halo buffer), tile t >= 1 produces outputs m = 32 (t-1) + lane.
+// ------------------------------------------------------------------------------------
+constexpr int kStreamMaxWarps = 12;                      // warps per CTA (one CTA per SM)
+constexpr int kStreamMaxStages = 8;
+constexpr int kStreamTile = 32;                          // blocks per warp tile
+constexpr int kStreamMinTiles = 8;                       // per warp: bounds the warm-up overhead of short chunks
+
+__host__ __device__ inline size_t stream_stage_bytes(int D, int in_format) {
+    return in_format == DDM_IN_CU8 ? ((static_cast<size_t>(kStreamTile) * D * 2 + 32 + 15) & ~static_cast<size_t>(15))
+                                   : static_cast<size_t>(kStreamTile) * D * sizeof(float2);
+}
+__host__ __device__ inline unsigned stream_fixed_bytes(int Q, int DP, int warps, int stages) {
+    const unsigned bars = (8u * warps * stages + 127u) & ~127u;
+    return bars + ((4u * (Q * DP + DP) + 8u * (2 * DP) + 127u) & ~127u);
+}
+
+template <int Q, bool MIX, int OUT, int IN>
+__global__ void __launch_bounds__(32 * kStreamMaxWarps, 1)
+chain_stream_kernel(const ChainParams P) {
+    constexpr int WT = kStreamTile;
+    constexpr bool U8 = IN == DDM_IN_CU8;
+    constexpr int ES = U8 ? 2 : 8;                 // bytes per input sample
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int S = P.stages;
+    const int kStreamWarps = blockDim.x >> 5, kStreamThreads = blockDim.x;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int D = P.D, DP = P.DP;
+    // ---- shared memory carve-up: barriers | taps | rotator tables | per-warp rings ----
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw) + warp * S;      // this warp's S barriers
+    float *s_taps = reinterpret_cast<float *>(smem_raw + ((8u * kStreamWarps * S + 127u) & ~127u));   // Q*DP taps
+    float *s_rx = s_taps + Q * DP;                                           // DP: cos
+    float2 *s_ry = reinterpret_cast<float2 *>(s_rx + DP);                    // DP: (sin, -sin)
+    float2 *s_c = s_ry + DP;                                                 // DP: 0.5 (1+j) rot (u8 input)
+    const size_t stage_bytes = stream_stage_bytes(D, IN);
+    unsigned char *ring = smem_raw + stream_fixed_bytes(Q, DP, kStreamWarps, S) + static_cast<size_t>(warp) * S * stage_bytes;
+
+    if (lane == 0) {
+        for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < Q * DP; i += kStreamThreads) s_taps[i] = P.taps[i];
+    for (int i = tid; i < DP; i += kStreamThreads) {
+        const float2 r = P.rot[i];          // (cos, -sin) = exp(-j 2 pi r a)
+        s_rx[i] = r.x;
+        s_ry[i] = make_float2(-r.y, r.y);
+        s_c[i] = make_float2(0.5f * (r.x - r.y), 0.5f * (r.x + r.y));
+    }
+    __syncthreads();                          // the only CTA barrier: tables and barriers are set up
+
+    // ---- this warp's range of the global tile sequence (captures back to back) ----
+    const long long NTC = P.num_tiles;                      // tiles per capture, warm-up tile 0 included
+    const long long TT = NTC * P.batch;
+    const long long nwarps = P.stream_warps;
+    const long long gw = static_cast<long long>(blockIdx.x) * kStreamWarps + warp;
+    if (gw >= nwarps) return;
+    const long long G0 = gw * TT / nwarps, G1 = (gw + 1) * TT / nwarps;
+    if (G0 >= G1) return;
+    long long cap = G0 / NTC;
+    long long tile = G0 - cap * NTC;
+    if (tile > 0) tile -= 1;                                // warm up on the tile before the range
+    long long g = cap * NTC + tile;                         // global id of the tile being consumed
+    long long icap = cap, itile = tile, ig = g;             // ... and of the next tile to issue
+
+    const long long n_even = P.n & ~1LL;
+    const long long end_all = P.b0 + P.M * D;               // end of the last needed block
+    const long long H = P.H;
+
+    // lane 0: start the bulk copies that fill `stage` with tile (c, t)
+    auto issue = [&](long long c, long long t, int stage) {
+        unsigned char *dst = ring + stage * stage_bytes;
+        const long long S0 = P.b0 + (t - 1) * (static_cast<long long>(WT) * D);   // first sample (may be < 0)
+        long long E = S0 + static_cast<long long>(WT) * D;
+        if (E > end_all) E = end_all;
+        uint32_t bytes = 0;
+        if (U8) {
+            const unsigned char *xb = static_cast<const unsigned char *>(P.x) + c * P.x_stride * 2;
+            const unsigned char *hb = static_cast<const unsigned char *>(P.halo);
+            const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;          // floor to 8 samples = 16 B
+            const long long Ea = (E >= 0 ? E + 7 : E) / 8 * 8;              // ceil to 8 samples
+            const long long n8 = P.n & ~7LL;
+            const long long h_beg = S0a > -H ? S0a : -H;                    // nothing older than the halo exists
+            const long long h_end = Ea < 0 ? Ea : 0;
+            const long long c_beg = S0a > 0 ? S0a : 0;
+            const long long c_end = Ea < n8 ? Ea : n8;
+            if (h_end > h_beg) bytes += static_cast<uint32_t>((h_end - h_beg) * 2);
+            if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 2);
+            // tail: the last n % 8 samples of the chunk and the pad behind them (zero-tap positions)
+            const long long t_beg = c_beg > n8 ? c_beg : n8;
+            for (long long i = t_beg; i < E; ++i) {
+                dst[(i - S0a) * 2] = i < P.n ? xb[2 * i] : 128;
+                dst[(i - S0a) * 2 + 1] = i < P.n ? xb[2 * i + 1] : 128;
+            }
+            mbar_arrive_expect_tx(&mbar[stage], bytes);
+            if (h_end > h_beg)
+                bulk_g2s(dst + (h_beg - S0a) * 2, hb + (H + h_beg) * 2, static_cast<uint32_t>((h_end - h_beg) * 2),
+                         &mbar[stage]);
+            if (c_end > c_beg)
+                bulk_g2s(dst + (c_beg - S0a) * 2, xb + c_beg * 2, static_cast<uint32_t>((c_end - c_beg) * 2),
+                         &mbar[stage]);
+            return;
+        }
+        const float2 *xf = static_cast<const float2 *>(P.x) + c * P.x_stride;
+        const float2 *hf = static_cast<const float2 *>(P.halo);
+        const long long Eu = E + (E & 1);          // odd D: an odd end is rounded up (16-byte copies)
+        const long long h_beg = S0 > -H ? S0 : -H;
+        const long long h_end = Eu < 0 ? Eu : 0;
+        const long long c_beg = S0 > 0 ? S0 : 0;
+        const long long c_end = Eu < n_even ? Eu : n_even;
+        if (h_end > h_beg) bytes += static_cast<uint32_t>((h_end - h_beg) * 8);
+        if (c_end > c_beg) bytes += static_cast<uint32_t>((c_end - c_beg) * 8);
+        // tail: the odd last sample of the chunk and the zero pad behind it
+        const long long t_beg = c_beg > n_even ? c_beg : n_even;
+        for (long long i = t_beg; i < E; ++i)
+            reinterpret_cast<float2 *>(dst)[i - S0] = i < P.n ? xf[i] : make_float2(0.f, 0.f);
+        mbar_arrive_expect_tx(&mbar[stage], bytes);
+        if (h_end > h_beg)
+            bulk_g2s(dst + (h_beg - S0) * 8, hf + (H + h_beg), static_cast<uint32_t>((h_end - h_beg) * 8), &mbar[stage]);
+        if (c_end > c_beg)
+            bulk_g2s(dst + (c_beg - S0) * 8, xf + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8), &mbar[stage]);
+    };
+    auto advance = [&](long long &c, long long &t, long long &gid) {
+        ++gid;
+        if (++t == NTC) {
+            t = 0;
+            ++c;
+        }
+    };
+
+    if (lane == 0) {
+        for (int i = 0; i < S && ig < G1; ++i) {
+            issue(icap, itile, i);
+            advance(icap, itile, ig);
+        }
+    }
+    // (the other lanes keep their copy of the issue iterator in step without issuing)
+    if (lane != 0)
+        for (int i = 0; i < S && ig < G1; ++i) advance(icap, itile, ig);
+
+    float2 prev[Q];                     // this lane's partial sums of the previous tile
+#pragma unroll
+    for (int q = 0; q < Q; ++q) prev[q] = make_float2(0.f, 0.f);
+    float2 y_last = make_float2(0.f, 0.f);       // this lane's y of the previous tile (lane 31's feeds the discriminator)
+    int stage = 0;
+    uint32_t parity = 0;
+
+    for (; g < G1; advance(cap, tile, g)) {
+        mbar_wait(&mbar[stage], parity);
+
+        const long long jblk = (tile - 1) * WT + lane;      // this lane's block index (tile 0: -32 .. -1)
+        float2 cur[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) cur[q] = make_float2(0.f, 0.f);
+        if (jblk < P.M) {
+            size_t sp_off = static_cast<size_t>(lane) * D * ES;
+            if (U8) {
+                const long long S0 = P.b0 + (tile - 1) * (static_cast<long long>(WT) * D);
+                const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;
+                sp_off += static_cast<size_t>(S0 - S0a) * 2;         // shift of the aligned copy (even)
+            }
+            const unsigned char *sp = ring + stage * stage_bytes + sp_off;
+            unsigned long long acc[Q];
+            chain_accumulate<Q, MIX, U8>(sp, D, DP, P.a_lastq, s_taps, s_rx, s_ry, s_c, acc);
+            float2 w0 = make_float2(1.f, 0.f);
+            if (MIX) w0 = phase_rotator(P.r_hi, P.r_lo, P.n0 + P.b0 + jblk * D);   // global index of the block start
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float2 p = unpack_f32x2(acc[q]);
+                cur[q] = MIX ? cmul(p, w0) : p;
+            }
+        }
+        // the stage has been read by every lane: re-arm it with the tile S steps ahead
+        __syncwarp();
+        if (ig < G1) {
+            if (lane == 0) {
+                fence_proxy_async();
+                issue(icap, itile, stage);
+            }
+            advance(icap, itile, ig);
+        }
+        if (++stage == S) {
+            stage = 0;
+            parity ^= 1u;
+        }
+
+        // ---- y[m] = sum_q P_q[m - q]: lane l takes P_q from lane l-q (this tile) or, for l < q, from
+        // lane 32+l-q of the previous tile; source lane s therefore offers cur when s < 32-q ----
+        float2 y = cur[0];
+#pragma unroll
+        for (int q = 1; q < Q; ++q) {
+            const float2 v = lane < WT - q ? cur[q] : prev[q];
+            y.x += __shfl_sync(0xffffffffu, v.x, (lane - q) & 31);
+            y.y += __shfl_sync(0xffffffffu, v.y, (lane - q) & 31);
+        }
+#pragma unroll
+        for (int q = 1; q < Q; ++q) prev[q] = cur[q];
+        const long long m = (tile - 1) * WT + lane;
+        const bool emit = tile >= 1 && g >= G0 && m < P.M;
+        if (OUT == DDM_CHAIN_OUT_IQ) {
+            if (emit) reinterpret_cast<float2 *>(P.out)[cap * P.out_stride + m] = y;
+        } else {
+            const float2 v = lane == 31 ? y_last : y;
+            const float2 yp = make_float2(__shfl_sync(0xffffffffu, v.x, (lane - 1) & 31),
+                                          __shfl_sync(0xffffffffu, v.y, (lane - 1) & 31));
+            y_last = y;
+            if (emit && (m > 0 || P.has_prev)) {
+                const float re = fmaf(y.x, yp.x, y.y * yp.y);
+                const float im = fmaf(y.y, yp.x, -y.x * yp.y);
+                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
+            }
+        }
     }
 }
 
@@ -639,7 +888,10 @@ struct ddm_chain {
     int H = 0, DP = 0;
     int Q[2] = {0, 0};
     int a_lastq[2] = {0, 0};
-    int per_sm[2] = {0, 0};                  // resident CTAs per SM of the fused kernel, per s
+    int per_sm[2] = {0, 0};                  // resident CTAs per SM of the CTA-tiled kernel, per s
+    bool stream = false;                     // warp-autonomous kernel (chain_stream_kernel) usable
+    int st_warps = 0, st_stages = 0;         // its geometry: warps per CTA (one CTA per SM), ring depth per warp
+    bool st_attr[2] = {false, false};        // dynamic shared memory attribute set, per s
     float *d_taps[2] = {nullptr, nullptr};   // [Q][DP] for s = 0, 1
     double *d_taps_lin = nullptr;            // K
     double2 *d_ctaps = nullptr;              // K: taps[k] exp(+j 2 pi r k), general path with mixer
@@ -671,8 +923,64 @@ size_t chain_smem_bytes(int Q, int D, int DP, int in_format = DDM_IN_CF32) {
     return fixed + kChainStages * stage;
 }
 
+// Geometry of the warp-autonomous kernel for one (D, input format): W warps (one CTA per SM), each with a
+// private ring of S stages of 32 blocks.  The rings take what shared memory there is: bytes in flight
+// are what the HBM stream needs (scripts/microbench/readbw2.cu), so prefer S >= 3 and then as many
+// warps as fit, down to one warp with two stages for very long blocks.
+bool stream_geometry(int Q, int D, int DP, int in_format, int *warps, int *stages) {
+    const size_t stage = stream_stage_bytes(D, in_format);
+    const size_t budget = 227 * 1024;
+    int forced_w = 0, forced_s = 0;
+    if (const char *e = std::getenv("DDM_STREAM_WARPS")) forced_w = std::atoi(e);      // tuning knobs (bench only)
+    if (const char *e = std::getenv("DDM_STREAM_STAGES")) forced_s = std::atoi(e);
+    auto fits = [&](int w, int s_) { return stream_fixed_bytes(Q, DP, w, s_) + stage * w * s_ <= budget; };
+    if (forced_w > 0 && forced_s > 0) {
+        if (forced_w > kStreamMaxWarps || forced_s > kStreamMaxStages || forced_s < 2 || !fits(forced_w, forced_s)) return false;
+        *warps = forced_w;
+        *stages = forced_s;
+        return true;
+    }
+    const int want[] = {8, 6, 4, 3, 2, 1};
+    for (int min_s = 3; min_s >= 2; --min_s)
+        for (int w : want) {
+            int s_ = kStreamMaxStages;
+            while (s_ >= min_s && !fits(w, s_)) --s_;
+            if (s_ >= min_s) {
+                *warps = w;
+                *stages = s_ > 4 && in_format != DDM_IN_CU8 ? 4 : s_;
+                return true;
+            }
+        }
+    return false;
+}
+
+template <int Q, bool MIX, int OUT, int IN>
+int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
+    ChainParams p = p0;
+    const int W = c->st_warps, S = c->st_stages;
+    const size_t smem = stream_fixed_bytes(Q, c->DP, W, S) + stream_stage_bytes(c->D, IN) * W * S;
+    auto kern = chain_stream_kernel<Q, MIX, OUT, IN>;
+    if (!c->st_attr[p.s]) {   // first launch of this variant on this handle's device
+        DDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        c->st_attr[p.s] = true;
+    }
+    p.stages = S;
+    p.num_tiles = 1 + (p.M + kStreamTile - 1) / kStreamTile;        // per capture, warm-up tile 0 included
+    const long long total_tiles = p.num_tiles * p.batch;
+    long long warps = static_cast<long long>(c->sms) * W;
+    if (warps > total_tiles / kStreamMinTiles) warps = total_tiles / kStreamMinTiles;
+    if (warps < 1) warps = 1;
+    p.stream_warps = warps;
+    const unsigned grid = static_cast<unsigned>((warps + W - 1) / W);
+    kern<<<grid, 32 * W, smem, st>>>(p);
+    DDM_CUDA(cudaGetLastError());
+    count_launch();
+    return DDM_OK;
+}
+
 template <int Q, bool MIX, int OUT, int IN>
 int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
+    if (c->stream) return launch_stream_q<Q, MIX, OUT, IN>(c, p, st);
     const size_t smem = chain_smem_bytes(Q, c->D, c->DP, IN);
     auto kern = chain_fused_kernel<Q, MIX, OUT, IN>;
     int &per_sm = c->per_sm[p.s];
@@ -835,8 +1143,11 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     const int qmax = (K + 1 + D - 1) / D;
     c->DP = (D + 3) & ~3;
     c->es = in_format == DDM_IN_CU8 ? 2 : 8;
-    c->fast = D >= 2 && qmax <= kChainMaxQ &&
-              chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024;
+    const bool legacy = std::getenv("DDM_CHAIN_LEGACY") != nullptr;         // A/B against the CTA-tiled kernel
+    c->stream = !legacy && D >= 2 && qmax <= kChainMaxQ &&
+                stream_geometry(qmax, D, c->DP, in_format, &c->st_warps, &c->st_stages);
+    c->fast = c->stream || (D >= 2 && qmax <= kChainMaxQ &&
+                            chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024);
     // halo: the Q (odd D: up to Q + 1) leading blocks of a tile plus one block of slack
     c->H = (qmax + 1 + (D & 1)) * D;
     if (c->H & 1) c->H += 1;

@@ -186,10 +186,26 @@ struct SmallDft<25, DIR> {
 // one Stockham radix-R pass over `batch` rows of length m (grid.y = row):
 //   v[r] = in[j + r m/R] * w^(r k),  k = j mod Ns,  w = exp(-+2 pi i / (Ns R));  DFT_R;
 //   out[(j - k) R + k + r Ns] = v[r]
-template <int R, int DIR>
+//
+// IO selects what the first / last pass of a transform fuses (the Hilbert envelope of real chunks,
+// two chunks per complex transform -- see ddm_am_hilbert):
+//   kIoPlain     double2 in, double2 out
+//   kIoLoadPair  first pass: row p reads the real chunks 2p (-> re) and 2p+1 (-> im) as f32
+//   kIoHilbert   last forward pass: bin k is multiplied by -i sgn(k) / n (0 for k = 0 and the Nyquist bin)
+//   kIoAbsPair   last inverse pass: out_a = hypot(x_a, re), out_b = hypot(x_b, im) as f32
+constexpr int kIoPlain = 0, kIoLoadPair = 1, kIoHilbert = 2, kIoAbsPair = 3;
+struct PassIo {
+    const float *x;         // the real chunks, chunk c at x + c * len
+    float *env;             // the envelopes, same layout
+    long long len;          // chunk length (= m)
+    long long chunks;       // number of chunks (the last pair may lack its second one)
+    double scale;
+};
+
+template <int R, int DIR, int IO = kIoPlain>
 __global__ void __launch_bounds__(R >= 16 ? 128 : 256)
 fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ tw, int m,
-         int Ns) {
+         int Ns, const PassIo io = PassIo{}) {
     const int q = m / R;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= q) return;
@@ -199,8 +215,18 @@ fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double
     const int k = j % Ns;
     const int step = q / Ns;                 // m / (R Ns)
     double2 v[R];
+    const long long ca = 2LL * blockIdx.y, cb = ca + 1;          // the pair's chunks (IO modes)
+    if (IO == kIoLoadPair) {
+        const float *xa = io.x + ca * io.len;
+        const float *xb = io.x + cb * io.len;
+        const bool has_b = cb < io.chunks;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = in[j + r * q];
+        for (int r = 0; r < R; ++r)
+            v[r] = make_double2(static_cast<double>(xa[j + r * q]), has_b ? static_cast<double>(xb[j + r * q]) : 0.0);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[j + r * q];
+    }
     if (k != 0) {
 #pragma unroll
         for (int r = 1; r < R; ++r) {
@@ -210,8 +236,35 @@ fft_pass(const double2 *__restrict__ in, double2 *__restrict__ out, const double
     }
     SmallDft<R, DIR>::run(v);
     const int j0 = (j - k) * R + k;
+    if (IO == kIoHilbert) {
+        // -i sgn(k) X[k] / n: the spectrum of the Hilbert transforms of both packed chunks at once
+        // (H is a real operator: ifft gives H{x_a} + i H{x_b}); scipy.signal.hilbert's mask minus one
 #pragma unroll
-    for (int r = 0; r < R; ++r) out[j0 + r * Ns] = v[r];
+        for (int r = 0; r < R; ++r) {
+            const int o = j0 + r * Ns;
+            double2 w = make_double2(0.0, 0.0);
+            if (o != 0 && 2 * o != m) {
+                const double sc = io.scale;
+                w = 2 * o < m ? make_double2(v[r].y * sc, -v[r].x * sc) : make_double2(-v[r].y * sc, v[r].x * sc);
+            }
+            out[o] = w;
+        }
+    } else if (IO == kIoAbsPair) {
+        const float *xa = io.x + ca * io.len;
+        const float *xb = io.x + cb * io.len;
+        float *ea = io.env + ca * io.len;
+        float *eb = io.env + cb * io.len;
+        const bool has_b = cb < io.chunks;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int o = j0 + r * Ns;
+            ea[o] = static_cast<float>(hypot(static_cast<double>(xa[o]), v[r].x));
+            if (has_b) eb[o] = static_cast<float>(hypot(static_cast<double>(xb[o]), v[r].y));
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[j0 + r * Ns] = v[r];
+    }
 }
 
 // buf[row][k] *= bfft[k]
@@ -415,12 +468,27 @@ std::vector<int> smooth_radices(long long n) {
     return r;
 }
 
-template <int R, int DIR>
-void launch_pass(double2 *in, double2 *out, const double2 *tw, int m, int Ns, int batch, cudaStream_t st) {
+template <int R, int DIR, int IO = kIoPlain>
+void launch_pass(double2 *in, double2 *out, const double2 *tw, int m, int Ns, int batch, cudaStream_t st,
+                 const PassIo &io = PassIo{}) {
     const int threads = R >= 16 ? 128 : 256;
     const dim3 grid((m / R + threads - 1) / threads, batch);
-    fft_pass<R, DIR><<<grid, threads, 0, st>>>(in, out, tw, m, Ns);
+    fft_pass<R, DIR, IO><<<grid, threads, 0, st>>>(in, out, tw, m, Ns, io);
     count_launch();
+}
+
+template <int DIR, int IO>
+void launch_pass_r(int R, double2 *in, double2 *out, const double2 *tw, int m, int Ns, int batch, cudaStream_t st,
+                   const PassIo &io) {
+    switch (R) {
+        case 2: launch_pass<2, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 3: launch_pass<3, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 4: launch_pass<4, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 5: launch_pass<5, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 8: launch_pass<8, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 16: launch_pass<16, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+        case 25: launch_pass<25, DIR, IO>(in, out, tw, m, Ns, batch, st, io); break;
+    }
 }
 
 // batched FFT of a 2-3-5 smooth size m, rows in bufs[cur]; returns the index of the buffer holding
@@ -562,6 +630,51 @@ int dft_rows(ddm_fft *c, FftPlan *p, const void *src, long long src_stride, int 
     return DDM_OK;
 }
 
+// Hilbert envelope of `chunks` real chunks of a 2-3-5 smooth length, two chunks per complex transform,
+// load / spectrum edit / envelope fused into the first and last passes: 2 x passes launches, each one
+// read + one write of the packed rows.  (A length with a single radix would need both fusions in one
+// pass; such chunks take the general route.)
+int hilbert_pairs(ddm_fft *c, FftPlan *p, const float *x, float *env, long long len, long long chunks,
+                  cudaStream_t st) {
+    const int m = p->m;
+    const long long pairs_total = (chunks + 1) / 2;
+    long long rows_per = std::max<long long>(1, (64LL << 20) / (2 * static_cast<long long>(m)));
+    rows_per = std::min<long long>(rows_per, 65535);
+    const int np = static_cast<int>(p->radices.size());
+    for (long long p0 = 0; p0 < pairs_total; p0 += rows_per) {
+        const int batch = static_cast<int>(std::min<long long>(rows_per, pairs_total - p0));
+        int rc = ensure_ws(c, static_cast<size_t>(m) * batch, st);
+        if (rc != DDM_OK) return rc;
+        PassIo io;
+        io.x = x + 2 * p0 * len;
+        io.env = env + 2 * p0 * len;
+        io.len = len;
+        io.chunks = chunks - 2 * p0;
+        io.scale = 1.0 / static_cast<double>(len);
+        int cur = 0, Ns = 1;
+        for (int i = 0; i < np; ++i) {                       // forward
+            const int R = p->radices[i];
+            double2 *in = c->d_ws[cur], *out = c->d_ws[cur ^ 1];
+            if (i == 0) launch_pass_r<1, kIoLoadPair>(R, in, out, p->d_tw, m, Ns, batch, st, io);
+            else if (i == np - 1) launch_pass_r<1, kIoHilbert>(R, in, out, p->d_tw, m, Ns, batch, st, io);
+            else launch_pass_r<1, kIoPlain>(R, in, out, p->d_tw, m, Ns, batch, st, io);
+            cur ^= 1;
+            Ns *= R;
+        }
+        Ns = 1;
+        for (int i = 0; i < np; ++i) {                       // inverse
+            const int R = p->radices[i];
+            double2 *in = c->d_ws[cur], *out = c->d_ws[cur ^ 1];
+            if (i == np - 1) launch_pass_r<-1, kIoAbsPair>(R, in, out, p->d_tw, m, Ns, batch, st, io);
+            else launch_pass_r<-1, kIoPlain>(R, in, out, p->d_tw, m, Ns, batch, st, io);
+            cur ^= 1;
+            Ns *= R;
+        }
+    }
+    DDM_CUDA(cudaGetLastError());
+    return DDM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -622,6 +735,11 @@ int ddm_am_hilbert(ddm_fft *c, const void *x_dev, int64_t n, int64_t chunk, void
         FftPlan *p = nullptr;
         int rc = get_plan(c, pt.len, st, &p);
         if (rc != DDM_OK) return rc;
+        if (p->pow2 && p->radices.size() >= 2) {
+            rc = hilbert_pairs(c, p, x + pt.start, out + pt.start, pt.len, pt.rows, st);
+            if (rc != DDM_OK) return rc;
+            continue;
+        }
         // sub-batches keep the workspace below ~1 GiB
         int64_t rows_per = std::max<int64_t>(1, (64LL << 20) / (2 * static_cast<int64_t>(p->m)));
         rows_per = std::min<int64_t>(rows_per, 65535);

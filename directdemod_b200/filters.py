@@ -331,6 +331,77 @@ class remez(filter):
         super().__init__(signal.remez(ntaps, edges, gains, fs=Fs), [1], storeState, zeroPhase, initOut)
 
 
+class cascade(filter):
+    """Several stateful linear filters applied back to back, ``x -> f1 -> f2 -> ...`` (what
+    ``sig.filter(f1).filter(f2)`` does in the reference, comm.py:80-92 + filters.py:64-70), as ONE
+    filter -- an addition to the reference's API for long streams.
+
+    A stable IIR stage forgets: its impulse response falls below any tolerance after a few hundred
+    samples.  The cascade's impulse response h = h1 * h2 * ... is therefore, to ``tol`` of its
+    absolute sum, a FINITE sequence, and the whole cascade is one FIR filter with taps h[:K] -- which
+    the library applies by overlap-save FFT in a single pass over the signal (csrc/filter.cu,
+    fir_fft_kernel): BASELINE configs[3]'s 1023-tap Remez followed by an 8th-order Butterworth becomes
+    one 1172-tap filter (tol = 1e-9), and the intermediate signal never exists.  The reference's
+    per-stage initial conditions (every stage starts from its own unscaled ``lfilter_zi``,
+    filters.py:45) are carried over exactly: the zero-input response of those states through the
+    cascade is the equivalent filter's initial delay line.  Coefficient work (impulse and zero-input
+    responses, float64 scipy) stays on the host like all filter design.
+
+    Raises ValueError when a stage is not a stateful LTI filter or the cascade does not die out
+    within ``max_taps`` samples."""
+
+    def __init__(self, filts, tol=1e-9, max_taps=2049):
+        filts = list(filts)
+        if not filts:
+            raise ValueError("Atleast one filter must be given")
+        for f in filts:
+            if not isinstance(f, filter) or f._zeroPhase or not f._storeState or f._initOut is not None:
+                raise ValueError("a cascade is made of stateful filters (no zeroPhase, no initOut)")
+        self._stages = filts
+        span = 4 * max_taps
+        h = np.zeros(span)
+        h[0] = 1.0
+        zir = np.zeros(span)
+        for f in filts:
+            bb, aa = np.asarray(f._b, dtype=np.float64), np.atleast_1d(np.asarray(f._a, dtype=np.float64))
+            h = signal.lfilter(bb, aa, h)
+            if max(len(bb), len(aa)) > 1:
+                zir, _ = signal.lfilter(bb, aa, zir, zi=signal.lfilter_zi(bb, aa))
+            else:
+                zir = signal.lfilter(bb, aa, zir)
+        tail = np.cumsum(np.abs(h)[::-1])[::-1]
+        small = np.nonzero(tail <= tol * tail[0])[0]
+        if small.size == 0 or not np.all(np.isfinite(h)):
+            raise ValueError("the cascade's impulse response does not die out within %d samples" % span)
+        k = max(int(small[0]), 2)
+        # the zero-input response of the initial states must fit the equivalent filter's delay line too
+        zmax = np.max(np.abs(zir)) if zir.size else 0.0
+        if zmax > 0:
+            late = np.nonzero(np.abs(zir) > tol * zmax)[0]
+            if late.size:
+                k = max(k, int(late[-1]) + 2)
+        if k > max_taps:
+            raise ValueError("the cascade needs %d equivalent taps (limit %d)" % (k, max_taps))
+        self._zir = zir[:k - 1].astype(np.complex128)
+        super().__init__(h[:k].copy(), [1.0], storeState=True)
+
+    @property
+    def stages(self):
+        return list(self._stages)
+
+    def _handle(self, dev=None):
+        fresh = self._h is None
+        h = super()._handle(dev)
+        if fresh and self._h is not None and not self._used:
+            # every stage starts from its own lfilter_zi (filters.py:45), not from the equivalent
+            # filter's all-ones history
+            self.setState(self._zir)
+        return h
+
+    def lookback(self):
+        return self._bd.size - 1
+
+
 class blackmanHarrisConv:
     """Blackman-Harris by 'same' convolution (filters.py:145-174); stateless.
 

@@ -158,8 +158,19 @@ class TimeShardedFilters:
     materialised -- and keep the slab part: by then the zero-input response of every stage has
     decayed below one ulp.  A filter that only runs as a sequential replay raises at construction."""
 
-    def __init__(self, filts, n_samples, rank, world, group=None):
+    def __init__(self, filts, n_samples, rank, world, group=None, fuse=True):
+        """``fuse``: run the cascade as ONE equivalent filter (filters.cascade: the stages' combined
+        impulse response, dead to 1e-9 after a finite number of taps, applied by overlap-save FFT in a
+        single pass) when the stages allow it; the halo is then that filter's taps - 1."""
         self.filts = list(filts)
+        self.fused = False
+        if fuse and len(self.filts) > 1:
+            from . import filters as _filters
+            try:
+                self.filts = [_filters.cascade(self.filts)]
+                self.fused = True
+            except ValueError:
+                pass
         self.rank, self.world, self.group = int(rank), int(world), group
         self.halo_len = int(sum(f.lookback() for f in self.filts)) if world > 1 else 0
         self.bounds = slab_bounds(n_samples, world, 1)

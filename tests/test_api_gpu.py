@@ -722,3 +722,32 @@ def test_filter_follows_the_device_of_its_input():
     g.applyOn(torch.from_numpy(x).cuda(0))
     with pytest.raises(ValueError):
         g.applyOn(torch.from_numpy(x).to("cuda:1"))
+
+
+def test_cascade_runs_as_one_filter_and_matches_the_stage_by_stage_reference():
+    """filters.cascade on the device: C4's remez-1023 -> butter-8 as ONE overlap-save pass, chunked
+    with carried state, against scipy run stage by stage like the reference (filters.py:64-70)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    from directdemod_b200 import _lib
+    fs = 2400000
+    rng = np.random.default_rng(41)
+    n = 2500000
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    fir = filters.remez(fs, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023)
+    iir = filters.butter(fs, 100000, n=8)
+    want = x.astype(np.complex128)
+    for f in (fir, iir):
+        want, _ = sps.lfilter(f.getB, f.getA, want, zi=sps.lfilter_zi(f.getB, f.getA))
+    cas = filters.cascade([fir, iir])
+    l0 = _lib.launch_count()
+    got = np.concatenate([cas.applyOn(x[a:b]) for a, b in ((0, 1200000), (1200000, 1200700), (1200700, n))])
+    assert got.shape == want.shape and O.rel_rms(got, want) <= TOL
+    assert O.rel_rms(got[:3000], want[:3000]) <= TOL          # the stages' initial conditions
+    assert _lib.launch_count() - l0 <= 8                       # one filter launch + one state launch per chunk
+    # real signals too
+    xr = rng.standard_normal(1300000).astype(np.float32)
+    wr = xr.astype(np.float64)
+    for f in (fir, iir):
+        wr, _ = sps.lfilter(f.getB, f.getA, wr, zi=sps.lfilter_zi(f.getB, f.getA))
+    assert O.rel_rms(filters.cascade([fir, iir]).applyOn(xr), wr) <= TOL

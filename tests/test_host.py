@@ -245,3 +245,31 @@ def test_reference_arm_runs_the_staged_unmodified_reference(tmp_path):
     assert got.signal.shape == want.shape and np.array_equal(got.signal, want)
     assert bench._cpu_step(1) > 0
     bench._CPU.clear()
+
+
+def test_cascade_equivalent_filter_reproduces_the_stage_by_stage_result():
+    """filters.cascade (host part): the equivalent FIR taps and initial delay line of the C4 cascade
+    (remez-1023 -> butter-8, BASELINE configs[3]) reproduce scipy's stage-by-stage stateful result
+    (each stage from its own lfilter_zi, filters.py:45,69) far below the 1e-5 tolerance."""
+    import scipy.signal as sps
+    from directdemod_b200 import constants, filters
+    fs = 2400000
+    fir = filters.remez(fs, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023)
+    iir = filters.butter(fs, 100000, n=8)
+    cas = filters.cascade([fir, iir])
+    assert cas.isFIR and 1023 < len(cas.getB) < 1400 and cas.lookback() == len(cas.getB) - 1
+    rng = np.random.default_rng(3)
+    x = ((rng.standard_normal(60000) + 1j * rng.standard_normal(60000)) * 40).astype(np.complex64).astype(np.complex128)
+    want = x
+    for f in (fir, iir):
+        want, _ = sps.lfilter(f.getB, f.getA, want, zi=sps.lfilter_zi(f.getB, f.getA))
+    got, _ = sps.lfilter(cas.getB, [1.0], x, zi=cas._zir)
+    err = np.sqrt(np.mean(np.abs(got - want) ** 2) / np.mean(np.abs(want) ** 2))
+    assert err <= 1e-8, err
+    # not a cascade: zero-phase stages, filters that never die out
+    with pytest.raises(ValueError):
+        filters.cascade([fir, filters.butter(fs, 100000, n=8, zeroPhase=True)])
+    with pytest.raises(ValueError):
+        filters.cascade([filters.filter([1.0], [1.0, -1.0])])               # integrator: pole on the unit circle
+    with pytest.raises(ValueError):
+        filters.cascade([filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP)], max_taps=64)
