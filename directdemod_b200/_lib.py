@@ -60,6 +60,7 @@ SIGNATURES = {
     "ddm_filter_reset": (_int, [_vp, _vp]),
     "ddm_filter_set_zi_base": (_int, [_vp, _pdbl]),
     "ddm_filter_set_iir_mode": (_int, [_vp, _int]),
+    "ddm_filter_set_iir_auto_floor": (_int, [_vp, _dbl]),
     "ddm_filter_set_fir_mode": (_int, [_vp, _int]),
     "ddm_filter_info": (_int, [_vp, _pint, _pi64, _pdbl]),
     "ddm_filter_apply_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp]),

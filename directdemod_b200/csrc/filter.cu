@@ -1116,6 +1116,7 @@ struct ddm_filter {
     long long warmup_fast = -1;     // ... matches to 1e-18: the warm-up of the DFMA modes
     double noise_floor = 0.0;       // relative roundoff noise of the float64 recursion itself
     int mode = 0;                   // DDM_IIR_AUTO / _PARALLEL / _SEQUENTIAL / _PARALLEL_EXACT
+    double auto_floor = 1e-7;       // AUTO replays sequentially above this measured roundoff floor
     int sms = 148;
     IirCoef coef;
 };
@@ -1343,7 +1344,7 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
     // AUTO: segment-parallel unless the filter's own roundoff floor would show at the 1e-5
     // parity tolerance, in which case only the sequential replay reproduces the reference
     const bool sequential = f->warmup < 0 || f->mode == DDM_IIR_SEQUENTIAL ||
-                            (f->mode == DDM_IIR_AUTO && f->noise_floor > 1e-7);
+                            (f->mode == DDM_IIR_AUTO && f->noise_floor > f->auto_floor);
     // the DFMA form goes through the warp-staged kernel when both pointers are 16-byte aligned
     static const bool no_staging = std::getenv("DDM_IIR_NO_STAGING") != nullptr;
     const bool staged = !sequential && f->mode != DDM_IIR_PARALLEL_EXACT && !no_staging &&
@@ -1702,6 +1703,12 @@ int ddm_filter_set_iir_mode(ddm_filter *f, int mode) {
                     mode == DDM_IIR_PARALLEL_EXACT,
                 "ddm_filter_set_iir_mode: bad mode %d", mode);
     f->mode = mode;
+    return DDM_OK;
+}
+
+int ddm_filter_set_iir_auto_floor(ddm_filter *f, double floor) {
+    DDM_REQUIRE(f != nullptr, "ddm_filter_set_iir_auto_floor: NULL handle");
+    f->auto_floor = floor > 0 ? floor : 1e-7;
     return DDM_OK;
 }
 

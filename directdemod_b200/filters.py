@@ -125,6 +125,19 @@ class filter:
         _lib.check(_lib.lib().ddm_filter_set_iir_mode(self._handle(), int(mode)), "ddm_filter_set_iir_mode")
         return self
 
+    def setIIRTolerance(self, floor):
+        """Where AUTO switches from segment-parallel to the sequential bit-exact replay: filters whose
+        measured float64 roundoff floor (``analysis()[1]``) exceeds ``floor`` are replayed.  The default
+        (1e-7) keeps every result within the 1e-5 parity tolerance of the reference's bits; a decoder
+        whose own tolerance is stated against scipy's float64 output -- which for the 12th-order
+        band-passes is itself only good to 4e-5 .. 3e-4 -- can raise it (decode_noaa.getImage and
+        afsk.front_end do) and stream such filters at HBM speed."""
+        self._unshare()
+        self._shard_floor = float(floor) if floor > 0 else 1e-7
+        _lib.check(_lib.lib().ddm_filter_set_iir_auto_floor(self._handle(), float(floor)),
+                   "ddm_filter_set_iir_auto_floor")
+        return self
+
     def analysis(self):
         """(warm-up length of the segment-parallel IIR, measured roundoff floor) -- host only,
         needs no device; (0, 0.0) for a FIR."""
@@ -142,7 +155,7 @@ class filter:
         if self.isFIR:
             return max(self._bd.size, self._ad.size) - 1
         w, nf = self.analysis()
-        if w < 0 or nf > 1e-7:
+        if w < 0 or nf > getattr(self, "_shard_floor", 1e-7):
             raise ValueError("this IIR runs as a sequential bit-exact replay (roundoff floor %.1e) and cannot "
                              "be time-sharded; shard it by independent units" % nf)
         return w

@@ -180,6 +180,13 @@ int ddm_filter_set_zi_base(ddm_filter *f, const double *zi_host);
 #define DDM_IIR_SEQUENTIAL 2
 #define DDM_IIR_PARALLEL_EXACT 3
 int ddm_filter_set_iir_mode(ddm_filter *f, int mode);
+/* The switch of DDM_IIR_AUTO: filters whose measured float64 roundoff floor (ddm_filter_info) is above
+ * `floor` replay the loop sequentially, the others run segment-parallel.  Default 1e-7: AUTO never
+ * gives up agreement with the reference that the 1e-5 parity tolerance could see.  A caller whose
+ * tolerance is stated against scipy's float64 result (which itself is only good to the filter's
+ * floor) may raise it -- e.g. 1e-3 lets the 12th-order band-passes of the decoders run parallel.
+ * floor <= 0 restores the default. */
+int ddm_filter_set_iir_auto_floor(ddm_filter *f, double floor);
 /* FIR execution path: direct register-tiled convolution (FP32-pipe bound, cost grows with the tap
  * count) or overlap-save through 4096-point FFTs in shared memory (HBM bound, up to 2049 taps).
  * AUTO takes the FFT path from 96 taps on. */

@@ -167,6 +167,15 @@ def test_iir_roundoff_floor_and_execution_modes(golden):
     refl, _ = sps.lfilter(b, a, xl, zi=sps.lfilter_zi(b, a))
     err = O.rel_rms(par.applyOn(xl), refl)
     assert err <= 10 * floor, (err, floor)
+    # the AUTO switch is a user-settable tolerance: raised above this filter's floor, AUTO runs it
+    # segment-parallel (same result as forcing mode 1); at the default it stays the bit-exact replay
+    tolr = filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP).setIIRTolerance(1e-2)
+    y_tol = tolr.applyOn(xl)
+    assert O.rel_rms(y_tol, refl) <= 10 * floor
+    assert np.array_equal(y_tol, filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP).setIIRMode(1).applyOn(xl))
+    assert tolr.lookback() > 0                                      # ... and may then be time-sharded
+    back = filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP).setIIRTolerance(1e-2).setIIRTolerance(0)
+    assert np.array_equal(back.applyOn(x).astype(np.float32), ref.astype(np.float32))
     # a well-conditioned filter: parallel by default and within the plain tolerance
     f8 = filters.butter(2400000, 100000, n=8)
     assert f8.info()[2] < 1e-7
