@@ -136,24 +136,24 @@ def test_accurate_sync_positions_bit_exact(apt_pass):
         assert list(map(int, got[:len(want)])) == list(map(int, want))
 
 
-def test_accurate_sync_32_windows_per_sync_word_bit_exact():
+def test_accurate_sync_32_windows_per_sync_word_bit_exact(tmp_path):
     """getAccurateSync on a 17.5 s pass: the first 32 windows of EACH sync word against the oracle
-    (decode_noaa.py:826-856 restated), the CPU windows computed by a pool of processes."""
-    import multiprocessing as mp
+    (decode_noaa.py:826-856 restated), the CPU windows computed by a pool of processes
+    (tests/oracle_pool.py, its own interpreter)."""
+    import subprocess
+    import sys
     from directdemod_b200 import decode_noaa
-    from tests.util import oracle_accurate_window
     fs = 2048000
     x = apt_iq(17, 17.5, fs=fs)
     dec = decode_noaa.decode_noaa(ArraySource(x, fs), 30000.0)
     res = dec.getAccurateSync()
     asyncA, asyncB = res[0], res[4]
     taps = O.taps_blackman_harris(151)[0]
-    parts = oracle_chain(x, fs, 30000.0, taps, 60000, list(range(0, len(x), 20000000)) + [len(x)])
-    audio, rate = parts
+    audio, rate = oracle_chain(x, fs, 30000.0, taps, 60000, list(range(0, len(x), 20000000)) + [len(x)])
     am = O.am_envelope_chunked(audio)
     width = int(3 * O.NOAA_T * 40 * fs)
-    jobs, owner = [], []
-    for bits, tag in ((O.NOAA_SYNCA, "A"), (O.NOAA_SYNCB, "B")):
+    windows, starts, which = [], [], []
+    for w, bits in enumerate((O.NOAA_SYNCA, O.NOAA_SYNCB)):
         crude, _ = O.find_syncs(am, rate, bits)
         cnt = 0
         for c in crude / rate * fs:
@@ -162,16 +162,23 @@ def test_accurate_sync_32_windows_per_sync_word_bit_exact():
                 continue
             if cnt == 32:
                 break
-            jobs.append((x[a:b].copy(), a, fs, bits))
-            owner.append(tag)
+            windows.append(x[a:b])
+            starts.append(a)
+            which.append(w)
             cnt += 1
-        assert cnt == 32, (tag, cnt)
-    with mp.get_context("spawn").Pool(min(16, os.cpu_count() or 1)) as pool:
-        want = pool.map(oracle_accurate_window, jobs, chunksize=2)
-    wantA = [w for w, t in zip(want, owner) if t == "A"]
-    wantB = [w for w, t in zip(want, owner) if t == "B"]
-    assert list(map(int, asyncA[:32])) == wantA
-    assert list(map(int, asyncB[:32])) == wantB
+        assert cnt == 32, (w, cnt)
+    jobs, out = str(tmp_path / "jobs.npz"), str(tmp_path / "out.npy")
+    np.savez(jobs, windows=np.stack(windows), starts=np.asarray(starts), which=np.asarray(which), fs=fs,
+             bits=np.asarray([O.NOAA_SYNCA, O.NOAA_SYNCB]))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # one BLAS thread per worker: numpy's direct convolution calls a threaded ddot per output sample,
+    # and a pool of processes each spinning up a thread team per call does not finish in hours
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    subprocess.run([sys.executable, "-m", "tests.oracle_pool", jobs, out, str(min(16, os.cpu_count() or 1))],
+                   cwd=root, check=True, timeout=900, env=env)
+    want = np.load(out)
+    assert list(map(int, asyncA[:32])) == [int(v) for v in want[:32]]
+    assert list(map(int, asyncB[:32])) == [int(v) for v in want[32:]]
 
 
 @pytest.mark.slow
