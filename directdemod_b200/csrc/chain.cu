@@ -71,7 +71,48 @@ struct ChainParams {
     int J;                 // outputs per tile (CTA-tiled kernel)
     long long stream_warps;   // warps that share the work (warp-autonomous kernel)
     int stages;               // ring depth per warp (warp-autonomous kernel)
+    double step_re, step_im;  // exp(-j 2 pi r 32 D): the block rotator's advance per warp tile
 };
+
+__device__ __forceinline__ double2 cmuld(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+
+// exp(-j 2 pi r g) in float64 (block rotators of the warp-autonomous kernel, rotators of the general path)
+__device__ __forceinline__ double2 phase_rotator_f64(double r_hi, double r_lo, long long g) {
+    const double gd = static_cast<double>(g);
+    const double p = r_hi * gd;
+    const double e = fma(r_hi, gd, -p);
+    double fr = p - rint(p);
+    fr += e + r_lo * gd;
+    double s, c;
+    sincospi(2.0 * fr, &s, &c);
+    return make_double2(c, -s);
+}
+
+// atan2f for the discriminator: |error| <= ~3 ulp like the library function, a third of its
+// instructions (one MUFU.RCP, a degree-8 polynomial in t^2 fitted to atan(t)/t on [0, 1], no
+// special-case ladder).  atan2(0, 0) = 0 like np.angle(0); NaN/Inf inputs give NaN.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = mn * __frcp_rn(mx);
+    t = mx == 0.f ? 0.f : t;
+    const float z = t * t;
+    float p = 2.931092439e-03f;
+    p = fmaf(p, z, -1.639302633e-02f);
+    p = fmaf(p, z, 4.321788567e-02f);
+    p = fmaf(p, z, -7.548755919e-02f);
+    p = fmaf(p, z, 1.066173221e-01f);
+    p = fmaf(p, z, -1.420892529e-01f);
+    p = fmaf(p, z, 1.999327745e-01f);
+    p = fmaf(p, z, -3.333310456e-01f);
+    p = fmaf(p, z, 9.999999872e-01f);
+    float r = p * t;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
 
 // ------------------------------------------------------------------------------------
 // The accumulation over the D samples of one block (both fused kernels): Q partial sums
@@ -405,7 +446,7 @@ chain_fused_kernel(const ChainParams P) {
                 }
                 const float re = fmaf(y.x, yp.x, y.y * yp.y);
                 const float im = fmaf(y.y, yp.x, -y.x * yp.y);
-                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
+                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = fast_atan2f(im, re);
             }
         }
         if (kChainEBufs == 1) __syncthreads();        // e_buf is reused by the next tile
@@ -457,25 +498,25 @@ chain_stream_kernel(const ChainParams P) {
     constexpr int ES = U8 ? 2 : 8;                 // bytes per input sample
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = P.stages;
-    const int kStreamWarps = blockDim.x >> 5, kStreamThreads = blockDim.x;
+    const int nw_cta = blockDim.x >> 5, nthreads = blockDim.x;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = P.D, DP = P.DP;
     // ---- shared memory carve-up: barriers | taps | rotator tables | per-warp rings ----
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw) + warp * S;      // this warp's S barriers
-    float *s_taps = reinterpret_cast<float *>(smem_raw + ((8u * kStreamWarps * S + 127u) & ~127u));   // Q*DP taps
+    float *s_taps = reinterpret_cast<float *>(smem_raw + ((8u * nw_cta * S + 127u) & ~127u));   // Q*DP taps
     float *s_rx = s_taps + Q * DP;                                           // DP: cos
     float2 *s_ry = reinterpret_cast<float2 *>(s_rx + DP);                    // DP: (sin, -sin)
     float2 *s_c = s_ry + DP;                                                 // DP: 0.5 (1+j) rot (u8 input)
-    const size_t stage_bytes = stream_stage_bytes(D, IN);
-    unsigned char *ring = smem_raw + stream_fixed_bytes(Q, DP, kStreamWarps, S) + static_cast<size_t>(warp) * S * stage_bytes;
+    const unsigned stage_bytes = static_cast<unsigned>(stream_stage_bytes(D, IN));
+    unsigned char *ring = smem_raw + stream_fixed_bytes(Q, DP, nw_cta, S) + static_cast<size_t>(warp) * S * stage_bytes;
 
     if (lane == 0) {
         for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < Q * DP; i += kStreamThreads) s_taps[i] = P.taps[i];
-    for (int i = tid; i < DP; i += kStreamThreads) {
+    for (int i = tid; i < Q * DP; i += nthreads) s_taps[i] = P.taps[i];
+    for (int i = tid; i < DP; i += nthreads) {
         const float2 r = P.rot[i];          // (cos, -sin) = exp(-j 2 pi r a)
         s_rx[i] = r.x;
         s_ry[i] = make_float2(-r.y, r.y);
@@ -484,36 +525,49 @@ chain_stream_kernel(const ChainParams P) {
     __syncthreads();                          // the only CTA barrier: tables and barriers are set up
 
     // ---- this warp's range of the global tile sequence (captures back to back) ----
-    const long long NTC = P.num_tiles;                      // tiles per capture, warm-up tile 0 included
-    const long long TT = NTC * P.batch;
+    const int NTC = static_cast<int>(P.num_tiles);          // tiles per capture, warm-up tile 0 included
+    const long long TT = static_cast<long long>(NTC) * P.batch;
     const long long nwarps = P.stream_warps;
-    const long long gw = static_cast<long long>(blockIdx.x) * kStreamWarps + warp;
+    const long long gw = static_cast<long long>(blockIdx.x) * nw_cta + warp;
     if (gw >= nwarps) return;
     const long long G0 = gw * TT / nwarps, G1 = (gw + 1) * TT / nwarps;
     if (G0 >= G1) return;
     long long cap = G0 / NTC;
-    long long tile = G0 - cap * NTC;
-    if (tile > 0) tile -= 1;                                // warm up on the tile before the range
-    long long g = cap * NTC + tile;                         // global id of the tile being consumed
-    long long icap = cap, itile = tile, ig = g;             // ... and of the next tile to issue
+    int tile = static_cast<int>(G0 - cap * NTC);
+    int skip = 0;                                           // tiles consumed before the first emitted one
+    if (tile > 0) {                                         // warm up on the tile before the range
+        tile -= 1;
+        skip = 1;
+    }
+    int todo = static_cast<int>(G1 - G0) + skip;            // tiles this warp consumes
+    long long icap = cap;                                   // the next tile to issue
+    int itile = tile, itodo = todo;
 
-    const long long n_even = P.n & ~1LL;
+    const long long tile_samples = static_cast<long long>(WT) * D;
+    const long long n_even = P.n & ~1LL, n8 = P.n & ~7LL;
     const long long end_all = P.b0 + P.M * D;               // end of the last needed block
     const long long H = P.H;
+    const long long lim_fast = U8 ? (end_all < n8 ? end_all : n8) : (end_all < n_even ? end_all : n_even);
 
-    // lane 0: start the bulk copies that fill `stage` with tile (c, t)
-    auto issue = [&](long long c, long long t, int stage) {
+    // lane 0: start the bulk copies that fill `stage` with tile t of capture c
+    auto issue = [&](long long c, int t, int stage) {
         unsigned char *dst = ring + stage * stage_bytes;
-        const long long S0 = P.b0 + (t - 1) * (static_cast<long long>(WT) * D);   // first sample (may be < 0)
-        long long E = S0 + static_cast<long long>(WT) * D;
-        if (E > end_all) E = end_all;
-        uint32_t bytes = 0;
+        const long long S0 = P.b0 + (t - 1) * tile_samples;                  // first sample (may be < 0)
         if (U8) {
             const unsigned char *xb = static_cast<const unsigned char *>(P.x) + c * P.x_stride * 2;
+            if (S0 >= 0 && ((S0 + tile_samples + 7) & ~7LL) <= lim_fast) {   // interior tile: one aligned copy
+                const long long S0a = S0 & ~7LL;
+                const uint32_t bytes = static_cast<uint32_t>((((S0 + tile_samples + 7) & ~7LL) - S0a) * 2);
+                mbar_arrive_expect_tx(&mbar[stage], bytes);
+                bulk_g2s(dst, xb + S0a * 2, bytes, &mbar[stage]);
+                return;
+            }
+            long long E = S0 + tile_samples;
+            if (E > end_all) E = end_all;
+            uint32_t bytes = 0;
             const unsigned char *hb = static_cast<const unsigned char *>(P.halo);
             const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;          // floor to 8 samples = 16 B
             const long long Ea = (E >= 0 ? E + 7 : E) / 8 * 8;              // ceil to 8 samples
-            const long long n8 = P.n & ~7LL;
             const long long h_beg = S0a > -H ? S0a : -H;                    // nothing older than the halo exists
             const long long h_end = Ea < 0 ? Ea : 0;
             const long long c_beg = S0a > 0 ? S0a : 0;
@@ -536,6 +590,14 @@ chain_stream_kernel(const ChainParams P) {
             return;
         }
         const float2 *xf = static_cast<const float2 *>(P.x) + c * P.x_stride;
+        if (S0 >= 0 && S0 + tile_samples <= lim_fast) {                       // interior tile: one copy
+            mbar_arrive_expect_tx(&mbar[stage], stage_bytes);
+            bulk_g2s(dst, xf + S0, stage_bytes, &mbar[stage]);
+            return;
+        }
+        long long E = S0 + tile_samples;
+        if (E > end_all) E = end_all;
+        uint32_t bytes = 0;
         const float2 *hf = static_cast<const float2 *>(P.halo);
         const long long Eu = E + (E & 1);          // odd D: an odd end is rounded up (16-byte copies)
         const long long h_beg = S0 > -H ? S0 : -H;
@@ -554,23 +616,31 @@ chain_stream_kernel(const ChainParams P) {
         if (c_end > c_beg)
             bulk_g2s(dst + (c_beg - S0) * 8, xf + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8), &mbar[stage]);
     };
-    auto advance = [&](long long &c, long long &t, long long &gid) {
-        ++gid;
-        if (++t == NTC) {
-            t = 0;
-            ++c;
-        }
-    };
 
-    if (lane == 0) {
-        for (int i = 0; i < S && ig < G1; ++i) {
-            issue(icap, itile, i);
-            advance(icap, itile, ig);
+    for (int i = 0; i < S && itodo > 0; ++i) {
+        if (lane == 0) issue(icap, itile, i);
+        --itodo;
+        if (++itile == NTC) {
+            itile = 0;
+            ++icap;
         }
     }
-    // (the other lanes keep their copy of the issue iterator in step without issuing)
-    if (lane != 0)
-        for (int i = 0; i < S && ig < G1; ++i) advance(icap, itile, ig);
+
+    // ---- block rotator exp(-j 2 pi r g), g = global index of this lane's block start.  Exact (float64
+    // sincospi of the double-double reduced phase) at every 64th tile of a capture; in between one
+    // float64 complex multiplication by the constant per-tile step.  A range that starts between two
+    // anchors repeats the multiplications from the anchor, so the value of a tile does not depend on
+    // how the stream was partitioned. ----
+    double2 wrot = make_double2(1.0, 0.0);
+    const double2 wstep = make_double2(P.step_re, P.step_im);
+    auto rot_exact = [&](int t) {
+        return phase_rotator_f64(P.r_hi, P.r_lo, P.n0 + P.b0 + (static_cast<long long>(t - 1) * WT + lane) * D);
+    };
+    if (MIX) {
+        const int anchor = tile & ~63;
+        wrot = rot_exact(anchor);
+        for (int t = anchor; t < tile; ++t) wrot = cmuld(wrot, wstep);
+    }
 
     float2 prev[Q];                     // this lane's partial sums of the previous tile
 #pragma unroll
@@ -579,43 +649,46 @@ chain_stream_kernel(const ChainParams P) {
     int stage = 0;
     uint32_t parity = 0;
 
-    for (; g < G1; advance(cap, tile, g)) {
+    for (int k = 0; k < todo; ++k) {
         mbar_wait(&mbar[stage], parity);
 
-        const long long jblk = (tile - 1) * WT + lane;      // this lane's block index (tile 0: -32 .. -1)
-        float2 cur[Q];
+        const long long jblk = static_cast<long long>(tile - 1) * WT + lane;      // tile 0: blocks -32 .. -1
+        unsigned long long acc[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) cur[q] = make_float2(0.f, 0.f);
+        for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
         if (jblk < P.M) {
-            size_t sp_off = static_cast<size_t>(lane) * D * ES;
+            unsigned sp_off = static_cast<unsigned>(lane) * D * ES;
             if (U8) {
-                const long long S0 = P.b0 + (tile - 1) * (static_cast<long long>(WT) * D);
+                const long long S0 = P.b0 + (tile - 1) * tile_samples;
                 const long long S0a = (S0 >= 0 ? S0 : S0 - 7) / 8 * 8;
-                sp_off += static_cast<size_t>(S0 - S0a) * 2;         // shift of the aligned copy (even)
+                sp_off += static_cast<unsigned>(S0 - S0a) * 2;               // shift of the aligned copy (even)
             }
-            const unsigned char *sp = ring + stage * stage_bytes + sp_off;
-            unsigned long long acc[Q];
-            chain_accumulate<Q, MIX, U8>(sp, D, DP, P.a_lastq, s_taps, s_rx, s_ry, s_c, acc);
-            float2 w0 = make_float2(1.f, 0.f);
-            if (MIX) w0 = phase_rotator(P.r_hi, P.r_lo, P.n0 + P.b0 + jblk * D);   // global index of the block start
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const float2 p = unpack_f32x2(acc[q]);
-                cur[q] = MIX ? cmul(p, w0) : p;
-            }
+            chain_accumulate<Q, MIX, U8>(ring + stage * stage_bytes + sp_off, D, DP, P.a_lastq, s_taps, s_rx, s_ry, s_c,
+                                         acc);
         }
         // the stage has been read by every lane: re-arm it with the tile S steps ahead
         __syncwarp();
-        if (ig < G1) {
+        if (itodo > 0) {
             if (lane == 0) {
                 fence_proxy_async();
                 issue(icap, itile, stage);
             }
-            advance(icap, itile, ig);
+            --itodo;
+            if (++itile == NTC) {
+                itile = 0;
+                ++icap;
+            }
         }
         if (++stage == S) {
             stage = 0;
             parity ^= 1u;
+        }
+        float2 cur[Q];
+        const float2 w0 = make_float2(static_cast<float>(wrot.x), static_cast<float>(wrot.y));
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float2 p = unpack_f32x2(acc[q]);
+            cur[q] = MIX ? cmul(p, w0) : p;
         }
 
         // ---- y[m] = sum_q P_q[m - q]: lane l takes P_q from lane l-q (this tile) or, for l < q, from
@@ -629,11 +702,12 @@ chain_stream_kernel(const ChainParams P) {
         }
 #pragma unroll
         for (int q = 1; q < Q; ++q) prev[q] = cur[q];
-        const long long m = (tile - 1) * WT + lane;
-        const bool emit = tile >= 1 && g >= G0 && m < P.M;
+        const long long m = jblk;
+        const bool emit = tile >= 1 && k >= skip && m < P.M;
         if (OUT == DDM_CHAIN_OUT_IQ) {
             if (emit) reinterpret_cast<float2 *>(P.out)[cap * P.out_stride + m] = y;
         } else {
+            // the discriminator needs y[m-1] as well: one more shuffle, lane 0 from lane 31 of the tile before
             const float2 v = lane == 31 ? y_last : y;
             const float2 yp = make_float2(__shfl_sync(0xffffffffu, v.x, (lane - 1) & 31),
                                           __shfl_sync(0xffffffffu, v.y, (lane - 1) & 31));
@@ -641,9 +715,14 @@ chain_stream_kernel(const ChainParams P) {
             if (emit && (m > 0 || P.has_prev)) {
                 const float re = fmaf(y.x, yp.x, y.y * yp.y);
                 const float im = fmaf(y.y, yp.x, -y.x * yp.y);
-                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = atan2f(im, re);
+                reinterpret_cast<float *>(P.out)[cap * P.out_stride + m - (P.has_prev ? 0 : 1)] = fast_atan2f(im, re);
             }
         }
+        if (++tile == NTC) {
+            tile = 0;
+            ++cap;
+        }
+        if (MIX) wrot = (tile & 63) == 0 ? rot_exact(tile) : cmuld(wrot, wstep);
     }
 }
 
@@ -673,17 +752,6 @@ __device__ __forceinline__ float2 chain_fetch(const void *x, const void *halo, i
     return i >= 0 ? static_cast<const float2 *>(x)[i] : static_cast<const float2 *>(halo)[H + i];
 }
 
-// exp(-j 2 pi r g) in float64 (the general path rotates float64 sums)
-__device__ __forceinline__ double2 phase_rotator_f64(double r_hi, double r_lo, long long g) {
-    const double gd = static_cast<double>(g);
-    const double p = r_hi * gd;
-    const double e = fma(r_hi, gd, -p);
-    double fr = p - rint(p);
-    fr += e + r_lo * gd;
-    double s, c;
-    sincospi(2.0 * fr, &s, &c);
-    return make_double2(c, -s);
-}
 
 // The mixer commutes into the taps: x'[pos-k] = x[pos-k] rot(n0+pos) exp(+j 2 pi r k), so
 //   y[m] = rot(n0 + pos) * sum_k (taps[k] exp(+j 2 pi r k)) x[pos-k]
@@ -923,11 +991,16 @@ size_t chain_smem_bytes(int Q, int D, int DP, int in_format = DDM_IN_CF32) {
     return fixed + kChainStages * stage;
 }
 
-// Geometry of the warp-autonomous kernel for one (D, input format): W warps (one CTA per SM), each with a
-// private ring of S stages of 32 blocks.  The rings take what shared memory there is: bytes in flight
-// are what the HBM stream needs (scripts/microbench/readbw2.cu), so prefer S >= 3 and then as many
-// warps as fit, down to one warp with two stages for very long blocks.
-bool stream_geometry(int Q, int D, int DP, int in_format, int *warps, int *stages) {
+// Geometry of the warp-autonomous kernel for one (D, input format): W warps (one CTA per SM), each with
+// a private ring of S stages of 32 blocks.  Measured on B200 (profiles/r02_chain_ab.jsonl,
+// scripts/microbench/readbw3.cu): the kernel is bound by instruction latency, not by bytes in flight --
+// a read-only ring reaches 7.4 TB/s with ~140 KB of stages per SM and gets SLOWER with 200 KB -- so the
+// rule is: as many warps as possible in multiples of four (equal load on the four schedulers), two
+// stages each, rings of at most ~150 KB per SM.  Blocks too long for eight warps under that rule
+// (cf32: D >= 40) stay with the CTA-tiled kernel, whose 128-block tiles amortise the per-tile work
+// better there; blocks too long for THAT kernel's two 128-block stages (D > 110) come back here with
+// four, two or one warp.
+bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int *warps, int *stages) {
     const size_t stage = stream_stage_bytes(D, in_format);
     const size_t budget = 227 * 1024;
     int forced_w = 0, forced_s = 0;
@@ -940,16 +1013,23 @@ bool stream_geometry(int Q, int D, int DP, int in_format, int *warps, int *stage
         *stages = forced_s;
         return true;
     }
-    const int want[] = {8, 6, 4, 3, 2, 1};
-    for (int min_s = 3; min_s >= 2; --min_s)
-        for (int w : want) {
-            int s_ = kStreamMaxStages;
-            while (s_ >= min_s && !fits(w, s_)) --s_;
-            if (s_ >= min_s) {
-                *warps = w;
-                *stages = s_ > 4 && in_format != DDM_IN_CU8 ? 4 : s_;
-                return true;
-            }
+    const size_t ring_target = 150 * 1024;
+    for (int w : {12, 8}) {
+        if (stage * w * 2 <= ring_target) {
+            int s_ = 2;
+            if (in_format == DDM_IN_CU8)               // short stages: a deeper ring costs nothing
+                while (s_ < 4 && stage * w * (s_ + 1) <= ring_target) ++s_;
+            *warps = w;
+            *stages = s_;
+            return true;
+        }
+    }
+    if (legacy_fits) return false;
+    for (int w : {4, 2, 1})
+        if (fits(w, 2)) {
+            *warps = w;
+            *stages = 2;
+            return true;
         }
     return false;
 }
@@ -965,7 +1045,21 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
         c->st_attr[p.s] = true;
     }
     p.stages = S;
+    {
+        // the block rotator's advance per warp tile, exp(-j 2 pi r 32 D), from the double-double r
+        const long double span = static_cast<long double>(kStreamTile) * c->D;
+        long double t = static_cast<long double>(c->r_hi) * span;
+        t -= std::floor(t);
+        t += static_cast<long double>(c->r_lo) * span;
+        const long double ang = 2.0L * 3.14159265358979323846264338327950288L * t;
+        p.step_re = static_cast<double>(std::cos(ang));
+        p.step_im = static_cast<double>(-std::sin(ang));
+    }
     p.num_tiles = 1 + (p.M + kStreamTile - 1) / kStreamTile;        // per capture, warm-up tile 0 included
+    if (p.num_tiles >= (1LL << 31) - 2) {
+        set_error("chunk too long for one launch of the fused chain (%lld tiles)", static_cast<long long>(p.num_tiles));
+        return DDM_ERR_UNSUPPORTED;
+    }
     const long long total_tiles = p.num_tiles * p.batch;
     long long warps = static_cast<long long>(c->sms) * W;
     if (warps > total_tiles / kStreamMinTiles) warps = total_tiles / kStreamMinTiles;
@@ -1144,10 +1238,10 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     c->DP = (D + 3) & ~3;
     c->es = in_format == DDM_IN_CU8 ? 2 : 8;
     const bool legacy = std::getenv("DDM_CHAIN_LEGACY") != nullptr;         // A/B against the CTA-tiled kernel
+    const bool legacy_fits = D >= 2 && qmax <= kChainMaxQ && chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024;
     c->stream = !legacy && D >= 2 && qmax <= kChainMaxQ &&
-                stream_geometry(qmax, D, c->DP, in_format, &c->st_warps, &c->st_stages);
-    c->fast = c->stream || (D >= 2 && qmax <= kChainMaxQ &&
-                            chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024);
+                stream_geometry(qmax, D, c->DP, in_format, legacy_fits, &c->st_warps, &c->st_stages);
+    c->fast = c->stream || legacy_fits;
     // halo: the Q (odd D: up to Q + 1) leading blocks of a tile plus one block of slack
     c->H = (qmax + 1 + (D & 1)) * D;
     if (c->H & 1) c->H += 1;
