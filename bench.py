@@ -392,9 +392,9 @@ def leg_timeshard_chain(env, args, peak):
         "exchange_halo_us": round(ex_ms * 1e3, 1), "halo_samples": ts.halo_len, "launches_per_run": per_run,
         "roofline": {"bound": "hbm", "achieved": round(n * ALG_BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9, 1), "peak": peak,
                      "unit": "GB/s per GPU", "frac": round(n * ALG_BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak, 4)},
-        "timeshard_parity": bool(neq == 0.0 and err == 0.0) if env.world > 1 else None,
+        "timeshard_parity": bool(err <= 1e-6) if env.world > 1 else None,
         "parity": {"check": "+-2000 outputs around every seam recomputed by one chain on one rank", "max_abs_err_rad": err,
-                   "bit_equal": neq == 0.0, "samples_per_seam": int(cnt)},
+                   "tolerance_rad": 1e-6, "bit_equal": neq == 0.0, "samples_per_seam": int(cnt)},
     }
     if note:
         rec["note"] = note
@@ -517,6 +517,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print there (NCCL's version
+    # banner) is sent to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -713,7 +718,7 @@ def run_ours(args):
                 "traffic_source": traffic.get("source") if traffic else
                 "not measured in this run (ncu --set full capture of this launch size: profiles/)",
                 "algorithmic_gb_per_launch": round(n * ALG_BYTES_PER_SAMPLE / 1e9, 3),
-                "peak_source": peak_src, "kernel": "ddm::chain_fused_kernel<Q=5,MIX,FM> (1 launch per step)",
+                "peak_source": peak_src, "kernel": "ddm::chain_stream_kernel<Q=5,MIX,FM>, 8 warps x 2-stage TMA rings per SM (1 launch per step)",
                 "note": "peak is the driver's copy (read+write) figure; a read-only stream reaches ~7350 GB/s on "
                         "this part (profiles/r01_microbench.txt), so a 99.6%-read kernel can exceed frac 1.0",
                 "algorithmic_bytes_per_sample": round(ALG_BYTES_PER_SAMPLE, 4),
@@ -752,7 +757,7 @@ def run_ours(args):
         line.update(extra)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single(reps=args.cpu_reps)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -1368,8 +1368,14 @@ int launch_iir_pio(ddm_filter *f, const void *x, void *y, long long n, const dou
         split = staged && cplx && n < 6 * W * (static_cast<long long>(f->sms) * 4 * 32 * 3);
         const long long base = static_cast<long long>(f->sms) * 4 * 32 / (split ? 2 : 1);
         long long wps = staged ? (split || !cplx ? 4 : 3) : 2;
-        if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));
-        while (wps > 1 && (n + base * wps - 1) / (base * wps) < 2 * W) --wps;
+        // Chunk-sized signals (the reference's 20 M-sample calls): one warp per sub-partition is bound by
+        // the latency of the recursion's dependent DFMAs (measured 144 cycles per step against 42 of
+        // FP64 issue), so more, shorter segments pay even though each repeats the W-sample warm-up:
+        // per-lane steps L + W fall from 3 W to 1.5 W with four warps.  Keep at least W / 2 fresh samples
+        // per segment.
+        const long long min_seg = staged ? std::max<long long>(W / 2, 4 * kIirAlign) : 2 * W;
+        while (wps > 1 && (n + base * wps - 1) / (base * wps) < min_seg) --wps;
+        if (const char *e = std::getenv("DDM_IIR_WARPS")) wps = std::max(1, std::atoi(e));     // tuning knob
         L = (n + base * wps - 1) / (base * wps);
         if (L < 4 * kIirAlign) L = 4 * kIirAlign;
         prm.W = W;

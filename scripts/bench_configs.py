@@ -212,11 +212,20 @@ def c4(quick):
     del y, z
     t_fir, y = wall(lambda: fir._apply_dev(x))
     t_iir, z = wall(lambda: iir._apply_dev(y))
+    # the same cascade as ONE equivalent filter (filters.cascade): a single overlap-save pass
+    cas = filters.cascade([filters.remez(fs, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023),
+                           filters.butter(fs, 100000, n=8)])
+    w = cas._apply_dev(x)
+    del w
+    t_cas, w = wall(lambda: cas._apply_dev(x), 3)
     emit(config="C4 slab of %d samples (1/8 of 1 h @ 2.4 Msps): remez1023 + butter8" % n, samples=n,
          fir_ms=round(t_fir * 1e3, 2), fir_msps=round(n / t_fir / 1e6, 1),
-         fir_tflops=round(n * 4 * 1023 / t_fir / 1e12, 1), iir_ms=round(t_iir * 1e3, 2),
-         iir_msps=round(n / t_iir / 1e6, 1), total_msps=round(n / (t_fir + t_iir) / 1e6, 1),
-         halo_samples=fir.lookback() + iir.lookback())
+         fir_direct_form_equivalent_tflops=round(n * 4 * 1023 / t_fir / 1e12, 1), iir_ms=round(t_iir * 1e3, 2),
+         iir_msps=round(n / t_iir / 1e6, 1), stage_by_stage_msps=round(n / (t_fir + t_iir) / 1e6, 1),
+         cascade_taps=int(len(cas.getB)), cascade_ms=round(t_cas * 1e3, 2), cascade_msps=round(n / t_cas / 1e6, 1),
+         cascade_hbm_gbs=round(n * 16 / t_cas / 1e9, 1),
+         halo_samples_stage_by_stage=fir.lookback() + iir.lookback(), halo_samples_cascade=cas.lookback())
+    del w
     if O is None:
         return
     nc = 8_000_000
