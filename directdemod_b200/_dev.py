@@ -20,11 +20,17 @@ def torch():
     return _t
 
 
+_checked = False
+
+
 def require_cuda():
+    global _checked
     t = torch()
-    if not t.cuda.is_available():
-        raise RuntimeError("directdemod_b200 needs a CUDA device; there is no CPU fallback")
-    _lib.lib()
+    if not _checked:
+        if not t.cuda.is_available():
+            raise RuntimeError("directdemod_b200 needs a CUDA device; there is no CPU fallback")
+        _lib.lib()
+        _checked = True
     return t
 
 
@@ -52,6 +58,8 @@ def to_device(x):
     if isinstance(x, t.Tensor):
         if x.dim() != 1:
             raise TypeError("The signal array must be 1-D")
+        if x.is_cuda and x.dtype in (t.complex64, t.float32) and x.is_contiguous():
+            return x                                     # the common case on the chunk loops: nothing to do
         want = t.complex64 if x.is_complex() else t.float32
         if not x.is_cuda:
             x = x.to("cuda")

@@ -413,10 +413,17 @@ class decode_noaa:
             logging.info('Beginning SyncB detection')
             self._syncB = self._correlateAndFindPeaks(sig, constants.NOAA_SYNCB)
             n = constants.NOAA_DETECTCONSSYNCSNUM
-            syncAdiff = np.abs(np.diff(self._syncA) - (self._syncCrudeSampRate * 0.5))
-            minSyncAdiff = np.min([np.max(syncAdiff[i:i + n]) for i in range(len(syncAdiff) - n + 1)])
-            syncBdiff = np.abs(np.diff(self._syncB) - (self._syncCrudeSampRate * 0.5))
-            minSyncBdiff = np.min([np.max(syncBdiff[i:i + n]) for i in range(len(syncBdiff) - n + 1)])
+
+            def steadiest(sync):
+                """min over all runs of n consecutive sync spacings of the run's largest deviation from
+                half a second (decode_noaa.py:795-799; the reference's list comprehension of ~1800
+                np.max calls is 4 ms of interpreter time per sync word -- one windowed maximum here)."""
+                dev = np.abs(np.diff(sync) - (self._syncCrudeSampRate * 0.5))
+                if len(dev) - n + 1 <= 0:
+                    return np.min([])               # the reference's error for a pass with too few syncs
+                return np.min(np.max(np.lib.stride_tricks.sliding_window_view(dev, n), axis=1))
+            minSyncAdiff = steadiest(self._syncA)
+            minSyncBdiff = steadiest(self._syncB)
             if minSyncAdiff < constants.NOAA_DETECTMAXCHANGE or minSyncBdiff < constants.NOAA_DETECTMAXCHANGE:
                 logging.info('NOAA Signal was found')
                 self._useful = 1

@@ -18,6 +18,12 @@ import scipy.signal as signal
 from . import _dev, _lib, constants
 
 
+# Default of filter.setIIRTolerance for filters created afterwards (None = the library's 1e-7): a
+# script that accepts scipy-float64-level agreement everywhere sets it once, e.g.
+# ``filters.IIR_AUTO_FLOOR = 1e-3``, and its 12th-order band-passes stream segment-parallel.
+IIR_AUTO_FLOOR = None
+
+
 class filter:
     """Parent of all filters (filters.py:15-89).
 
@@ -69,7 +75,7 @@ class filter:
                 _lib.lib().ddm_filter_destroy(self._h)
             self._h = None
         shared = not self._storeState and not getattr(self, "_private", False)
-        key = (dev, self._zeroPhase, self._bd.tobytes(), self._ad.tobytes())
+        key = (dev, self._zeroPhase, IIR_AUTO_FLOOR, self._bd.tobytes(), self._ad.tobytes())
         if self._h is None and shared:
             _dev.require_cuda()
             cached = filter._shared_handles.get(key)
@@ -95,6 +101,10 @@ class filter:
                 zi = np.ascontiguousarray(signal.lfilter_zi(self._b, self._a), dtype=np.float64)
                 _lib.check(l.ddm_filter_set_zi_base(h, zi.ctypes.data_as(C.POINTER(C.c_double))),
                            "ddm_filter_set_zi_base")
+            if IIR_AUTO_FLOOR is not None and not hasattr(self, "_shard_floor"):
+                self._shard_floor = float(IIR_AUTO_FLOOR)
+            if getattr(self, "_shard_floor", None) is not None:
+                _lib.check(l.ddm_filter_set_iir_auto_floor(h, self._shard_floor), "ddm_filter_set_iir_auto_floor")
             if self._storeState and not self._needs_lfiltic:
                 _lib.check(l.ddm_filter_reset(h, _dev.stream_ptr(dev)), "ddm_filter_reset")
             if shared and len(filter._shared_handles) < 256:
@@ -183,7 +193,10 @@ class filter:
 
     @property
     def isFIR(self):
-        return bool(np.all(self._ad[1:] == 0.0))
+        v = self.__dict__.get("_is_fir")
+        if v is None:
+            v = self.__dict__["_is_fir"] = bool(np.all(self._ad[1:] == 0.0))
+        return v
 
     @property
     def _fresh(self):
