@@ -30,6 +30,27 @@ def _is_cuda_tensor(x):
     return _dev.is_tensor(x) and x.is_cuda
 
 
+# chunks from this length on run consecutive stateful filters as one overlap-save pass (the FFT path of
+# the long-FIR kernel starts there; below it the stage-by-stage kernels are the faster tool)
+_CASCADE_MIN = 1 << 20
+
+
+def _cascadable(f):
+    """A stage filters.cascade can absorb: stateful LTI, and -- for a recursive filter -- one the library
+    runs segment-parallel anyway (the bit-exact sequential replay of an ill-conditioned filter is a
+    promise the equivalent FIR cannot keep)."""
+    ok = f.__dict__.get("_cascadable")
+    if ok is None:
+        ok = bool(type(f) is not _filters.cascade and f._storeState and not f._zeroPhase and f._initOut is None)
+        if ok and not f.isFIR:
+            try:
+                f.lookback()
+            except ValueError:
+                ok = False
+        f._cascadable = ok
+    return ok and not f._needs_lfiltic and f._chain is None
+
+
 class commSignal:
     def __init__(self, sampRate, sig=np.array([]), chunker=None):
         """sampRate: Hz, forced to int, must be > 0 (ValueError); sig: 1-D array (TypeError
@@ -173,7 +194,11 @@ class commSignal:
         if isinstance(filt, _filters.filter):
             fusable = (filt.isFIR and filt._storeState and not filt._needs_lfiltic and self._complex
                        and all(op[0] == "mix" for op in self._pending))
-            if not fusable:
+            # a second stateful filter right behind a queued one may run with it as ONE equivalent
+            # filter (filters.cascade) when the chunk is long enough: keep both queued
+            chained = (self._pending and self._pending[-1][0] == "filter" and self._len >= _CASCADE_MIN
+                       and _cascadable(filt) and _cascadable(self._pending[-1][1]))
+            if not fusable and not chained:
                 self._flush()
             self._claim(filt)
             self._pending.append(("filter", filt))
@@ -331,6 +356,11 @@ class commSignal:
                     x = y
                     i += took
                     continue
+                took, y = self._try_cascade(ops, i, x)
+                if took:
+                    x = y
+                    i += took
+                    continue
                 x = self._run_single(ops[i], x)
                 i += 1
         finally:
@@ -406,6 +436,40 @@ class commSignal:
         if fm is not None:
             fm._chain = ch
             fm._last = None
+        return j - i, y
+
+    def _try_cascade(self, ops, i, x):
+        """Two or more queued stateful filters in a row over a long chunk: one equivalent filter
+        (filters.cascade), one overlap-save pass, no intermediate signal.  The stages' states move into
+        the cascade (from their current values, so a stream may switch over in mid-flight) and come
+        back the moment a stage is used on its own again (filter._sync_pending -> cascade.release)."""
+        j = i
+        stages = []
+        while j < len(ops) and ops[j][0] == "filter" and _cascadable(ops[j][1]):
+            stages.append(ops[j][1])
+            j += 1
+        if len(stages) < 2 or x.numel() < _CASCADE_MIN:
+            return 0, None
+        key = tuple(id(f) for f in stages)
+        cas = stages[0].__dict__.get("_cascade")
+        if cas is None or cas._key != key or any(f.__dict__.get("_cascade") is not cas for f in stages):
+            if stages[0].__dict__.get("_no_cascade") == key:
+                return 0, None
+            for f in stages:                                   # leave any other cascade first
+                other = f.__dict__.get("_cascade")
+                if other is not None:
+                    other.release()
+            try:
+                cas = _filters.cascade(stages, states=[None if f._fresh else f.getState() for f in stages])
+            except ValueError:
+                stages[0]._no_cascade = key                    # does not die out in time: stage by stage
+                return 0, None
+            cas._key = key
+            for f in stages:
+                f._cascade = cas
+        y = cas._apply_dev(x, _queued=True)
+        for f in stages:
+            f._used = True
         return j - i, y
 
     def _run_single(self, op, x):

@@ -116,10 +116,17 @@ class filter:
     def _sync_pending(self):
         """commSignal.filter() only queues a stateful filter; anything that reads or advances the
         delay line directly must first let that queue run, so state is consumed in call order like
-        in the reference (which executes eagerly)."""
+        in the reference (which executes eagerly).  A filter whose state currently lives in a fused
+        cascade (commSignal ran ``.filter(f1).filter(f2)`` as one equivalent filter) takes it back."""
         owner = getattr(self, "_pending_owner", None)
         if owner is not None:
             owner._flush()
+        self._leave_cascade()
+
+    def _leave_cascade(self):
+        cas = self.__dict__.get("_cascade")
+        if cas is not None:
+            cas.release()
 
     def _unshare(self):
         """Execution modes are per-handle settings: a filter that changes one gets its own handle."""
@@ -248,6 +255,8 @@ class filter:
     def _apply_dev(self, xd, host_x=None, _queued=False):
         if not _queued:
             self._sync_pending()
+        else:
+            self._leave_cascade()
         l = _lib.lib()
         h = self._handle(xd.device.index)
         self._release_chain()
@@ -376,7 +385,10 @@ class cascade(filter):
     Raises ValueError when a stage is not a stateful LTI filter or the cascade does not die out
     within ``max_taps`` samples."""
 
-    def __init__(self, filts, tol=1e-9, max_taps=2049):
+    def __init__(self, filts, tol=1e-9, max_taps=2049, states=None):
+        """``states``: the stages' current delay lines (complex arrays as from ``getState``; None for a
+        stage that has not run yet) when the cascade takes over a stream in mid-flight; default: every
+        stage fresh."""
         filts = list(filts)
         if not filts:
             raise ValueError("Atleast one filter must be given")
@@ -384,15 +396,18 @@ class cascade(filter):
             if not isinstance(f, filter) or f._zeroPhase or not f._storeState or f._initOut is not None:
                 raise ValueError("a cascade is made of stateful filters (no zeroPhase, no initOut)")
         self._stages = filts
+        self._hist = None                 # the last taps-1 raw input samples (cuda), for release()
         span = 4 * max_taps
         h = np.zeros(span)
         h[0] = 1.0
-        zir = np.zeros(span)
-        for f in filts:
+        zir = np.zeros(span, dtype=np.complex128)
+        for idx, f in enumerate(filts):
             bb, aa = np.asarray(f._b, dtype=np.float64), np.atleast_1d(np.asarray(f._a, dtype=np.float64))
             h = signal.lfilter(bb, aa, h)
             if max(len(bb), len(aa)) > 1:
-                zir, _ = signal.lfilter(bb, aa, zir, zi=signal.lfilter_zi(bb, aa))
+                st = None if states is None else states[idx]
+                zi0 = signal.lfilter_zi(bb, aa) if st is None else np.asarray(st, dtype=np.complex128)
+                zir, _ = signal.lfilter(bb, aa, zir, zi=zi0.astype(np.complex128))
             else:
                 zir = signal.lfilter(bb, aa, zir)
         tail = np.cumsum(np.abs(h)[::-1])[::-1]
@@ -426,6 +441,41 @@ class cascade(filter):
 
     def lookback(self):
         return self._bd.size - 1
+
+    def _apply_dev(self, xd, host_x=None, _queued=False):
+        y = super()._apply_dev(xd, host_x=host_x, _queued=_queued)
+        k1 = self._bd.size - 1
+        if xd.numel() >= k1:
+            self._hist = xd[xd.numel() - k1:].clone()
+        elif xd.numel() > 0:
+            t = _dev.torch()
+            old = self._hist if self._hist is not None else t.zeros(0, dtype=xd.dtype, device=xd.device)
+            self._hist = t.cat([old.to(xd.dtype), xd])[-k1:]
+        self._ran = getattr(self, "_ran", 0) + int(xd.numel())
+        return y
+
+    def release(self):
+        """Hand the carried state back to the stages (they are about to be used on their own): each
+        stage's delay line is what the stage-by-stage run leaves after the last taps-1 input samples
+        -- exact for an FIR stage, and for an IIR stage as exact as the cascade itself, whose taps end
+        where that stage's memory of older samples has died out.  Host float64, a few thousand samples."""
+        stages = self._stages
+        for f in stages:
+            if f.__dict__.get("_cascade") is self:
+                f._cascade = None
+        if self._hist is None:
+            return
+        if getattr(self, "_ran", 0) < self._bd.size - 1:
+            raise RuntimeError("a fused cascade cannot hand back the state of a stream shorter than its taps")
+        sig = _dev.to_host(self._hist).astype(np.complex128)
+        for f in stages:
+            bb, aa = np.asarray(f._b, dtype=np.float64), np.atleast_1d(np.asarray(f._a, dtype=np.float64))
+            if max(len(bb), len(aa)) > 1:
+                sig, zf = signal.lfilter(bb, aa, sig, zi=np.zeros(max(len(bb), len(aa)) - 1, dtype=np.complex128))
+                f.setState(zf)
+            else:
+                sig = signal.lfilter(bb, aa, sig)
+        self._hist = None
 
 
 class blackmanHarrisConv:

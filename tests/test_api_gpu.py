@@ -760,3 +760,38 @@ def test_cascade_runs_as_one_filter_and_matches_the_stage_by_stage_reference():
     for f in (fir, iir):
         wr, _ = sps.lfilter(f.getB, f.getA, wr, zi=sps.lfilter_zi(f.getB, f.getA))
     assert O.rel_rms(filters.cascade([fir, iir]).applyOn(xr), wr) <= TOL
+
+
+def test_commsignal_runs_consecutive_filters_as_one_cascade_and_hands_state_back():
+    """``sig.filter(fir).filter(iir)`` (comm.py:80-92 twice) on long chunks runs as ONE equivalent
+    overlap-save filter; the stages' states move into it in mid-stream and come back when a later,
+    short chunk takes the stage-by-stage kernels again.  Reference: scipy stage by stage, state
+    carried across all chunks (filters.py:64-70)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    from directdemod_b200 import _lib
+    fs = 2400000
+    rng = np.random.default_rng(43)
+    cuts = [0, 3000, 1303000, 2603000, 2604500, 3904500]       # short, long, long, short, long
+    n = cuts[-1]
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    fir = filters.remez(fs, [[0, 100000], [120000, 1199999]], [1, 0], ntaps=1023)
+    iir = filters.butter(fs, 100000, n=8)
+    want = x.astype(np.complex128)
+    for f in (fir, iir):
+        want, _ = sps.lfilter(f.getB, f.getA, want, zi=sps.lfilter_zi(f.getB, f.getA))
+    parts, launches = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        l0 = _lib.launch_count()
+        s = comm.commSignal(fs, x[a:b]).filter(fir).filter(iir)
+        parts.append(s.signal)
+        launches.append(_lib.launch_count() - l0)
+    got = np.concatenate(parts)
+    assert got.shape == want.shape
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert O.rel_rms(got[a:b], want[a:b]) <= TOL, (a, b, O.rel_rms(got[a:b], want[a:b]))
+    assert launches[1] <= 2 and launches[2] <= 2                # one filter launch (+ its state update)
+    assert launches[0] >= 3 and launches[3] >= 3                # short chunks: stage by stage
+    # the stages can be read on their own afterwards (state handed back) and still agree with scipy
+    _, z1 = sps.lfilter(fir.getB, [1.0], x.astype(np.complex128), zi=sps.lfilter_zi(fir.getB, [1.0]))
+    assert O.rel_rms(fir.getState(), z1) <= TOL
