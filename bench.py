@@ -718,7 +718,7 @@ def run_ours(args):
                 "traffic_source": traffic.get("source") if traffic else
                 "not measured in this run (ncu --set full capture of this launch size: profiles/)",
                 "algorithmic_gb_per_launch": round(n * ALG_BYTES_PER_SAMPLE / 1e9, 3),
-                "peak_source": peak_src, "kernel": "ddm::chain_stream_kernel<Q=5,MIX,FM>, 8 warps x 2-stage TMA rings per SM (1 launch per step)",
+                "peak_source": peak_src, "kernel": "ddm::chain_stream_kernel<Q=5,MIX,FM>, 16 warps per SM, one TMA stage per warp (1 launch per step)",
                 "note": "peak is the driver's copy (read+write) figure; a read-only stream reaches ~7350 GB/s on "
                         "this part (profiles/r01_microbench.txt), so a 99.6%-read kernel can exceed frac 1.0",
                 "algorithmic_bytes_per_sample": round(ALG_BYTES_PER_SAMPLE, 4),

@@ -490,8 +490,8 @@ __host__ __device__ inline unsigned stream_fixed_bytes(int Q, int DP, int warps,
     return bars + ((4u * (Q * DP + DP) + 8u * (2 * DP) + 127u) & ~127u);
 }
 
-template <int Q, bool MIX, int OUT, int IN>
-__global__ void __launch_bounds__(32 * kStreamMaxWarps, 1)
+template <int Q, bool MIX, int OUT, int IN, int LBW = kStreamMaxWarps>
+__global__ void __launch_bounds__(32 * LBW, 1)
 chain_stream_kernel(const ChainParams P) {
     constexpr int WT = kStreamTile;
     constexpr bool U8 = IN == DDM_IN_CU8;
@@ -996,7 +996,7 @@ size_t chain_smem_bytes(int Q, int D, int DP, int in_format = DDM_IN_CF32) {
 // scripts/microbench/readbw3.cu): the kernel is bound by instruction latency, not by bytes in flight --
 // a read-only ring reaches 7.4 TB/s with ~140 KB of stages per SM and gets SLOWER with 200 KB -- so the
 // rule is: as many warps as possible in multiples of four (equal load on the four schedulers), two
-// stages each, rings of at most ~150 KB per SM.  Blocks too long for eight warps under that rule
+// stages each (one with sixteen warps), rings of at most ~150 KB per SM.  Blocks too long for eight warps under that rule
 // (cf32: D >= 40) stay with the CTA-tiled kernel, whose 128-block tiles amortise the per-tile work
 // better there; blocks too long for THAT kernel's two 128-block stages (D > 110) come back here with
 // four, two or one warp.
@@ -1008,12 +1008,21 @@ bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int 
     if (const char *e = std::getenv("DDM_STREAM_STAGES")) forced_s = std::atoi(e);
     auto fits = [&](int w, int s_) { return stream_fixed_bytes(Q, DP, w, s_) + stage * w * s_ <= budget; };
     if (forced_w > 0 && forced_s > 0) {
-        if (forced_w > kStreamMaxWarps || forced_s > kStreamMaxStages || forced_s < 2 || !fits(forced_w, forced_s)) return false;
+        const int max_w = (Q == 5 && in_format == DDM_IN_CF32) ? 16 : kStreamMaxWarps;
+        if (forced_w > max_w || forced_s > kStreamMaxStages || forced_s < 1 || !fits(forced_w, forced_s)) return false;
         *warps = forced_w;
         *stages = forced_s;
         return true;
     }
     const size_t ring_target = 150 * 1024;
+    // Q <= 5 (the NOAA configuration: 151 taps, D = 31 .. 37) has a 128-register build: sixteen warps with
+    // ONE stage each -- the other fifteen warps cover a warp's reload -- measured as fast as eight warps
+    // with two stages (2.17 ms) and without their slow outliers (p90 2.19 against 2.5 ms)
+    if (Q == 5 && in_format == DDM_IN_CF32 && stage * 16 <= ring_target) {
+        *warps = 16;
+        *stages = 1;
+        return true;
+    }
     for (int w : {12, 8}) {
         if (stage * w * 2 <= ring_target) {
             int s_ = 2;
@@ -1040,6 +1049,9 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
     const int W = c->st_warps, S = c->st_stages;
     const size_t smem = stream_fixed_bytes(Q, c->DP, W, S) + stream_stage_bytes(c->D, IN) * W * S;
     auto kern = chain_stream_kernel<Q, MIX, OUT, IN>;
+    if constexpr (Q == 5 && IN == DDM_IN_CF32) {
+        if (W > kStreamMaxWarps) kern = chain_stream_kernel<Q, MIX, OUT, IN, 16>;      // 128-register build
+    }
     if (!c->st_attr[p.s]) {   // first launch of this variant on this handle's device
         DDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         c->st_attr[p.s] = true;

@@ -32,9 +32,11 @@ for _ in range(30):
 ts.sort()
 print(json.dumps({"ms_med": round(ts[15], 4), "ms_min": round(ts[0], 4), "ms_p90": round(ts[27], 4)}))
 ''' % ROOT
-variants = [("cta-tiled", {"DDM_CHAIN_LEGACY": "1"}), ("warp generic w8s2", {"DDM_STREAM_GENERIC": "1"}),
-            ("warp specialised w8s2", {}), ("warp specialised w12s2", {"DDM_STREAM_WARPS": "12", "DDM_STREAM_STAGES": "2"}),
-            ("warp generic w12s2", {"DDM_STREAM_GENERIC": "1", "DDM_STREAM_WARPS": "12", "DDM_STREAM_STAGES": "2"})]
+variants = [("warp w8s2 (default)", {}),
+            ("warp w16s1 (128-register build)", {"DDM_STREAM_WARPS": "16", "DDM_STREAM_STAGES": "1"}),
+            ("warp w12s1", {"DDM_STREAM_WARPS": "12", "DDM_STREAM_STAGES": "1"}),
+            ("warp w8s1", {"DDM_STREAM_WARPS": "8", "DDM_STREAM_STAGES": "1"}),
+            ("warp w12s2", {"DDM_STREAM_WARPS": "12", "DDM_STREAM_STAGES": "2"})]
 for rnd in range(2):
     for name, env in variants:
         e = dict(os.environ)
