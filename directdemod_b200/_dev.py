@@ -15,9 +15,15 @@ import numpy as np
 from . import _lib
 
 
+_torch = None
+
+
 def torch():
-    import torch as _t
-    return _t
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
 
 
 _checked = False

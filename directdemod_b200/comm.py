@@ -176,7 +176,7 @@ class commSignal:
         if not self._complex:
             # the reference multiplies a real array by a complex one in place -> numpy refuses
             raise TypeError("Cannot cast ufunc 'multiply' output from dtype('complex128') to a real dtype")
-        if np.ndim(freqOffset) != 0:
+        if not isinstance(freqOffset, (int, float)) and np.ndim(freqOffset) != 0:
             f = np.ascontiguousarray(np.asarray(freqOffset, dtype=np.float64).ravel())
             if f.size != self.length:
                 raise ValueError("operands could not be broadcast together with shapes (%d,) (%d,)"
