@@ -330,12 +330,20 @@ __device__ __forceinline__ void pk_twiddle(cpk (&v)[16], const float2 *T) {
 constexpr int kFftFirT3 = 4 * 256, kFftFirT2 = 4 * 16;
 
 // the 4096-point transform on packed values
-template <int DIR>
-__device__ __forceinline__ void pkfft_4096(cpk (&v)[16], cpk *buf, const float2 *T3, const float2 *T2, int j) {
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `after_first_barrier` runs right behind the transform's first CTA barrier -- the point at which every
+// thread has consumed the block's staged input (the kernel re-arms the staging buffer there)
+template <int DIR, typename Hook = NoHook>
+__device__ __forceinline__ void pkfft_4096(cpk (&v)[16], cpk *buf, const float2 *T3, const float2 *T2, int j,
+                                           Hook after_first_barrier = Hook()) {
     pk_dft16<DIR>(v);
 #pragma unroll
     for (int r = 0; r < 16; ++r) buf[fftfir_idx(16 * j + r)] = v[r];
     __syncthreads();
+    after_first_barrier();
     {
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[r] = buf[fftfir_idx(j + 256 * r)];
@@ -364,13 +372,15 @@ __device__ __forceinline__ void cp_async_zfill(void *smem_dst, const void *gsrc,
 
 constexpr size_t fft_fir_smem_bytes(bool cplx) {
     return sizeof(float2) * (kFftFirN + kFftFirN / 16 + kFftFirT3 + kFftFirT2) +
-           (cplx ? sizeof(float2) : sizeof(float)) * kFftFirN;
+           (cplx ? sizeof(float2) : sizeof(float)) * (kFftFirN + 4) + 16;       // + aligned-copy slack + mbarrier
 }
 
-// Persistent CTAs (2 per SM) walk the blocks of the signal.  The next block's 4096 input samples
-// are fetched with cp.async into thread-private slots of a staging buffer (thread j copies and later
-// reads elements j + 256 r: no barrier needed) while the current block is transformed; samples
-// before the start / behind the end of the signal are zero-filled by the copy itself.
+// Persistent CTAs (2 per SM) walk the blocks of the signal.  The next block's 4096 input samples are
+// staged while the current block is transformed: interior blocks by ONE TMA bulk copy (UBLKCP, issued by
+// thread 0 right behind the first barrier of the forward transform, i.e. as soon as every thread has
+// taken the current block out of the staging buffer; completion on an mbarrier) from the 16-byte
+// boundary below the block -- every thread indexes with that shift; the blocks at the two ends of the
+// signal by per-thread cp.async into thread-private slots with zero fill, as before.
 template <bool CPLX>
 __global__ void __launch_bounds__(kFftFirThreads, 2)
 fir_fft_kernel(const typename FirTraits<CPLX>::T *__restrict__ x, typename FirTraits<CPLX>::T *__restrict__ y,
@@ -382,49 +392,95 @@ fir_fft_kernel(const typename FirTraits<CPLX>::T *__restrict__ x, typename FirTr
     float2 *T3 = reinterpret_cast<float2 *>(buf + kFftFirN + kFftFirN / 16);
     float2 *T2 = T3 + kFftFirT3;
     T *stage = reinterpret_cast<T *>(T2 + kFftFirT2);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + kFftFirN + 4);
     const int j = threadIdx.x;
     const int V = kFftFirN - (K - 1);                      // valid outputs per block
+    constexpr int kPer16 = 16 / sizeof(T);                 // samples per 16 bytes
+    const bool x_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 
-    auto prefetch = [&](long long blk) {
+    // interior block whose window can be fetched by one aligned bulk copy
+    auto tma_ok = [&](long long blk) {
         const long long in0 = blk * V - (K - 1);
-        if (in0 >= 0 && in0 + kFftFirN <= n) {              // interior block: no per-sample checks
-            const T *src = x + in0 + j;
+        const long long a0 = in0 & ~static_cast<long long>(kPer16 - 1);
+        return x_aligned && in0 >= 0 && a0 + kFftFirN + kPer16 <= n;
+    };
+    auto shift_of = [&](long long blk) {
+        const long long in0 = blk * V - (K - 1);
+        return static_cast<int>(in0 & (kPer16 - 1));
+    };
+    auto prefetch_tma = [&](long long blk) {               // thread 0
+        const long long in0 = blk * V - (K - 1);
+        const long long a0 = in0 & ~static_cast<long long>(kPer16 - 1);
+        const uint32_t bytes = static_cast<uint32_t>((kFftFirN + ((in0 - a0) ? kPer16 : 0)) * sizeof(T));
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(stage, x + a0, bytes, bar);
+    };
+    auto prefetch_lanes = [&](long long blk) {             // every thread, its own slots
+        const long long in0 = blk * V - (K - 1);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) cp_async_zfill<sizeof(T)>(&stage[j + 256 * r], src + 256 * r, true);
-        } else {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const long long g = in0 + j + 256 * r;
-                const bool ok = g >= 0 && g < n;
-                cp_async_zfill<sizeof(T)>(&stage[j + 256 * r], x + (ok ? g : 0), ok);
-            }
+        for (int r = 0; r < 16; ++r) {
+            const long long g = in0 + j + 256 * r;
+            const bool ok = g >= 0 && g < n;
+            cp_async_zfill<sizeof(T)>(&stage[j + 256 * r], x + (ok ? g : 0), ok);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    long long blk = blockIdx.x;
-    if (blk < blocks) prefetch(blk);
+    if (j == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         T3[p * 256 + j] = __ldg(&tw[j << p]);
         if (j < 16) T2[p * 16 + j] = __ldg(&tw[(16 * j) << p]);
     }
     __syncthreads();
+    long long blk = blockIdx.x;
+    if (blk < blocks) {
+        if (tma_ok(blk)) {
+            if (j == 0) prefetch_tma(blk);
+        } else {
+            prefetch_lanes(blk);
+        }
+    }
+    uint32_t parity = 0;
 
     for (; blk < blocks; blk += gridDim.x) {
         cpk v[16];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        int shift = 0;
+        if (tma_ok(blk)) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            shift = shift_of(blk);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             if constexpr (CPLX) {
-                const float2 s = stage[j + 256 * r];
+                const float2 s = stage[j + 256 * r + shift];
                 v[r] = pack_f32x2(s.x, s.y);
             } else {
-                v[r] = pack_f32x2(stage[j + 256 * r], 0.f);
+                v[r] = pack_f32x2(stage[j + 256 * r + shift], 0.f);
             }
         }
-        if (blk + gridDim.x < blocks) prefetch(blk + gridDim.x);
-        pkfft_4096<1>(v, buf, T3, T2, j);
+        const long long nxt = blk + gridDim.x;
+        const bool nxt_tma = nxt < blocks && tma_ok(nxt);
+        // the next block's copy starts behind the first barrier of the forward transform: every thread
+        // has read its samples out of the staging buffer by then (a thread-private cp.async refill could
+        // start at once, but a block staged by lanes may be followed by one staged by TMA and vice versa,
+        // so both wait for the barrier)
+        pkfft_4096<1>(v, buf, T3, T2, j, [&]() {
+            if (nxt < blocks) {
+                if (nxt_tma) {
+                    if (j == 0) prefetch_tma(nxt);
+                } else {
+                    prefetch_lanes(nxt);
+                }
+            }
+        });
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
             const float2 hh = __ldg(&H[j + 256 * r]);
