@@ -147,6 +147,14 @@ class FusedChain:
         z = (zi[0::2] + 1j * zi[1::2])[:self.ntaps - 1]
         return z, (complex(last[0], last[1]) if self.position[2] else None)
 
+    def count_for(self, n, dec_off, has_prev):
+        """Outputs a chunk of n samples produces at decimation phase ``dec_off`` (pure arithmetic)."""
+        n, dec_off = int(n), int(dec_off)
+        m = 0 if n <= dec_off else (n - dec_off + self.decim - 1) // self.decim
+        if self.demod and not has_prev:
+            m = max(m - 1, 0)
+        return m
+
     def out_count(self, n):
         m = self._positions_in(int(n))
         if self.demod and not self._pos[2]:
