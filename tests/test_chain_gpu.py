@@ -228,3 +228,21 @@ def test_batch_of_independent_captures_in_one_launch():
     got2 = ch2.apply_batch(torch.from_numpy(caps[:2]).cuda()).cpu().numpy()
     want, _ = O.chain_stream(caps[1], fs, f, taps, fs / 33)
     assert wrap_rel_rms(got2[1], want) <= TOL
+
+
+def test_batch_of_short_captures_crosses_capture_boundaries_inside_a_warp_range():
+    """Many short captures at the NOAA decimation (warp-autonomous kernel): a warp's contiguous range of
+    tiles spans several captures, each of which must start from the reference's fresh state."""
+    import torch
+    from directdemod_b200.fused import FusedChain
+    fs, f, decim, n, ncap = 2048000, 30000.0, 34, 5002, 40
+    taps = O.taps_blackman_harris(151)[0]
+    caps = np.stack([fm_tone_c64(300 + k, n, fs, f, 900.0 + 70 * k, 2.0) for k in range(ncap)])
+    got = FusedChain(taps, decim, f, fs).apply_batch(torch.from_numpy(caps).cuda()).cpu().numpy()
+    for k in (0, 1, 7, 20, 39):
+        want, _ = O.chain_stream(caps[k], fs, f, taps, fs / decim)
+        assert got[k].shape == want.shape
+        assert wrap_rel_rms(got[k], want) <= TOL, k
+    iq = FusedChain(taps, decim, f, fs, demod=False).apply_batch(torch.from_numpy(caps).cuda()).cpu().numpy()
+    want, _ = O.chain_stream(caps[13], fs, f, taps, fs / decim, demod=False)
+    assert iq[13].shape == want.shape and O.rel_rms(iq[13], want) <= TOL
