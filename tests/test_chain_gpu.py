@@ -246,3 +246,29 @@ def test_batch_of_short_captures_crosses_capture_boundaries_inside_a_warp_range(
     iq = FusedChain(taps, decim, f, fs, demod=False).apply_batch(torch.from_numpy(caps).cuda()).cpu().numpy()
     want, _ = O.chain_stream(caps[13], fs, f, taps, fs / decim, demod=False)
     assert iq[13].shape == want.shape and O.rel_rms(iq[13], want) <= TOL
+
+
+def test_host_entry_point_pipelines_long_chunks_in_pieces():
+    """ddm_chain_apply_host splits chunks of >= 2^22 samples into four pieces whose copies run ahead of
+    the kernels: same samples as the device entry point on the same chunk, cf32 and u8, carried state
+    included (second chunk)."""
+    import torch
+    from directdemod_b200.fused import FusedChain
+    fs, f, decim = 2048000, 30000.0, 34
+    taps = O.taps_blackman_harris(151)[0]
+    n = (1 << 22) + 12345
+    x = fm_tone_c64(77, 2 * n, fs, f, 1700.0, 2.0)
+    for fmt in ("cf32", "cu8"):
+        if fmt == "cu8":
+            data = np.clip(np.rint(np.stack([x.real, x.imag], axis=1) + 127.5), 0, 255).astype(np.uint8)
+            dev_in = lambda a, b: torch.from_numpy(data[a:b]).cuda()
+            host_in = lambda a, b: data[a:b]
+        else:
+            dev_in = lambda a, b: torch.from_numpy(x[a:b]).cuda()
+            host_in = lambda a, b: x[a:b]
+        cd, chost = FusedChain(taps, decim, f, fs, in_format=fmt), FusedChain(taps, decim, f, fs, in_format=fmt)
+        for a, b in ((0, n), (n, 2 * n)):
+            want = cd.apply(dev_in(a, b)).cpu().numpy()
+            got = chost.apply_host(host_in(a, b))
+            assert got.shape == want.shape and np.array_equal(got, want), (fmt, a)
+        assert cd.position == chost.position
