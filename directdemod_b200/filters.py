@@ -118,10 +118,13 @@ class filter:
         delay line directly must first let that queue run, so state is consumed in call order like
         in the reference (which executes eagerly).  A filter whose state currently lives in a fused
         cascade (commSignal ran ``.filter(f1).filter(f2)`` as one equivalent filter) takes it back."""
+        self._flush_owner()
+        self._leave_cascade()
+
+    def _flush_owner(self):
         owner = getattr(self, "_pending_owner", None)
         if owner is not None:
             owner._flush()
-        self._leave_cascade()
 
     def _leave_cascade(self):
         cas = self.__dict__.get("_cascade")
@@ -252,11 +255,42 @@ class filter:
         xd = _dev.to_device(x)
         return _dev.to_host(self._apply_dev(xd, host_x=x))
 
+    # A stable recursive filter forgets: to 1e-9 it is an FIR of a few hundred taps (see ``cascade``).
+    # For COMPLEX chunk-sized signals that form is the faster kernel: the segment-parallel recursion
+    # repeats a ~1000-sample warm-up per segment and a 20 M-sample chunk does not leave segments long
+    # enough to hide it (107 Gsps for the 8th-order low-pass), the overlap-save FFT kernel does not care
+    # (140 Gsps for its 418-tap equivalent); slab-sized signals (290 Gsps) and real signals (half the recursion's work) stay with
+    # the recursion.  The filter's own state moves in and out like a cascade stage's.
+    _FIR_FORM_MIN, _FIR_FORM_MAX, _FIR_FORM_TAPS = 1 << 20, 50000000, 1025       # measured crossover: ~60 M samples
+
+    def _fir_form(self, xd):
+        if (self.isFIR or not self._storeState or self._needs_lfiltic or not xd.is_complex()
+                or not (self._FIR_FORM_MIN <= xd.numel() <= self._FIR_FORM_MAX)
+                or self.__dict__.get("_no_fir_form") or type(self) is cascade):
+            return None
+        cas = self.__dict__.get("_cascade")
+        if cas is not None and cas.__dict__.get("_key") == (id(self),):
+            return cas
+        try:
+            self.lookback()                        # recursive filters the library replays bit-exactly stay as they are
+            self._leave_cascade()
+            cas = cascade([self], states=[None if self._fresh else self.getState()], max_taps=self._FIR_FORM_TAPS)
+        except ValueError:
+            self._no_fir_form = True
+            return None
+        cas._key = (id(self),)
+        self._cascade = cas
+        return cas
+
     def _apply_dev(self, xd, host_x=None, _queued=False):
         if not _queued:
-            self._sync_pending()
-        else:
-            self._leave_cascade()
+            self._flush_owner()
+        cas = self._fir_form(xd)
+        if cas is not None:
+            y = cas._apply_dev(xd, _queued=True)
+            self._used = True
+            return y
+        self._leave_cascade()
         l = _lib.lib()
         h = self._handle(xd.device.index)
         self._release_chain()

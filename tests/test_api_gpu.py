@@ -795,3 +795,31 @@ def test_commsignal_runs_consecutive_filters_as_one_cascade_and_hands_state_back
     # the stages can be read on their own afterwards (state handed back) and still agree with scipy
     _, z1 = sps.lfilter(fir.getB, [1.0], x.astype(np.complex128), zi=sps.lfilter_zi(fir.getB, [1.0]))
     assert O.rel_rms(fir.getState(), z1) <= TOL
+
+
+def test_recursive_filter_takes_its_fir_form_for_complex_chunks_and_returns_to_the_recursion():
+    """An 8th-order Butterworth on complex chunks of 2^20 .. 2^26 samples runs as its equivalent FIR
+    through the overlap-save kernel; shorter chunks and state reads go back to the recursion.  The
+    stream must match scipy's stateful lfilter across the switches (filters.py:64-70)."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    fs = 2400000
+    rng = np.random.default_rng(47)
+    cuts = [0, 5000, 1205000, 2405000, 2406000, 3606000]
+    n = cuts[-1]
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    f = filters.butter(fs, 100000, n=8)
+    want, zf = sps.lfilter(f.getB, f.getA, x.astype(np.complex128), zi=sps.lfilter_zi(f.getB, f.getA))
+    parts, forms = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        parts.append(f.applyOn(x[a:b]))
+        forms.append(f.__dict__.get("_cascade") is not None)
+    got = np.concatenate(parts)
+    assert forms == [False, True, True, False, True]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        assert O.rel_rms(got[a:b], want[a:b]) <= TOL, (a, b, O.rel_rms(got[a:b], want[a:b]))
+    assert O.rel_rms(f.getState(), zf) <= 1e-5
+    # real signals keep the recursion
+    g = filters.butter(fs, 100000, n=8)
+    g.applyOn(rng.standard_normal(1300000).astype(np.float32))
+    assert g.__dict__.get("_cascade") is None
