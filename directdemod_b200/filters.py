@@ -237,6 +237,7 @@ class filter:
         _lib.check(_lib.lib().ddm_filter_set_state(self._handle(), z.ctypes.data_as(C.POINTER(C.c_double)),
                                                    _dev.stream_ptr()), "ddm_filter_set_state")
         self._needs_lfiltic = False
+        self._used = True           # no longer "fresh": a fused kernel must start from THIS state, not lfilter_zi
 
     def _release_chain(self):
         """If a fused chain owns this filter's state, take it back (commSignal fused this

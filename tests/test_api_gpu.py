@@ -823,3 +823,28 @@ def test_recursive_filter_takes_its_fir_form_for_complex_chunks_and_returns_to_t
     g = filters.butter(fs, 100000, n=8)
     g.applyOn(rng.standard_normal(1300000).astype(np.float32))
     assert g.__dict__.get("_cascade") is None
+
+
+def test_a_state_set_by_hand_survives_the_fused_paths():
+    """setState on a filter that has not run yet: the fused chain and the equivalent-FIR form must
+    start from THAT delay line, not from the reference's lfilter_zi."""
+    chunker, comm, constants, demod_fm, filters = _mods()
+    import scipy.signal as sps
+    rng = np.random.default_rng(53)
+    # stateful FIR in front of a decimator (the fusable pattern)
+    x = (rng.standard_normal(40000) + 1j * rng.standard_normal(40000)).astype(np.complex64)
+    b = sps.windows.blackmanharris(151)
+    zi = (rng.standard_normal(150) + 1j * rng.standard_normal(150))
+    bh = filters.blackmanHarris(151)
+    bh.setState(zi)
+    got = comm.commSignal(2048000, x).filter(bh).bwLim(60000).signal
+    want, _ = sps.lfilter(b, [1.0], x.astype(np.complex128), zi=zi)
+    assert O.rel_rms(got, want[::34]) <= TOL
+    # recursive filter on a long complex chunk (equivalent-FIR form)
+    fs, n = 2400000, 1200000
+    xl = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 40).astype(np.complex64)
+    f = filters.butter(fs, 100000, n=8)
+    z0 = (rng.standard_normal(8) + 1j * rng.standard_normal(8)) * 5
+    f.setState(z0)
+    w, _ = sps.lfilter(f.getB, f.getA, xl.astype(np.complex128), zi=z0)
+    assert O.rel_rms(f.applyOn(xl), w) <= TOL
