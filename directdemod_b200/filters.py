@@ -47,6 +47,12 @@ class filter:
         self._a = a
         self._bd = np.atleast_1d(np.asarray(b, dtype=np.float64)).copy()
         self._ad = np.atleast_1d(np.asarray(a, dtype=np.float64)).copy()
+        # the reference computes lfilter_zi in its constructor (filters.py:45) and so raises there for a
+        # filter without a steady state (pole at z = 1); an FIR always has one, and for 1023 taps scipy's
+        # companion-matrix solve takes 0.1 s, so only recursive filters are checked eagerly
+        self._zi0 = None
+        if self._storeState and np.any(self._ad[1:] != 0.0):
+            self._zi0 = np.ascontiguousarray(signal.lfilter_zi(self._b, self._a), dtype=np.float64)
         self._h = None              # ddm_filter handle, created on first use (needs the GPU)
         self._needs_lfiltic = self._storeState and self._initOut is not None
         self._chain = None          # fused chain currently holding this filter's state
@@ -98,7 +104,8 @@ class filter:
             if self._state_len() > 0 and (self._storeState or self._zeroPhase):
                 # scipy's own lfilter_zi, so even ill-conditioned filters start from the very
                 # bits the reference starts from (filters.py:45)
-                zi = np.ascontiguousarray(signal.lfilter_zi(self._b, self._a), dtype=np.float64)
+                zi = self._zi0 if self._zi0 is not None else \
+                    np.ascontiguousarray(signal.lfilter_zi(self._b, self._a), dtype=np.float64)
                 _lib.check(l.ddm_filter_set_zi_base(h, zi.ctypes.data_as(C.POINTER(C.c_double))),
                            "ddm_filter_set_zi_base")
             if IIR_AUTO_FLOOR is not None and not hasattr(self, "_shard_floor"):
