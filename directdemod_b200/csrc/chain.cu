@@ -1010,7 +1010,7 @@ bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int 
     if (const char *e = std::getenv("DDM_STREAM_STAGES")) forced_s = std::atoi(e);
     auto fits = [&](int w, int s_) { return stream_fixed_bytes(Q, DP, w, s_) + stage * w * s_ <= budget; };
     if (forced_w > 0 && forced_s > 0) {
-        const int max_w = (Q == 5 && in_format == DDM_IN_CF32) ? 16 : kStreamMaxWarps;
+        const int max_w = Q == 5 ? 16 : kStreamMaxWarps;
         if (forced_w > max_w || forced_s > kStreamMaxStages || forced_s < 1 || !fits(forced_w, forced_s)) return false;
         *warps = forced_w;
         *stages = forced_s;
@@ -1019,10 +1019,11 @@ bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int 
     const size_t ring_target = 150 * 1024;
     // Q <= 5 (the NOAA configuration: 151 taps, D = 31 .. 37) has a 128-register build: sixteen warps with
     // ONE stage each -- the other fifteen warps cover a warp's reload -- measured as fast as eight warps
-    // with two stages (2.17 ms) and without their slow outliers (p90 2.19 against 2.5 ms)
-    if (Q == 5 && in_format == DDM_IN_CF32 && stage * 16 <= ring_target) {
+    // with two stages (2.17 ms) and without their slow outliers (p90 2.19 against 2.5 ms); 8-bit input, which
+    // is bound by the unpacking arithmetic, gains 3.6 % from the sixteen warps (1.97 -> 1.90 ms per 1.84 G samples)
+    if (Q == 5 && stage * 16 <= ring_target) {
         *warps = 16;
-        *stages = 1;
+        *stages = (in_format == DDM_IN_CU8 && stage * 32 <= ring_target) ? 2 : 1;      // u8 stages are a quarter the size
         return true;
     }
     for (int w : {12, 8}) {
@@ -1051,7 +1052,7 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
     const int W = c->st_warps, S = c->st_stages;
     const size_t smem = stream_fixed_bytes(Q, c->DP, W, S) + stream_stage_bytes(c->D, IN) * W * S;
     auto kern = chain_stream_kernel<Q, MIX, OUT, IN>;
-    if constexpr (Q == 5 && IN == DDM_IN_CF32) {
+    if constexpr (Q == 5) {
         if (W > kStreamMaxWarps) kern = chain_stream_kernel<Q, MIX, OUT, IN, 16>;      // 128-register build
     }
     if (!c->st_attr[p.s]) {   // first launch of this variant on this handle's device
