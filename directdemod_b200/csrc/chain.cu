@@ -994,14 +994,13 @@ size_t chain_smem_bytes(int Q, int D, int DP, int in_format = DDM_IN_CF32) {
 }
 
 // Geometry of the warp-autonomous kernel for one (D, input format): W warps (one CTA per SM), each with
-// a private ring of S stages of 32 blocks.  Measured on B200 (profiles/r02_chain_ab.jsonl,
-// scripts/microbench/readbw3.cu): the kernel is bound by instruction latency, not by bytes in flight --
-// a read-only ring reaches 7.4 TB/s with ~140 KB of stages per SM and gets SLOWER with 200 KB -- so the
-// rule is: as many warps as possible in multiples of four (equal load on the four schedulers), two
-// stages each (one with sixteen warps), rings of at most ~150 KB per SM.  Blocks too long for eight warps under that rule
-// (cf32: D >= 40) stay with the CTA-tiled kernel, whose 128-block tiles amortise the per-tile work
-// better there; blocks too long for THAT kernel's two 128-block stages (D > 110) come back here with
-// four, two or one warp.
+// a private ring of S stages of 32 blocks.  Measured on B200 (profiles/r02_chain_ab*.jsonl,
+// r02_chain_dsweep.txt, scripts/microbench/readbw3.cu): the kernel is bound by instruction latency, not
+// by bytes in flight -- a read-only ring reaches 7.4 TB/s with ~140 KB of stages per SM and gets SLOWER
+// with 200 KB -- so the rule is: as many warps as possible in multiples of four (equal load on the four
+// schedulers), rings of at most ~150 KB per SM, a second stage per warp only if it fits under that.
+// Returns false where the CTA-tiled kernel is the better tool (blocks of 19 KB and more, D >= 76 for
+// cf32, which it stages up to D = 110) -- beyond that this kernel comes back with four, two or one warp.
 bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int *warps, int *stages) {
     const size_t stage = stream_stage_bytes(D, in_format);
     const size_t budget = 227 * 1024;
@@ -1026,16 +1025,23 @@ bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int 
         *stages = (in_format == DDM_IN_CU8 && stage * 32 <= ring_target) ? 2 : 1;      // u8 stages are a quarter the size
         return true;
     }
-    for (int w : {12, 8}) {
-        if (stage * w * 2 <= ring_target) {
-            int s_ = 2;
+    // everything else: the most warps (12, else 8) whose rings stay under the target, two stages each if
+    // that still fits, else one.  Measured against the CTA-tiled kernel on the 1.84 G-sample pass
+    // (profiles/r02_chain_ab.jsonl, r02_chain_dsweep.txt): D = 20 2.86 vs 3.28 ms, D = 24 3.08 vs 3.70,
+    // D = 40 2.75 vs 3.16, D = 68 2.14 vs 2.39; a tie around D = 50 (2.19 vs 2.17), where the CTA-tiled
+    // kernel's 128-block tiles amortise the per-tile work as well as eight warps hide it -- it keeps the
+    // blocks of 12.5 .. 14 KB -- and the CTA-tiled kernel ahead from D = 74 on (D = 100: 2.07 vs 2.14).
+    const bool tie_zone = in_format == DDM_IN_CF32 && stage > 12800 - 1 && stage < 14 * 1024 && legacy_fits;
+    if (!tie_zone)
+        for (int w : {12, 8}) {
+            if (stage * w > ring_target) continue;
+            int s_ = stage * w * 2 <= ring_target ? 2 : 1;
             if (in_format == DDM_IN_CU8)               // short stages: a deeper ring costs nothing
                 while (s_ < 4 && stage * w * (s_ + 1) <= ring_target) ++s_;
             *warps = w;
             *stages = s_;
             return true;
         }
-    }
     if (legacy_fits) return false;
     for (int w : {4, 2, 1})
         if (fits(w, 2)) {
