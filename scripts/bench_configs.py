@@ -185,6 +185,7 @@ def c3(quick):
         acc_p = float(pp[-1])
         x[a:b] = torch.polar(torch.full_like(pp, 50.0), torch.remainder(pp, 1.0) * (2 * np.pi)).to(torch.complex64)
         torch.view_as_real(x[a:b]).add_(torch.empty((b - a, 2), device="cuda").normal_(0, 1.0, generator=g))
+    afsk.front_end(DeviceSource(x[:40000000], fs), 0.0, bw)      # first use: lazy kernel loading, filter analysis
     t_fe, (sig, bf, ch) = wall(lambda: afsk.front_end(DeviceSource(x, fs), 0.0, bw))
     emit(config="C3 AFSK1200 front end, %d s @ 960 kHz IQ -> 48 kHz (chain, FM, BP, bank, edges)" % seconds,
          samples=n, audio_samples=int(bf.numel()), total_ms=round(t_fe * 1e3, 2), msps_iq=round(n / t_fe / 1e6, 1))
