@@ -160,6 +160,8 @@ class filter:
         band-passes is itself only good to 4e-5 .. 3e-4 -- can raise it (decode_noaa.getImage and
         afsk.front_end do) and stream such filters at HBM speed."""
         self._unshare()
+        self.__dict__.pop("_cascadable", None)        # (commSignal's cached verdict depends on this switch)
+        self.__dict__.pop("_no_fir_form", None)
         self._shard_floor = float(floor) if floor > 0 else 1e-7
         _lib.check(_lib.lib().ddm_filter_set_iir_auto_floor(self._handle(), float(floor)),
                    "ddm_filter_set_iir_auto_floor")

@@ -97,6 +97,12 @@ int ddm_chain_set_position(ddm_chain *c, int64_t n0, int64_t dec_off, int has_pr
 /* copy the current halo (the last halo_len raw input samples seen) to halo_dev */
 int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream);
 
+/* One chunk of the stream: x_dev (device, n samples in the handle's input format) -> out_dev (device,
+ * f32 or cf32), *n_out results; the carried state advances by n samples.  One kernel launch for the
+ * configurations of the fused fast path (decimation >= 2, at most 10 partial sums per output: 151
+ * taps from D = 16 on), which is either the warp-autonomous kernel (per-warp TMA rings, partial sums
+ * exchanged by shuffles) or the CTA-tiled one, chosen per block length (chain.cu, stream_geometry);
+ * any other configuration runs the general float64-accumulating kernels. */
 int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n,
                         void *out_dev, int64_t out_capacity, int64_t *n_out, void *stream);
 /* `batch` independent captures of n samples each (capture k at x_dev + k*x_stride samples), every
@@ -105,6 +111,10 @@ int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n,
  * per capture.  The handle is reset and left in its reset state. */
 int ddm_chain_apply_batch_dev(ddm_chain *c, const void *x_dev, int64_t n, int64_t batch, int64_t x_stride,
                               void *out_dev, int64_t out_stride, int64_t *n_out, void *stream);
+/* The same for HOST buffers (what source.read(a, b) returned; the audio array): copies in, runs the
+ * chain, copies the results back, returns when they are there.  Chunks of >= 2^22 samples go through in
+ * four pieces whose host->device copies are queued ahead of the kernels on a second stream.  Pinned
+ * host memory makes the copies asynchronous; pageable memory works, slower. */
 int ddm_chain_apply_host(ddm_chain *c, const void *x_host, int64_t n,
                          void *out_host, int64_t out_capacity, int64_t *n_out, void *stream);
 
