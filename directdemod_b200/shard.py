@@ -94,7 +94,6 @@ class TimeShardedChain:
         its first ``head`` samples) needs no neighbour data -- its history is the end of the head -- so
         its launch is queued while the NCCL send/recv is in flight, and only the short head launch
         waits for the halo.  Same samples, same global positions, same results as one launch."""
-        import torch
         import torch.distributed as dist
         n = self.end - self.start
         if x_slab.numel() != n:
@@ -117,6 +116,18 @@ class TimeShardedChain:
         if self.rank + 1 < self.world:
             ops.append(dist.P2POp(dist.isend, x_slab[-self.halo_len:].contiguous(), self.rank + 1, self.group))
         reqs = dist.batch_isend_irecv(ops)
+        out, head, m_head = self._launch_body(x_slab)
+        for r in reqs:
+            r.wait()
+        return self._launch_head(x_slab, self._recv, out, head, m_head)
+
+    def _launch_body(self, x_slab):
+        """Everything behind the slab's first ``head`` samples: needs no neighbour data (its history is
+        the end of the head).  Returns (output tensor with the body part filled in, head, head outputs)."""
+        import torch
+        ch = self.chain
+        n = self.end - self.start
+        off = decim_offset_at(self.start, self.decim)
         # head: a whole number of decimation periods, at least the halo, ~1 M samples; the body starts
         # on a kept sample like the slab itself
         step = 2 * self.decim                                      # even: the body stays 16-byte aligned
@@ -131,9 +142,12 @@ class TimeShardedChain:
         if head < n:
             ch.set_position(self.start + head, off_body, True, x_slab[head - self.halo_len:head])
             ch.apply(x_slab[head:], out=out[m_head:])
-        for r in reqs:
-            r.wait()
-        ch.set_position(self.start, off, True, self._recv)
+        return out, head, m_head
+
+    def _launch_head(self, x_slab, halo, out, head, m_head):
+        """The slab's first ``head`` samples, behind the halo received from the previous rank."""
+        ch = self.chain
+        ch.set_position(self.start, decim_offset_at(self.start, self.decim), True, halo)
         ch.apply(x_slab[:head], out=out[:m_head])
         return out
 

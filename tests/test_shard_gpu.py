@@ -137,3 +137,34 @@ def test_time_sharded_c4_cascade_slabs_on_one_gpu():
     assert O.rel_rms(got, want) <= TOL
     for a in np.cumsum([len(p) for p in parts])[:-1]:                              # no seam at the slab joins
         assert O.rel_rms(got[a - 500:a + 500], want[a - 500:a + 500]) <= TOL
+
+
+def test_time_sharded_chain_body_then_head_on_one_gpu():
+    """What a rank > 0 of a time-sharded stream launches -- the slab's body first (no neighbour data
+    needed), its head once the halo has arrived -- run for every rank of a 3-way split on ONE device with
+    the halo handed over directly: the parts concatenate to the single-launch result, also for a slab
+    too short to be split and for an odd decimation factor."""
+    import torch
+    from directdemod_b200 import shard
+    from directdemod_b200.fused import FusedChain
+    for decim, fs, n in ((34, 2048000, 9000000), (33, 2048000, 7000003), (34, 2048000, 2500000)):
+        f, world = 30000.0, 3
+        taps = O.taps_blackman_harris(151)[0]
+        x = fm_tone_c64(31, n, fs, f, 1300.0, 2.0)
+        xd = torch.from_numpy(x).cuda()
+        single = FusedChain(taps, decim, f, fs).apply(xd).cpu().numpy()
+        parts = []
+        for rank in range(world):
+            ts = shard.TimeShardedChain(taps, decim, f, fs, n, rank, world, device=0)
+            slab = xd[ts.start:ts.end]
+            if rank == 0:
+                ts.chain.set_position(0, 0, False)
+                parts.append(ts.chain.apply(slab).cpu().numpy())
+                continue
+            out, head, m_head = ts._launch_body(slab)
+            assert (head < slab.numel()) == (slab.numel() > (1 << 20) + 2 * ts.halo_len + 2 * decim)
+            y = ts._launch_head(slab, xd[ts.start - ts.halo_len:ts.start].contiguous(), out, head, m_head)
+            parts.append(y.cpu().numpy())
+        got = np.concatenate(parts)
+        assert got.shape == single.shape, (decim, n)
+        assert np.max(np.abs(np.angle(np.exp(1j * (got.astype(np.float64) - single))))) <= 1e-6, (decim, n)
