@@ -457,22 +457,29 @@ chain_fused_kernel(const ChainParams P) {
 // fast path, second generation: warp-autonomous streams.
 //
 // ncu on chain_fused_kernel (profiles/r02_chain_fused_v1_warpstates.csv) showed the CTA-tiled kernel
-// waiting, not issuing: half of its executed instructions are the mbarrier spin, a CTA holds one
-// 34.8 KB tile in flight while it works on the other, and the per-tile CTA barrier plus the
-// thread-0 address arithmetic sit between "tile consumed" and "next copy issued".  Here the unit
-// of scheduling is the WARP:
+// bound by instruction latency, not by its copies: issue slots 43 % busy, stall samples "wait" 33 %,
+// short scoreboard 16 %, CTA barrier 9 %, the mbarrier under 2 % -- two warps per scheduler cannot cover
+// a 640-instruction tile of which half is per-tile work (rotator sincospif, atan2f, index arithmetic, the
+// partial-sum exchange through shared memory behind a barrier, Q halo blocks recomputed per tile).  Here
+// the unit of scheduling is the WARP:
 //   * every warp owns a contiguous range of 32-block tiles of the stream and a private ring of
-//     kStreamStages stages with its own mbarriers; lane 0 re-arms a stage with the tile S steps
-//     ahead as soon as the warp has read it (one __syncwarp, no CTA barrier anywhere in the loop),
-//     so a warp keeps S-1 .. S tiles in flight and an SM with 8 warps ~ 200 KB;
+//     P.stages stages with its own mbarriers; lane 0 re-arms a stage (one bulk copy for an interior
+//     tile) as soon as the warp has read it -- one __syncwarp, no CTA barrier anywhere in the loop.
+//     Up to sixteen warps per SM with one stage each (the others cover a warp's reload) or 8 / 12
+//     warps with two: the host picks per block length (stream_geometry) from measurements;
 //   * the partial sums never touch shared memory: lane l needs P_q of lane l-q -- one shuffle --
 //     and the first q lanes take it from the previous tile of the same warp, which every lane
 //     still holds in registers (source lane s hands out its current sum when s < 32-q, else its
 //     previous one).  Consecutive tiles of a warp are consecutive in the stream, so there is no
 //     halo block to recompute (the CTA-tiled kernel re-read and re-accumulated Q of every 128
 //     blocks); a range starts with one warm-up tile whose outputs are dropped.
-// Block geometry, tap tables, accumulation (chain_accumulate) and summation order are those of
-// the first kernel, so the results are bit-identical to it.
+//   * the block rotator is a float64 complex number advanced by one multiplication per tile and
+//     recomputed exactly at every 64th tile of a capture (a range that starts between two anchors
+//     repeats the multiplications from the anchor: a tile's value does not depend on the partition);
+//     atan2f is a degree-8 polynomial with one MUFU.RCP.
+// Block geometry, tap tables, accumulation (chain_accumulate) and summation order are those of the first
+// kernel; results agree with it to the last bits of the rotator and the arctangent (rms 6e-8 rad).
+// LBW: launch bound in warps -- the 16-warp build (Q = 5 only) has to fit 128 registers.
 // Tile t of a capture holds blocks 32 (t-1) .. 32 t - 1: tile 0 is the capture's own warm-up tile
 // (history from the halo buffer), tile t >= 1 produces outputs m = 32 (t-1) + lane.
 // ------------------------------------------------------------------------------------
