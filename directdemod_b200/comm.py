@@ -7,8 +7,9 @@ dtype.  Operators that form the hot chain
     offsetFreq(f) -> filter(<stateful FIR>) -> bwLim(rate) -> funcApply(demod_fm().demod)
 
 (decode_noaa.py:623, decode_fm.py:64-68, decode_afsk1200.py:79-91) are queued and executed
-as ONE fused kernel launch per chunk (directdemod_b200/fused.py, csrc/chain.cu); anything
-else runs operator by operator on the device.  All carried state (mixer sample index and
+as ONE fused kernel launch per chunk (directdemod_b200/fused.py, csrc/chain.cu); consecutive
+stateful filters over a long chunk -- ``filter(fir).filter(iir)`` -- run as one equivalent filter in
+one overlap-save pass (filters.cascade); anything else runs operator by operator on the device.  All carried state (mixer sample index and
 decimation phase in the chunker, filter delay line, FM last sample) keeps the reference's
 meaning and can move between the fused and the stand-alone kernels at any chunk boundary.
 """

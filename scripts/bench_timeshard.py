@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""One long stream split in time across the GPUs of a box (torchrun, NCCL halo exchange):
+"""(Round 1; bench.py now carries both measurements as the sub-records `timeshard_chain` and `c4_cascade`
+of its JSON line, with seam self-checks.)
+One long stream split in time across the GPUs of a box (torchrun, NCCL halo exchange):
 (a) the fused chain on a C2-like stream, (b) the C4 cascade (1023-tap Remez + 8th-order
 Butterworth).  Strong scaling: the stream length is fixed, every rank holds 1/world of it.
 Device time per rank by CUDA events (halo exchange included), max over ranks.
