@@ -273,3 +273,42 @@ def test_cascade_equivalent_filter_reproduces_the_stage_by_stage_result():
         filters.cascade([filters.filter([1.0], [1.0, -1.0])])               # integrator: pole on the unit circle
     with pytest.raises(ValueError):
         filters.cascade([filters.butter(60235, 400, 4400, n=6, typeFlt=constants.FLT_BP)], max_taps=64)
+
+
+def test_chain_position_mirror_follows_the_reference_carry_rules():
+    """fused.FusedChain keeps (sample counter, decimation offset, has-previous) on the host so the
+    decoders' 93-chunk loops size their outputs without asking the library.  The mirror is pure
+    integer arithmetic: pin it to the oracle's chunk loop (comm.py:76, comm.py:124, demod_fm.py:44-48)
+    on ragged chunk sizes, including chunks shorter than the carried offset (an empty chunk, which
+    scipy's lfilter refuses, must leave the mirror where it was)."""
+    from directdemod_b200 import fused
+    from oracle import ddoracle as od
+
+    rng = np.random.default_rng(11)
+    for decim, demod in [(1, True), (2, False), (7, True), (34, True), (50, False), (341, True)]:
+        ch = object.__new__(fused.FusedChain)        # no device: only the host arithmetic is exercised
+        ch.decim, ch.demod, ch._pos = decim, demod, (0, 0, False)
+        taps = np.array([0.5, 0.5])
+        st = od.ChainState(taps)
+        fs = 1000 * decim
+        sizes = [1, 0, max(decim - 1, 1), decim, decim + 1, 3, 0] + list(rng.integers(1, 5 * decim + 3, 40))
+        for n in sizes:
+            n = int(n)
+            if n == 0:
+                before = ch.position_cached
+                assert ch.out_count(0) == 0
+                ch._advance(0)
+                assert ch.position_cached == before
+                continue
+            x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+            kept, _ = od.chain_chunk(x, fs, 0.0, taps, fs // decim, st, demod=False)
+            if demod and len(kept):          # demod_fm.py:44-51 (it raises on an empty chunk; here: 0 outputs)
+                want, st.fm_last = od.fm_discriminator(kept, st.fm_last)
+            else:
+                want = kept
+            assert ch.out_count(n) == len(want), (decim, demod, n)
+            assert ch.count_for(n, ch._pos[1], ch._pos[2]) == len(want)
+            ch._advance(n)
+            assert ch.position_cached[0] == st.n0
+            assert ch.position_cached[1] == st.dec_off
+            assert ch.position_cached[2] == (st.fm_last is not None) or not demod
