@@ -54,6 +54,7 @@ constexpr int kChainUnroll = DDM_CHAIN_UNROLL;   // 4-sample bodies per loop tri
 struct ChainParams {
     const void *x;         // chunk, n samples (cf32 or interleaved u8 pairs)
     const void *halo;      // H samples that precede the chunk, same format
+    void *halo_out;        // the other halo buffer: receives the last H samples of the chunk (or NULL)
     void *out;             // f32 (FM) or cf32 (IQ)
     const float *taps;     // [Q][DP]
     const float2 *rot;     // [DP] exp(-j 2 pi r a)
@@ -73,6 +74,23 @@ struct ChainParams {
     int stages;               // ring depth per warp (warp-autonomous kernel)
     double step_re, step_im;  // exp(-j 2 pi r 32 D): the block rotator's advance per warp tile
 };
+
+// The carry of the delay line, done by the kernel that consumes the chunk: the last CTA copies the last H
+// raw samples into the handle's second halo buffer (the host swaps the two), so a chunk costs one launch
+// and no copy node between consecutive chunks' kernels.
+template <bool U8>
+__device__ __forceinline__ void save_halo(const ChainParams &P, int tid, int nthreads) {
+    if (P.halo_out == nullptr || blockIdx.x != gridDim.x - 1) return;
+    if (U8) {
+        const uchar2 *src = static_cast<const uchar2 *>(P.x) + (P.n - P.H);
+        uchar2 *dst = static_cast<uchar2 *>(P.halo_out);
+        for (int i = tid; i < P.H; i += nthreads) dst[i] = src[i];
+    } else {
+        const float2 *src = static_cast<const float2 *>(P.x) + (P.n - P.H);
+        float2 *dst = static_cast<float2 *>(P.halo_out);
+        for (int i = tid; i < P.H; i += nthreads) dst[i] = src[i];
+    }
+}
 
 __device__ __forceinline__ double2 cmuld(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -308,6 +326,7 @@ chain_fused_kernel(const ChainParams P) {
         s_ry[i] = make_float2(-r.y, r.y);
         s_c[i] = make_float2(0.5f * (r.x - r.y), 0.5f * (r.x + r.y));
     }
+    save_halo<U8>(P, tid, NT);
     __syncthreads();
 
     const long long n_even = P.n & ~1LL;
@@ -486,7 +505,7 @@ chain_fused_kernel(const ChainParams P) {
 constexpr int kStreamMaxWarps = 12;                      // warps per CTA (one CTA per SM)
 constexpr int kStreamMaxStages = 8;
 constexpr int kStreamTile = 32;                          // blocks per warp tile
-constexpr int kStreamMinTiles = 8;                       // per warp: bounds the warm-up overhead of short chunks
+constexpr int kStreamMinTiles = 4;                       // per warp: bounds the warm-up overhead of short chunks
 
 __host__ __device__ inline size_t stream_stage_bytes(int D, int in_format) {
     return in_format == DDM_IN_CU8 ? ((static_cast<size_t>(kStreamTile) * D * 2 + 32 + 15) & ~static_cast<size_t>(15))
@@ -518,6 +537,14 @@ chain_stream_kernel(const ChainParams P) {
     const unsigned stage_bytes = static_cast<unsigned>(stream_stage_bytes(D, IN));
     unsigned char *ring = smem_raw + stream_fixed_bytes(Q, DP, nw_cta, S) + static_cast<size_t>(warp) * S * stage_bytes;
 
+    // Programmatic dependent launch: the chunk loops queue this kernel back to back, each launch depending
+    // on the one before only through the halo.  The next launch may be scheduled as soon as every CTA of
+    // this one has started, so its CTAs take over SMs as they fall free and do their set-up (barriers, tables
+    // -- the handle's constants, written at creation) during this launch's tail; everything that reads the
+    // chunk, the halo or anything else an earlier kernel may have produced comes after griddepcontrol.wait,
+    // which returns when all earlier work in the stream is complete and visible.  Launched without the
+    // attribute both instructions are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (lane == 0) {
         for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
         fence_mbar_init();
@@ -529,6 +556,8 @@ chain_stream_kernel(const ChainParams P) {
         s_ry[i] = make_float2(-r.y, r.y);
         s_c[i] = make_float2(0.5f * (r.x - r.y), 0.5f * (r.x + r.y));
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    save_halo<U8>(P, tid, nthreads);
     __syncthreads();                          // the only CTA barrier: tables and barriers are set up
 
     // ---- this warp's range of the global tile sequence (captures back to back) ----
@@ -557,16 +586,19 @@ chain_stream_kernel(const ChainParams P) {
     const long long lim_fast = U8 ? (end_all < n8 ? end_all : n8) : (end_all < n_even ? end_all : n_even);
 
     // lane 0: start the bulk copies that fill `stage` with tile t of capture c
-    auto issue = [&](long long c, int t, int stage) {
+    // `first` > 0: a warm-up tile in the interior of a capture, of which only blocks first..31 are needed
+    // (their partial sums feed the first emitted tile) -- the copy starts there
+    auto issue = [&](long long c, int t, int stage, int first) {
         unsigned char *dst = ring + stage * stage_bytes;
         const long long S0 = P.b0 + (t - 1) * tile_samples;                  // first sample (may be < 0)
         if (U8) {
             const unsigned char *xb = static_cast<const unsigned char *>(P.x) + c * P.x_stride * 2;
             if (S0 >= 0 && ((S0 + tile_samples + 7) & ~7LL) <= lim_fast) {   // interior tile: one aligned copy
                 const long long S0a = S0 & ~7LL;
-                const uint32_t bytes = static_cast<uint32_t>((((S0 + tile_samples + 7) & ~7LL) - S0a) * 2);
+                const long long S1a = (S0 + static_cast<long long>(first) * D) & ~7LL;
+                const uint32_t bytes = static_cast<uint32_t>((((S0 + tile_samples + 7) & ~7LL) - S1a) * 2);
                 mbar_arrive_expect_tx(&mbar[stage], bytes);
-                bulk_g2s(dst, xb + S0a * 2, bytes, &mbar[stage]);
+                bulk_g2s(dst + (S1a - S0a) * 2, xb + S1a * 2, bytes, &mbar[stage]);
                 return;
             }
             long long E = S0 + tile_samples;
@@ -598,8 +630,9 @@ chain_stream_kernel(const ChainParams P) {
         }
         const float2 *xf = static_cast<const float2 *>(P.x) + c * P.x_stride;
         if (S0 >= 0 && S0 + tile_samples <= lim_fast) {                       // interior tile: one copy
-            mbar_arrive_expect_tx(&mbar[stage], stage_bytes);
-            bulk_g2s(dst, xf + S0, stage_bytes, &mbar[stage]);
+            const unsigned lead = static_cast<unsigned>(first) * D * 8;       // first is even: a multiple of 16 bytes
+            mbar_arrive_expect_tx(&mbar[stage], stage_bytes - lead);
+            bulk_g2s(dst + lead, xf + S0 + static_cast<long long>(first) * D, stage_bytes - lead, &mbar[stage]);
             return;
         }
         long long E = S0 + tile_samples;
@@ -624,8 +657,11 @@ chain_stream_kernel(const ChainParams P) {
             bulk_g2s(dst + (c_beg - S0) * 8, xf + c_beg, static_cast<uint32_t>((c_end - c_beg) * 8), &mbar[stage]);
     };
 
+    // blocks of an interior warm-up tile that matter: the last Q (rounded up to even, which keeps the
+    // copy's start on a 16-byte boundary for odd D)
+    const int warm_first = skip ? WT - (Q + (Q & 1)) : 0;
     for (int i = 0; i < S && itodo > 0; ++i) {
-        if (lane == 0) issue(icap, itile, i);
+        if (lane == 0) issue(icap, itile, i, i == 0 ? warm_first : 0);
         --itodo;
         if (++itile == NTC) {
             itile = 0;
@@ -663,7 +699,7 @@ chain_stream_kernel(const ChainParams P) {
         unsigned long long acc[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) acc[q] = 0ULL;
-        if (jblk < P.M) {
+        if (jblk < P.M && (k > 0 || lane >= warm_first)) {
             unsigned sp_off = static_cast<unsigned>(lane) * D * ES;
             if (U8) {
                 const long long S0 = P.b0 + (tile - 1) * tile_samples;
@@ -678,7 +714,7 @@ chain_stream_kernel(const ChainParams P) {
         if (itodo > 0) {
             if (lane == 0) {
                 fence_proxy_async();
-                issue(icap, itile, stage);
+                issue(icap, itile, stage, 0);
             }
             --itodo;
             if (++itile == NTC) {
@@ -976,6 +1012,10 @@ struct ddm_chain {
     int es = 8;                              // bytes per input sample
     long long n_real = 0;                    // real samples in the halo (u8: the rest is virtual)
     int cur = 0;
+    bool pdl = true;                         // programmatic dependent launch of the warp-autonomous kernel (DDM_CHAIN_NO_PDL: A/B)
+    bool halo_in_kernel = true;              // the fused kernel carries the halo itself (DDM_CHAIN_HALO_MEMCPY: A/B switch)
+    double step_re = 1, step_im = 0;         // block rotator advance of the warp-autonomous kernel (set once)
+    bool step_set = false;
     double2 *d_ytmp = nullptr;
     size_t ytmp_cap = 0;
     void *d_in = nullptr, *d_out = nullptr;  // staging for the _host entry point
@@ -1073,16 +1113,19 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
         c->st_attr[p.s] = true;
     }
     p.stages = S;
-    {
+    if (!c->step_set) {
         // the block rotator's advance per warp tile, exp(-j 2 pi r 32 D), from the double-double r
         const long double span = static_cast<long double>(kStreamTile) * c->D;
         long double t = static_cast<long double>(c->r_hi) * span;
         t -= std::floor(t);
         t += static_cast<long double>(c->r_lo) * span;
         const long double ang = 2.0L * 3.14159265358979323846264338327950288L * t;
-        p.step_re = static_cast<double>(std::cos(ang));
-        p.step_im = static_cast<double>(-std::sin(ang));
+        c->step_re = static_cast<double>(std::cos(ang));
+        c->step_im = static_cast<double>(-std::sin(ang));
+        c->step_set = true;
     }
+    p.step_re = c->step_re;
+    p.step_im = c->step_im;
     p.num_tiles = 1 + (p.M + kStreamTile - 1) / kStreamTile;        // per capture, warm-up tile 0 included
     if (p.num_tiles >= (1LL << 31) - 2) {
         set_error("chunk too long for one launch of the fused chain (%lld tiles)", static_cast<long long>(p.num_tiles));
@@ -1094,8 +1137,17 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
     if (warps < 1) warps = 1;
     p.stream_warps = warps;
     const unsigned grid = static_cast<unsigned>((warps + W - 1) / W);
-    kern<<<grid, 32 * W, smem, st>>>(p);
-    DDM_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    DDM_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return DDM_OK;
 }
@@ -1265,6 +1317,8 @@ int ddm_chain_create(int device, const double *taps, int ntaps, int decim, doubl
     const int qmax = (K + 1 + D - 1) / D;
     c->DP = (D + 3) & ~3;
     c->es = in_format == DDM_IN_CU8 ? 2 : 8;
+    c->halo_in_kernel = std::getenv("DDM_CHAIN_HALO_MEMCPY") == nullptr;
+    c->pdl = std::getenv("DDM_CHAIN_NO_PDL") == nullptr;
     const bool legacy = std::getenv("DDM_CHAIN_LEGACY") != nullptr;         // A/B against the CTA-tiled kernel
     const bool legacy_fits = D >= 2 && qmax <= kChainMaxQ && chain_smem_bytes(qmax, D, c->DP, in_format) <= 227 * 1024;
     c->stream = !legacy && D >= 2 && qmax <= kChainMaxQ &&
@@ -1563,6 +1617,7 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
     const unsigned char *x = static_cast<const unsigned char *>(x_dev);
     const int D = c->D;
     const size_t es = static_cast<size_t>(c->es);
+    bool halo_saved = false;
 
     if (M > 0) {
         const bool aligned = (reinterpret_cast<uintptr_t>(x_dev) & 15) == 0;
@@ -1593,8 +1648,13 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
             p.a_lastq = c->a_lastq[s];
             p.batch = 1;
             p.x_stride = p.out_stride = 0;
+            if (n >= c->H && c->halo_in_kernel) p.halo_out = c->d_halo[c->cur ^ 1];
             int rc = launch_fused(c, Q, p, st);
             if (rc != DDM_OK) return rc;
+            if (p.halo_out != nullptr) {
+                c->cur ^= 1;
+                halo_saved = true;
+            }
         } else {
             const size_t need = static_cast<size_t>(M + 1);
             if (need > c->ytmp_cap) {
@@ -1652,7 +1712,9 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
     }
 
     // ---- carry: halo <- last H samples of (halo ++ x) ----
-    if (n >= c->H) {
+    if (halo_saved) {
+        // the fused kernel wrote it (save_halo)
+    } else if (n >= c->H) {
         DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], x + (n - c->H) * es, es * c->H, cudaMemcpyDeviceToDevice, st));
     } else if (n > 0) {
         const int nxt = c->cur ^ 1;

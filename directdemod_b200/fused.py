@@ -28,6 +28,16 @@ def _stream_ptr(device_index):
     return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
 
 
+def _raw_stream_getter():
+    """device index -> current stream handle as an int.  torch's C-level getter when this build has
+    it (no Stream object per call on the chunk loops), else the public route."""
+    torch = _torch()
+    fast = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if fast is not None:
+        return fast
+    return lambda dev: torch.cuda.current_stream(dev).cuda_stream
+
+
 class FusedChain:
     def __init__(self, taps, decim, freq_offset, samp_rate, demod=True, device=None, in_format="cf32"):
         """in_format: "cf32" (complex64 samples) or "cu8" (interleaved unsigned 8-bit I/Q exactly as
@@ -65,6 +75,7 @@ class FusedChain:
         # two C calls per chunk on the 93-chunk loops of the decoders
         self._pos = (0, 0, False)
         self._fn_apply = self._l.ddm_chain_apply_dev
+        self._raw_stream = _raw_stream_getter()
         self._dev_str = "cuda:%d" % self.device
 
     # -- lifetime ---------------------------------------------------------------------
@@ -191,7 +202,7 @@ class FusedChain:
             raise ValueError("out tensor must be contiguous %s with >= %d elements" % (dt, m))
         got = C.c_int64()
         rc = self._fn_apply(self._h, x.data_ptr(), n, out.data_ptr(), out.numel(), C.byref(got),
-                            torch.cuda.current_stream(self.device).cuda_stream)
+                            self._raw_stream(self.device))
         if rc != 0:
             _lib.check(rc, "ddm_chain_apply_dev")
         self._advance(n)

@@ -272,3 +272,52 @@ def test_host_entry_point_pipelines_long_chunks_in_pieces():
             got = chost.apply_host(host_in(a, b))
             assert got.shape == want.shape and np.array_equal(got, want), (fmt, a)
         assert cd.position == chost.position
+
+
+@pytest.mark.parametrize("fmt", ["cf32", "cu8"])
+@pytest.mark.parametrize("decim,fs", [(34, 2048000), (33, 2048000), (20, 960000)])
+def test_chunk_loop_mechanics_are_bit_neutral(monkeypatch, fmt, decim, fs):
+    """The chunk loops' launch mechanics -- the delay line carried by the kernel itself (save_halo) or by
+    a copy node, chunks shorter than the halo in between (which always take the copy), the trimmed
+    warm-up tile of a warp's range, programmatic dependent launch on or off -- must not move a single
+    bit: every variant of a ragged chunk loop gives the same bits, and the one-launch result of the same
+    stream within the tolerance (the chunk invariance of the reference's stateful chain, filters.py:69 + comm.py:76,124 +
+    demod_fm.py:44-48, which the oracle tests pin separately)."""
+    import torch
+    from directdemod_b200.fused import FusedChain
+    rng = np.random.default_rng(decim)
+    n = 3_000_000
+    taps = O.taps_blackman_harris(151)[0]
+    if fmt == "cu8":
+        xd = torch.from_numpy(rng.integers(0, 256, 2 * n, dtype=np.uint8)).cuda()
+        piece = lambda a, b: xd[2 * a:2 * b]
+    else:
+        xd = torch.from_numpy(noise_c64(rng, n)).cuda()
+        piece = lambda a, b: xd[a:b]
+    # even cut points (the fused kernels want 16-byte aligned chunk starts; others take the general path,
+    # covered elsewhere), long chunks, chunks of a few halos, chunks shorter than the halo
+    cuts = [0, 1_000_000, 1_000_100, 1_000_150, 1_700_000, 1_700_008, 2_400_000, 2_400_600, n]
+    if fmt == "cu8":
+        cuts = [c // 8 * 8 for c in cuts]
+
+    def loop(env):
+        for k in ("DDM_CHAIN_HALO_MEMCPY", "DDM_CHAIN_NO_PDL"):
+            monkeypatch.delenv(k, raising=False)
+        for k in env:
+            monkeypatch.setenv(k, "1")
+        ch = FusedChain(taps, decim, 30000.0, fs, in_format=fmt)          # the switches are read at creation
+        parts = [ch.apply(piece(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+        ch.close()
+        return torch.cat(parts)
+
+    ch = FusedChain(taps, decim, 30000.0, fs, in_format=fmt)
+    whole = ch.apply(piece(0, n))
+    ch.close()
+    base = loop(())
+    assert base.shape == whole.shape
+    # against the one-launch result: the same samples up to float32 rounding (odd D shifts the block
+    # grid by one sample with the parity of the carried offset, so bit equality is not promised here)
+    assert wrap_rel_rms(base.cpu().numpy(), whole.cpu().numpy()) <= TOL
+    for env in (("DDM_CHAIN_HALO_MEMCPY",), ("DDM_CHAIN_NO_PDL",), ("DDM_CHAIN_HALO_MEMCPY", "DDM_CHAIN_NO_PDL")):
+        got = loop(env)
+        assert torch.equal(got, base), (env, float((got - base).abs().max()))
