@@ -315,6 +315,9 @@ chain_fused_kernel(const ChainParams P) {
         (32u + 4u * (Q * DP + DP) + 8u * (2 * DP + kChainEBufs * Q * NT) + 127u) & ~127u;
     unsigned char *s_stage0 = smem_raw + fixed_bytes;
 
+    // programmatic dependent launch, as in chain_stream_kernel: set-up overlaps the previous launch's tail,
+    // every read of the chunk or the halo comes after the wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int i = 0; i < S; ++i) mbar_init(&mbar[i], 1);
         fence_mbar_init();
@@ -326,6 +329,7 @@ chain_fused_kernel(const ChainParams P) {
         s_ry[i] = make_float2(-r.y, r.y);
         s_c[i] = make_float2(0.5f * (r.x - r.y), 0.5f * (r.x + r.y));
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     save_halo<U8>(P, tid, NT);
     __syncthreads();
 
@@ -1170,8 +1174,17 @@ int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
     }
     long long grid = static_cast<long long>(c->sms) * per_sm;
     if (grid > p.num_tiles * p.batch) grid = p.num_tiles * p.batch;
-    kern<<<static_cast<unsigned>(grid), kChainThreads, smem, st>>>(p);
-    DDM_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kChainThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = c->pdl ? 1 : 0;
+    DDM_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return DDM_OK;
 }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Where the host time of the drop-in API goes: cProfile of decode_noaa._audio (93 chunks through
-commSignal) and getCrudeSync on a device-resident 15-minute pass.   python scripts/prof_python.py"""
+commSignal), getCrudeSync and the line assembly of getImage on a device-resident 15-minute pass.
+    python scripts/prof_python.py [audio,crude,image]"""
 import cProfile
 import io
 import os
@@ -20,10 +21,18 @@ torch.cuda.set_device(0)
 fs = 2048000
 x = B.apt_iq_device(900, fs)
 src = B.DeviceSource(x, fs)
-for what in ("audio", "crude"):
+which = sys.argv[1].split(",") if len(sys.argv) > 1 else ["audio", "crude"]
+for what in which:
     dec = decode_noaa.decode_noaa(src, 30000.0)
-    fn = (lambda: dec._audio(constants.NOAA_CRUDESYNCSAMPRATE, False)) if what == "audio" else dec.getCrudeSync
-    decode_noaa.decode_noaa(src, 30000.0).getCrudeSync()          # warm
+    if what == "image":
+        dec.getImage                       # warm run; the syncs stay cached, the image is assembled again below
+        dec._image = None
+        dec._audOut = None                 # (the band-pass of :274 works on the audio in place)
+        dec._audio(constants.NOAA_CRUDESYNCSAMPRATE, False)
+        fn = lambda: dec.getImage
+    else:
+        fn = (lambda: dec._audio(constants.NOAA_CRUDESYNCSAMPRATE, False)) if what == "audio" else dec.getCrudeSync
+        decode_noaa.decode_noaa(src, 30000.0).getCrudeSync()          # warm
     torch.cuda.synchronize()
     pr = cProfile.Profile()
     t0 = time.perf_counter()
@@ -33,5 +42,5 @@ for what in ("audio", "crude"):
     pr.disable()
     print("==== %s: %.2f ms wall" % (what, (time.perf_counter() - t0) * 1e3))
     s = io.StringIO()
-    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22)
-    print("\n".join(s.getvalue().splitlines()[:45]))
+    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+    print("\n".join(s.getvalue().splitlines()[:55]))

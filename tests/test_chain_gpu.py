@@ -275,7 +275,7 @@ def test_host_entry_point_pipelines_long_chunks_in_pieces():
 
 
 @pytest.mark.parametrize("fmt", ["cf32", "cu8"])
-@pytest.mark.parametrize("decim,fs", [(34, 2048000), (33, 2048000), (20, 960000)])
+@pytest.mark.parametrize("decim,fs", [(34, 2048000), (33, 2048000), (20, 960000), (50, 10000000)])
 def test_chunk_loop_mechanics_are_bit_neutral(monkeypatch, fmt, decim, fs):
     """The chunk loops' launch mechanics -- the delay line carried by the kernel itself (save_halo) or by
     a copy node, chunks shorter than the halo in between (which always take the copy), the trimmed
