@@ -102,7 +102,11 @@ int ddm_chain_get_halo(const ddm_chain *c, void *halo_dev, void *stream);
  * configurations of the fused fast path (decimation >= 2, at most 10 partial sums per output: 151
  * taps from D = 16 on), which is either the warp-autonomous kernel (per-warp TMA rings, partial sums
  * exchanged by shuffles) or the CTA-tiled one, chosen per block length (chain.cu, stream_geometry);
- * any other configuration runs the general float64-accumulating kernels. */
+ * any other configuration runs the general float64-accumulating kernels.  In a chunk loop the launch of
+ * chunk k+1 overlaps the tail of chunk k (programmatic dependent launch; everything that reads the chunk
+ * or the carried state waits for all earlier work of the stream), and the kernel itself saves the last
+ * halo_len samples for the next call -- no other node is queued per chunk.  The chunk must stay
+ * valid and unmodified until the launch has completed in stream order, as for any asynchronous call. */
 int ddm_chain_apply_dev(ddm_chain *c, const void *x_dev, int64_t n,
                         void *out_dev, int64_t out_capacity, int64_t *n_out, void *stream);
 /* `batch` independent captures of n samples each (capture k at x_dev + k*x_stride samples), every
