@@ -1016,7 +1016,8 @@ struct ddm_chain {
     int es = 8;                              // bytes per input sample
     long long n_real = 0;                    // real samples in the halo (u8: the rest is virtual)
     int cur = 0;
-    bool pdl = true;                         // programmatic dependent launch of the warp-autonomous kernel (DDM_CHAIN_NO_PDL: A/B)
+    bool pdl = true;                         // programmatic dependent launch of the fused kernels (DDM_CHAIN_NO_PDL: A/B)
+    bool chained = false;                    // the handle's previous call was a chunk of the same stream (chunk loop)
     bool halo_in_kernel = true;              // the fused kernel carries the halo itself (DDM_CHAIN_HALO_MEMCPY: A/B switch)
     double step_re = 1, step_im = 0;         // block rotator advance of the warp-autonomous kernel (set once)
     bool step_set = false;
@@ -1103,6 +1104,17 @@ bool stream_geometry(int Q, int D, int DP, int in_format, bool legacy_fits, int 
     return false;
 }
 
+// Programmatic dependent launch is for chunk loops only: the second and later chunks of a stream, queued
+// back to back by consecutive apply calls, of chunk-loop size.  A launch that follows a repositioning
+// (time-sharded slabs, resets, batches) or a very long one gains nothing from it, and its CTAs, resident
+// early and waiting, keep the SMs from kernels of other streams: measured on the time-sharded stream at
+// N = 2, where the NCCL halo exchange of the next step then waits for a whole slab (9.91 against 8.73 ms,
+// profiles/r02_timeshard_pdl_ab.jsonl).
+constexpr long long kPdlMaxSamples = 1LL << 26;
+inline bool use_pdl(const ddm_chain *c, const ChainParams &p) {
+    return c->pdl && c->chained && p.batch == 1 && p.n <= kPdlMaxSamples;
+}
+
 template <int Q, bool MIX, int OUT, int IN>
 int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
     ChainParams p = p0;
@@ -1150,7 +1162,7 @@ int launch_stream_q(ddm_chain *c, const ChainParams &p0, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = c->pdl ? 1 : 0;
+    cfg.numAttrs = use_pdl(c, p) ? 1 : 0;
     DDM_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return DDM_OK;
@@ -1183,7 +1195,7 @@ int launch_fused_q(ddm_chain *c, const ChainParams &p, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = c->pdl ? 1 : 0;
+    cfg.numAttrs = use_pdl(c, p) ? 1 : 0;
     DDM_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     count_launch();
     return DDM_OK;
@@ -1276,6 +1288,7 @@ int build_initial_halo(ddm_chain *c) {
 
 int fill_initial_halo(ddm_chain *c, cudaStream_t st) {
     c->n_real = 0;
+    c->chained = false;
     if (c->in_format == DDM_IN_CU8) {
         // u8 cannot encode the all-ones mixed history: it is kept virtual (n_real = 0) and the
         // first H samples of a fresh stream go through the general kernel, which knows about it
@@ -1497,6 +1510,7 @@ int ddm_chain_set_position(ddm_chain *c, int64_t n0, int64_t dec_off, int has_pr
     DDM_CUDA(cudaMemcpyAsync(c->d_halo[c->cur], halo_dev, static_cast<size_t>(c->es) * c->H,
                              cudaMemcpyDeviceToDevice, st));
     c->n_real = c->H;
+    c->chained = false;
     return DDM_OK;
 }
 
@@ -1742,6 +1756,7 @@ int chain_apply_piece(ddm_chain *c, const void *x_dev, int64_t n, void *out_dev,
     c->dec_off = positive_mod(D - positive_mod(n - c->dec_off, D), D);
     c->n0 += n;
     if (M > 0) c->has_prev = 1;
+    c->chained = true;
     return DDM_OK;
 }
 }  // namespace
