@@ -312,3 +312,38 @@ def test_chain_position_mirror_follows_the_reference_carry_rules():
             assert ch.position_cached[0] == st.n0
             assert ch.position_cached[1] == st.dec_off
             assert ch.position_cached[2] == (st.fm_last is not None) or not demod
+
+
+def test_fill_sync_matches_the_unmodified_reference_on_ragged_sync_lists():
+    """decode_noaa.__fillSync (decode_noaa.py:467-508) is pure host logic inside getImage: keep the syncs
+    spaced by the modal distance, extrapolate back to the start, fill every gap up to the end.  The drop-in
+    restates it with a set beside the list (the reference's `x not in list` is quadratic); pin it to the
+    reference's own method on passes with missed syncs, false detections, late starts and ties in the modal
+    spacing -- same list, element for element."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("no reference checkout and nothing staged")
+    ref = ref_shim.load()
+    import importlib
+    ref_noaa = importlib.import_module("directdemod.decode_noaa")
+    from directdemod_b200 import decode_noaa as ours
+    their = object.__new__(ref_noaa.decode_noaa)
+    fill_ref = getattr(their, "_decode_noaa__fillSync")
+    rng = np.random.default_rng(20)
+    spacing = 20480                                   # half a second at 40960 Hz
+    for case in range(40):
+        n_lines = int(rng.integers(6, 120))
+        start = int(rng.integers(0, 3 * spacing))
+        syncs = start + spacing * np.arange(n_lines) + rng.integers(-3, 4, n_lines)
+        keep = rng.random(n_lines) > (0.0 if case % 4 == 0 else 0.25)          # missed syncs
+        keep[:2] = True                                # (an all-gaps pass has no modal spacing to speak of)
+        syncs = syncs[keep]
+        if case % 3 == 0:                              # false detections between two lines
+            extra = rng.choice(syncs[:-1], size=min(3, len(syncs) - 1), replace=False) + rng.integers(500, 9000, min(3, len(syncs) - 1))
+            syncs = np.sort(np.concatenate([syncs, extra]))
+        syncs = np.unique(syncs).astype(np.float64)    # getImage hands over floats (sync / crudeRate * fs)
+        max_len = int(syncs[-1] + rng.integers(0, 5 * spacing))
+        want = fill_ref(list(syncs), max_len)
+        got = ours.decode_noaa._fillSync(list(syncs), max_len)
+        assert len(got) == len(want), case
+        assert all(a == b for a, b in zip(got, want)), case
