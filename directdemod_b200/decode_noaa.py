@@ -66,6 +66,32 @@ def _resample_rows(x, starts, n, num):
     return out
 
 
+def _quantise_rows(image, backup):
+    """The pixel rows of decode_noaa.py:432-461 in one vectorised pass.  ``image`` holds (row, slope,
+    intercept) for the lines written once a telemetry frame had been seen (:440-452: row * slope +
+    intercept), ``backup`` (row, low, high) for the first-guess levels used when none ever was (:434-438,
+    :455-456: 255 (row - low) / (high - low)); each row goes through round, clip to 0..255, uint8 exactly
+    as the reference does line by line.  Every row has the same length here (shorter lines raise earlier),
+    so the reference's "keep the rows of the most common length" (:459-461) keeps them all; its error on a
+    pass without a single whole line is kept."""
+    def quantise(v):
+        v = np.round(v)
+        v[v < 0] = 0
+        v[v > 255] = 255
+        return v.astype(np.uint8)
+    if len(image) == 0 and len(backup) == 0:
+        raise ValueError("max() arg is an empty sequence")
+    if len(image) == 0:
+        rows = np.stack([r for r, _, _ in backup])
+        low = np.array([lo for _, lo, _ in backup], dtype=np.float64)[:, None]
+        high = np.array([hi for _, _, hi in backup], dtype=np.float64)[:, None]
+        return quantise(255 * (rows - low) / (high - low))
+    rows = np.stack([r for r, _, _ in image])
+    slope = np.array([a for _, a, _ in image], dtype=np.float64)[:, None]
+    icpt = np.array([b for _, _, b in image], dtype=np.float64)[:, None]
+    return quantise(rows * slope + icpt)
+
+
 class decode_noaa:
     def __init__(self, sigsrc, offset, bw=None):
         """sigsrc: IQ source with ``sampFreq``, ``length`` and ``read(a, b)``; offset: frequency
@@ -269,12 +295,6 @@ class decode_noaa:
         valuesPixCorr, valuesSigCorr = [], []
         chidFifo1, chidFifo2 = [], []
 
-        def quantise(v):
-            v = np.round(v)
-            v[v < 0] = 0
-            v[v > 255] = 255
-            return v.astype(np.uint8)
-
         for li, (k, sA, eA, sB, eB) in enumerate(lines):
             if pix.get((li, "A")) is None or pix.get((li, "B")) is None:
                 raise ValueError("cannot reshape array of size 0 into shape (%d,0)" % half)
@@ -330,21 +350,7 @@ class decode_noaa:
                     image.append((old, self._slope, self._intercept))
                 imageBuffer = []
                 image.append((row, self._slope, self._intercept))
-        # every row has 2 * half pixels here (shorter lines raised above), so the reference's "keep the rows
-        # of the most common length" (:459-462) keeps them all
-        if len(image) == 0 and len(backupImage) == 0:
-            raise ValueError("max() arg is an empty sequence")      # :460 on a pass without a single whole line
-        if len(image) == 0:
-            # :457 no telemetry frame seen: the first-guess levels, 255 (row - low) / (high - low)
-            rows = np.stack([r for r, _, _ in backupImage])
-            low = np.array([lo for _, lo, _ in backupImage], dtype=np.float64)[:, None]
-            high = np.array([hi for _, _, hi in backupImage], dtype=np.float64)[:, None]
-            self._image = quantise(255 * (rows - low) / (high - low))
-        else:
-            rows = np.stack([r for r, _, _ in image])
-            slope = np.array([a for _, a, _ in image], dtype=np.float64)[:, None]
-            icpt = np.array([b for _, _, b in image], dtype=np.float64)[:, None]
-            self._image = quantise(rows * slope + icpt)
+        self._image = _quantise_rows(image, backupImage)
         logging.info('Image extraction complete')
         return self._image
 

@@ -347,3 +347,32 @@ def test_fill_sync_matches_the_unmodified_reference_on_ragged_sync_lists():
         got = ours.decode_noaa._fillSync(list(syncs), max_len)
         assert len(got) == len(want), case
         assert all(a == b for a, b in zip(got, want)), case
+
+
+def test_image_rows_quantised_in_one_pass_equal_the_line_by_line_form():
+    """getImage records every line's pixel row with the two numbers its formula uses and quantises all rows
+    at once (decode_noaa._quantise_rows); the reference rounds, clips and casts line by line with the
+    levels in force at that line (decode_noaa.py:432-452).  Same bytes, including levels that change from
+    line to line, out-of-range pixels on both sides and the pass that never saw a telemetry frame."""
+    from directdemod_b200 import decode_noaa as ours
+
+    def line_by_line(v):
+        v = np.round(v)
+        v[v < 0] = 0
+        v[v > 255] = 255
+        return v.astype(np.uint8)
+    rng = np.random.default_rng(7)
+    rows = [rng.normal(0.35, 0.3, 2080) for _ in range(60)]
+    slope = [float(rng.normal(420, 60)) for _ in rows]
+    icpt = [float(rng.normal(-25, 30)) for _ in rows]
+    low = [float(rng.normal(0.1, 0.02)) for _ in rows]
+    high = [float(rng.normal(0.8, 0.02)) for _ in rows]
+    got = ours._quantise_rows(list(zip(rows, slope, icpt)), list(zip(rows[:5], low, high)))
+    want = np.array([line_by_line(r * a + b) for r, a, b in zip(rows, slope, icpt)])
+    assert got.dtype == np.uint8 and got.shape == want.shape and np.array_equal(got, want)
+    assert got.min() == 0 and got.max() == 255                      # both clips were exercised
+    got = ours._quantise_rows([], list(zip(rows, low, high)))       # no telemetry frame: first-guess levels
+    want = np.array([line_by_line(255 * (r - lo) / (hi - lo)) for r, lo, hi in zip(rows, low, high)])
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    with pytest.raises(ValueError):                                 # the reference's max() of an empty sequence
+        ours._quantise_rows([], [])
