@@ -126,9 +126,10 @@ def hilbert(x):
 
 
 def resample(x, num):
-    """Fourier-domain resampling of a real signal (down-sampling case): keep the lowest
-    num//2+1 rfft bins; when ``num`` is even the new Nyquist bin collects both aliases
-    (doubled, real part survives the irfft); rescale by num/n."""
+    """Fourier-domain resampling of a real signal: keep the lowest min(num, n)//2+1 rfft bins.  Down,
+    ``num`` even: the new Nyquist bin collects both aliases (doubled, real part survives the irfft).
+    Up, ``n`` even: the old Nyquist bin is shared between the two frequencies it now stands for
+    (halved), whatever the parity of ``num``.  Rescale by num/n."""
     x = np.asarray(x, dtype=np.float64)
     n = len(x)
     spec = np.fft.rfft(x)
@@ -138,7 +139,7 @@ def resample(x, num):
     out[:m] = spec[:m]
     if num % 2 == 0 and num < n:
         out[num // 2] *= 2.0
-    elif num % 2 == 0 and num > n and n % 2 == 0:
+    elif num > n and n % 2 == 0:
         out[n // 2] *= 0.5
     return np.fft.irfft(out, num) * (float(num) / n)
 

@@ -265,3 +265,77 @@ def test_afsk_bank_matches_loop_definition():
         si = np.sum(seg * np.cos((i / bw) / (1 / 2200) * 2 * np.pi))
         sq = np.sum(seg * np.sin((i / bw) / (1 / 2200) * 2 * np.pi))
         assert abs(out[s] - (mi * mi + mq * mq - si * si - sq * sq)) < 1e-9
+
+
+# ---------------- the restatement against scipy on drawn shapes (hypothesis) ----------------
+try:
+    from hypothesis import given, settings, strategies as st
+    _HAVE_HYPOTHESIS = True
+except Exception:                                             # pragma: no cover
+    _HAVE_HYPOTHESIS = False
+
+if _HAVE_HYPOTHESIS:
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(n=st.integers(2, 700), num=st.integers(1, 900), seed=st.integers(0, 2**16))
+    def test_restated_resample_and_hilbert_on_drawn_lengths(n, num, seed):
+        """scipy.signal.resample (comm.py:114, decode_noaa.py:350-351: real signals, down AND up, even/odd
+        on both sides) and scipy.signal.hilbert (demod_am.py:29) restated from their definitions, on drawn
+        lengths."""
+        import scipy.signal as sps
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(n)
+        want = sps.resample(x, num)
+        got = R.resample(x, num)
+        assert got.shape == want.shape
+        scale = max(np.sqrt(np.mean(np.abs(want) ** 2)), 1e-30)
+        assert np.max(np.abs(got - want)) <= 1e-10 * max(scale, 1.0)
+        assert O.rel_rms(R.hilbert(x), sps.hilbert(x)) < 1e-12
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(order=st.integers(1, 8), n=st.integers(40, 400), seed=st.integers(0, 2**16),
+           kind=st.sampled_from(["lp", "hp", "bp"]), split=st.integers(1, 39))
+    def test_restated_recursion_carries_state_across_any_split(order, n, seed, kind, split):
+        """filters.py:64-70: lfilter with carried zi over two chunks == one call, for drawn Butterworth
+        designs (filters.py:262-269), restated recursion against scipy's."""
+        import scipy.signal as sps
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        wn = {"lp": 0.2, "hp": 0.3, "bp": [0.1, 0.35]}[kind]
+        b, a = sps.butter(order, wn, btype={"lp": "low", "hp": "high", "bp": "band"}[kind])
+        zi = sps.lfilter_zi(b, a)
+        assert np.allclose(R.lfilter_zi(b, a), zi, rtol=1e-6, atol=1e-9)
+        want, zf = sps.lfilter(b, a, x, zi=zi.astype(complex))
+        y1, z1 = R.lfilter(b, a, x[:split], zi)
+        y2, z2 = R.lfilter(b, a, x[split:], z1)
+        got = np.concatenate([y1, y2])
+        tol = 1e-9 if order * (2 if kind == "bp" else 1) <= 8 else 1e-6      # high-order tf forms: scipy's own floor
+        assert O.rel_rms(got, want) < tol
+        assert np.allclose(z2, zf, rtol=1e-5, atol=1e-7 * max(1.0, float(np.max(np.abs(zf)))))
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(n=st.integers(1, 300), m=st.integers(1, 120), seed=st.integers(0, 2**16))
+    def test_restated_same_mode_windows_on_drawn_lengths(n, m, seed):
+        """'same'-mode alignment of correlate / convolve (decode_noaa.py:671-672) for even and odd needle
+        lengths, haystack at least as long as the needle (the reference's case)."""
+        import scipy.signal as sps
+        if m > n:
+            n, m = m, n
+        rng = np.random.default_rng(seed)
+        h, k = rng.standard_normal(n), rng.standard_normal(m)
+        assert np.allclose(R.correlate_same(h, k), sps.correlate(h, k, mode="same"), rtol=1e-10, atol=1e-10)
+        assert np.allclose(R.convolve_same(h, k), np.convolve(h, k, mode="same"), rtol=1e-10, atol=1e-10)
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(order=st.integers(1, 6), n=st.integers(60, 400), seed=st.integers(0, 2**16), fir=st.booleans())
+    def test_restated_zero_phase_filter_on_drawn_designs(order, n, seed, fir):
+        """filters.py:73 filtfilt: odd extension by 3*max(len a, len b), both passes seeded with zi * edge."""
+        import scipy.signal as sps
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal(n)
+        if fir:
+            b, a = sps.windows.hamming(2 * order + 3), np.array([1.0])
+        else:
+            b, a = sps.butter(order, 0.25)
+        if n <= 3 * max(len(a), len(b)):
+            return                                   # scipy refuses inputs shorter than the padding
+        assert O.rel_rms(R.filtfilt(b, a, x), sps.filtfilt(b, a, x)) < 1e-9
