@@ -1,0 +1,141 @@
+"""The oracle port (oracle/ddoracle.py) against the UNMODIFIED reference, imported through
+oracle/ref_shim.py from the reference checkout or the staged copy (oracle/_ref), on drawn inputs.
+
+The committed fixtures (tests/golden) pin fixed cases; here the two run side by side on shapes a
+property-based generator draws -- chunk sizes that split blocks, decimation factors that do not divide the
+chunk, offsets of either sign, filters of several kinds -- which is what "the oracle restates the
+reference" has to mean for every input, not for nine of them.  CPU only; skipped when no reference is
+reachable.  No GPU code is involved: this validates the checker the GPU tests rely on.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import ddoracle as O
+from oracle import ref_shim
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st      # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="no reference checkout and nothing staged")
+
+
+class _Src:
+    """What chunker.chunker wants from a source (source.py: length) -- nothing else is touched."""
+
+    def __init__(self, n):
+        self.length = n
+
+
+def _ref():
+    ref_shim.load()
+    from directdemod import chunker, comm, constants, demod_am, demod_fm, filters
+    return chunker, comm, constants, demod_am, demod_fm, filters
+
+
+def _signal(seed, n, complex_=True):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(n) * 40
+    if complex_:
+        x = x + 1j * rng.standard_normal(n) * 40
+        return x.astype(np.complex64)
+    return x
+
+
+@settings(max_examples=25, deadline=None, derandomize=True)
+@given(n=st.integers(400, 6000), chunk=st.integers(97, 3000), decim=st.integers(1, 40),
+       f_off=st.floats(-3e5, 3e5, allow_nan=False), ntaps=st.sampled_from([1, 7, 31, 151]),
+       demod=st.booleans(), seed=st.integers(0, 2**16))
+def test_fused_chain_port_equals_reference_chunk_loop(n, chunk, decim, f_off, ntaps, demod, seed):
+    """decode_noaa.py:613-627 / decode_afsk1200.py:79-91: the chunk loop through commSignal with the
+    chunker's carried variables, against the port's explicit state."""
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    fs = 2048000
+    target = fs / decim * 1.0001 if decim > 1 else fs          # int(fs / target) == decim
+    if int(fs / target) != decim:
+        target = fs / decim
+    x = _signal(seed, n)
+    ck = chunker.chunker(_Src(n), chunk)
+    bh = filters.blackmanHarris(ntaps)
+    fm = demod_fm.demod_fm()
+    out = comm.commSignal(int(fs / int(fs / target)))
+    for a, b in ck.getChunks:
+        sig = comm.commSignal(fs, x[a:b], ck).offsetFreq(f_off).filter(bh).bwLim(target, uniq="First")
+        if demod:
+            if sig.length == 0:
+                return                      # the reference's discriminator raises on an empty chunk
+            sig = sig.funcApply(fm.demod)
+        out.extend(sig)
+    st_ = O.ChainState(O.taps_blackman_harris(ntaps)[0])
+    parts = []
+    for a, b in O.chunk_bounds(n, chunk):
+        y, _ = O.chain_chunk(x[a:b], fs, f_off, O.taps_blackman_harris(ntaps)[0], target, st_, demod=demod)
+        parts.append(y)
+    want = np.concatenate(parts)
+    got = np.asarray(out.signal)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)          # the same scipy calls in the same order: the same bits
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(n=st.integers(200, 3000), split=st.integers(1, 199), seed=st.integers(0, 2**16),
+       kind=st.sampled_from(["bh", "hamming", "gauss", "roll", "butlp", "buthp", "butbp", "butbs", "remez"]),
+       cplx=st.booleans())
+def test_stateful_filters_port_equals_reference(n, split, seed, kind, cplx):
+    """filters.py:21-75: every designer, stateful over two chunks, stateless and zero phase."""
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    fs = 48000
+    make = {
+        "bh": (lambda **kw: filters.blackmanHarris(31, **kw), lambda: O.taps_blackman_harris(31)),
+        "hamming": (lambda **kw: filters.hamming(41, **kw), lambda: O.taps_hamming(41)),
+        "gauss": (lambda **kw: filters.gaussian(25, 3.0, **kw), lambda: O.taps_gaussian(25, 3.0)),
+        "roll": (lambda **kw: filters.rollingAverage(5, **kw), lambda: O.taps_rolling_average(5)),
+        "butlp": (lambda **kw: filters.butter(fs, 3000, n=5, **kw), lambda: O.taps_butter(fs, 3000, n=5)),
+        "buthp": (lambda **kw: filters.butter(fs, 3000, n=3, typeFlt=constants.FLT_HP, **kw),
+                  lambda: O.taps_butter(fs, 3000, n=3, kind=O.FLT_HP)),
+        "butbp": (lambda **kw: filters.butter(fs, 1000, 4000, n=3, typeFlt=constants.FLT_BP, **kw),
+                  lambda: O.taps_butter(fs, 1000, 4000, n=3, kind=O.FLT_BP)),
+        "butbs": (lambda **kw: filters.butter(fs, 1000, 4000, n=2, typeFlt=constants.FLT_BS, **kw),
+                  lambda: O.taps_butter(fs, 1000, 4000, n=2, kind=O.FLT_BS)),
+        "remez": (lambda **kw: filters.remez(fs, [[0, 4000], [6000, 24000]], [1, 0], ntaps=33, **kw),
+                  lambda: O.taps_remez(fs, [[0, 4000], [6000, 24000]], [1, 0], ntaps=33)),
+    }[kind]
+    x = _signal(seed, n, cplx)
+    b, a = make[1]()
+    f = make[0]()
+    assert np.array_equal(np.asarray(f.getB), np.asarray(b)) and np.array_equal(np.asarray(f.getA), np.asarray(a))
+    y1 = f.applyOn(x[:split])
+    y2 = f.applyOn(x[split:])
+    w1, z = O.filt_stateful(b, a, x[:split], O.initial_zi(b, a))
+    w2, _ = O.filt_stateful(b, a, x[split:], z)
+    assert np.array_equal(np.concatenate([y1, y2]), np.concatenate([w1, w2]))
+    assert np.array_equal(make[0](storeState=False).applyOn(x), O.filt_stateless(b, a, x))
+    if n > 3 * max(len(a), len(b)):
+        assert np.array_equal(make[0](zeroPhase=True).applyOn(x), O.filt_zero_phase(b, a, x))
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(n=st.integers(64, 4000), seed=st.integers(0, 2**16), target=st.integers(2000, 40000),
+       split=st.integers(1, 63))
+def test_demodulators_and_strict_resample_port_equals_reference(n, seed, target, split):
+    """demod_fm / demod_fmAD with carried state (demod_fm.py:29-51, :74-96), demod_am (demod_am.py:18-29)
+    and the strict bwLim (comm.py:110-116)."""
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    x = _signal(seed, n)
+    fm = demod_fm.demod_fm()
+    got = np.concatenate([fm.demod(x[:split].astype(np.complex128)), fm.demod(x[split:].astype(np.complex128))])
+    w1, last = O.fm_discriminator(x[:split].astype(np.complex128), None)
+    w2, _ = O.fm_discriminator(x[split:].astype(np.complex128), last)
+    assert np.array_equal(got, np.concatenate([w1, w2]))
+    ad = demod_fm.demod_fmAD()
+    got = np.concatenate([ad.demod(x[:split].astype(np.complex128)), ad.demod(x[split:].astype(np.complex128))])
+    w1, last = O.fm_angle_diff(x[:split].astype(np.complex128), None)
+    w2, _ = O.fm_angle_diff(x[split:].astype(np.complex128), last)
+    assert np.array_equal(got, np.concatenate([w1, w2]))
+    r = x.real.astype(np.float64)
+    assert np.array_equal(demod_am.demod_am().demod(r), O.am_envelope(r))
+    fs = 60235
+    if target <= fs and int(target * n / fs) >= 1:
+        sig = comm.commSignal(fs, r).bwLim(target, True)
+        want, rate = O.resample_strict(r, fs, target)
+        assert sig.sampRate == rate and np.array_equal(np.asarray(sig.signal), want)
