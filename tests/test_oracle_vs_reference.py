@@ -139,3 +139,39 @@ def test_demodulators_and_strict_resample_port_equals_reference(n, seed, target,
         sig = comm.commSignal(fs, r).bwLim(target, True)
         want, rate = O.resample_strict(r, fs, target)
         assert sig.sampRate == rate and np.array_equal(np.asarray(sig.signal), want)
+
+
+@settings(max_examples=20, deadline=None, derandomize=True)
+@given(lines=st.integers(3, 14), k=st.integers(1, 4), seed=st.integers(0, 2**16), sync_b=st.booleans(),
+       missing=st.integers(0, 3), flat=st.booleans(), variant=st.sampled_from(["norm", "filter", "neg"]))
+def test_sync_search_port_equals_reference(lines, k, seed, sync_b, missing, flat, variant):
+    """decode_noaa.__correlateAndFindPeaks (decode_noaa.py:677-767): needle, normalised correlation,
+    threshold from the K largest / smallest values, sequential group scan -- on envelopes with syncs
+    removed, with plateaus (ties in the strict-< maximum), and through the three call variants the
+    decoder uses (plain, hamming(492) zero-phase prefilter, +-0.5 needle)."""
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    import importlib
+    ref_noaa = importlib.import_module("directdemod.decode_noaa")
+    their = object.__new__(ref_noaa.decode_noaa)
+    search = getattr(their, "_decode_noaa__correlateAndFindPeaks")
+    fs = 4160 * k
+    rng = np.random.default_rng(seed)
+    bits = O.NOAA_SYNCB if sync_b else O.NOAA_SYNCA
+    needle = O.sync_needle(bits, fs)
+    n = lines * (fs // 2) + int(rng.integers(0, fs // 4))
+    sig = 0.35 + 0.03 * rng.standard_normal(n)
+    if flat:
+        sig = np.round(sig, 2)                       # plateaus: equal correlation values inside a group
+    starts = [int(rng.integers(50, 400)) + j * (fs // 2) for j in range(lines)]
+    for j in sorted(rng.choice(lines, size=min(missing, lines - 2), replace=False)) if missing else []:
+        starts[j] = None
+    for s in starts:
+        if s is not None and s + len(needle) <= n:
+            sig[s:s + len(needle)] = needle
+    kw = {"norm": {}, "filter": {"useFilter": True}, "neg": {"usePosNeedle": False}}[variant]
+    if variant == "filter" and n <= 3 * 492:
+        return                                       # filtfilt refuses inputs shorter than its padding
+    want_ref = np.asarray(search(comm.commSignal(fs, sig), bits, **kw))
+    got, _ = O.find_syncs(sig, fs, bits, prefilter_taps=O.taps_hamming(492)[0] if variant == "filter" else None,
+                          positive=variant != "neg")
+    assert got.dtype.kind == "i" and np.array_equal(got, want_ref)
