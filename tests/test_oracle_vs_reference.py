@@ -175,3 +175,72 @@ def test_sync_search_port_equals_reference(lines, k, seed, sync_b, missing, flat
     got, _ = O.find_syncs(sig, fs, bits, prefilter_taps=O.taps_hamming(492)[0] if variant == "filter" else None,
                           positive=variant != "neg")
     assert got.dtype.kind == "i" and np.array_equal(got, want_ref)
+
+
+def test_afsk_front_end_port_equals_reference_intermediates():
+    """decode_afsk1200.getMsg (decode_afsk1200.py:62-158) is one monolithic property, so the arrays the
+    oracle restates -- the band-passed FM audio, the mark/space bank output of the pure-Python double loop
+    (:106-142) and the bit-edge correlation (:145-158) -- are read out of the UNMODIFIED reference's own
+    frame when getMsg returns (sys.setprofile; nothing of the reference is edited or copied).  This pins
+    the vectorised restatement of the bank, which no fixture of the reference covers."""
+    import importlib
+    import sys
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    ref_afsk = importlib.import_module("directdemod.decode_afsk1200")
+    fs, bw, n = 96000, 48000, 16000
+    rng = np.random.default_rng(12)
+    t = np.arange(n) / fs
+    bits = rng.integers(0, 2, int(n / fs * 1200) + 2)
+    tone = np.where(bits[(t * 1200).astype(int)] == 1, 1200.0, 2200.0)
+    audio = np.sin(2 * np.pi * np.cumsum(tone) / fs)
+    x = (50 * np.exp(1j * 2 * np.pi * 3000 * np.cumsum(audio) / fs)
+         + 1.0 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+
+    class Src:
+        sampFreq, length = fs, n
+
+        def read(self, a, b=None):
+            return x[a:b]
+
+    seen = {}
+
+    def grab(frame, event, arg):
+        if event == "return" and frame.f_code.co_name == "getMsg":
+            loc = frame.f_locals
+            if "sig" in loc:
+                seen["audio"] = np.array(loc["sig"].signal)
+            for k in ("binary_filter", "changes"):
+                if k in loc:
+                    seen[k] = np.array(loc[k])
+    dec = ref_afsk.decode_afsk1200(Src(), 0.0, bw)
+    sys.setprofile(grab)
+    try:
+        dec.getMsg
+    except Exception:
+        pass                                  # whatever the bit logic makes of 0.17 s of signal is not the point
+    finally:
+        sys.setprofile(None)
+    assert {"audio", "binary_filter", "changes"} <= set(seen), sorted(seen)
+
+    taps = O.taps_blackman_harris(151)[0]
+    iq, rate = O.chain_stream(x, fs, 0.0, taps, bw, demod=False)
+    assert rate == 48000
+    fm, _ = O.fm_discriminator(iq, None)
+    b, a = O.taps_butter(rate, 700, 2700, n=6, kind=O.FLT_BP)
+    aud, _ = O.filt_stateful(b, a, fm, O.initial_zi(b, a))
+    assert np.array_equal(aud, seen["audio"])                         # the same scipy calls: the same bits
+    want_bf = O.afsk_bank(aud, bw)
+    assert want_bf.shape == seen["binary_filter"].shape
+    # the loop adds 40 products one by one, the restatement uses np.correlate: same numbers up to the order of the sums
+    scale = np.max(np.abs(seen["binary_filter"]))
+    assert np.max(np.abs(want_bf - seen["binary_filter"])) <= 1e-12 * scale
+    assert np.all(want_bf[-40:] == 0) and np.all(seen["binary_filter"][-40:] == 0)
+    spb = bw // 1200
+    kernel = np.ones(spb)
+    kernel[:spb // 2] = -1
+    want_ch = np.correlate(np.sign(want_bf), kernel, mode="same") / spb
+    near_zero = np.abs(seen["binary_filter"]) <= 1e-9 * scale           # a sign there may legitimately differ
+    if not near_zero.any():
+        assert np.array_equal(want_ch, seen["changes"])
+    else:
+        assert np.mean(want_ch == seen["changes"]) > 0.99
