@@ -33,10 +33,18 @@ def main():
     useful = dec.useful
     img = dec.getImage
     print("reference: useful=%d, %d syncA, image %s, %.1f s" % (useful, len(syncA), np.asarray(img).shape, time.time() - t0))
+    # accurate sync of every window the reference accepts (decode_noaa.py:808-880), ~0.4 s per window
+    t0 = time.time()
+    acc = dec.getAccurateSync()
+    print("reference: %d + %d accurate syncs, %.1f s" % (len(acc[0]), len(acc[4]), time.time() - t0))
     out = os.path.join(ROOT, "tests", "golden", "noaa_pass.npz")
     np.savez_compressed(out, seed=SEED, seconds=SECONDS, fs=FS, f_off=F_OFF, useful=useful,
                         syncA=np.asarray(syncA), syncB=np.asarray(syncB), image=np.asarray(img, dtype=np.uint8),
-                        input_checksum=np.array([float(np.abs(x[::1000]).sum())]))
+                        input_checksum=np.array([float(np.abs(x[::1000]).sum())]),
+                        asyncA=np.asarray(acc[0], dtype=np.int64), asyncApk=np.asarray(acc[2], dtype=np.float64),
+                        asyncAtime=np.asarray(acc[3], dtype=np.float64),
+                        asyncB=np.asarray(acc[4], dtype=np.int64), asyncBpk=np.asarray(acc[6], dtype=np.float64),
+                        asyncBtime=np.asarray(acc[7], dtype=np.float64))
     print("wrote", out, os.path.getsize(out), "bytes")
 
 

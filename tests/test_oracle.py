@@ -339,3 +339,32 @@ if _HAVE_HYPOTHESIS:
         if n <= 3 * max(len(a), len(b)):
             return                                   # scipy refuses inputs shorter than the padding
         assert O.rel_rms(R.filtfilt(b, a, x), sps.filtfilt(b, a, x)) < 1e-9
+
+
+def test_noaa_sync_oracle_matches_unmodified_reference_fixture(golden):
+    """The oracle's crude and accurate sync (the checker of tests/test_sync_gpu.py) against what the
+    UNMODIFIED reference produced for the same synthetic pass (oracle/gen_golden_noaa.py ->
+    tests/golden/noaa_pass.npz: getCrudeSync, decode_noaa.py:769-806, and getAccurateSync, :808-880):
+    sync positions equal sample for sample.  Windows: the first two, the middle one and the last one of
+    each sync word (0.4 s of CPU each)."""
+    from tests.util import apt_iq, oracle_accurate_window
+    g = golden("noaa_pass")
+    fs, f_off = int(g["fs"]), float(g["f_off"])
+    x = apt_iq(int(g["seed"]), float(g["seconds"]), fs=fs, f_off=f_off)
+    assert abs(float(np.abs(x[::1000]).sum()) - float(g["input_checksum"][0])) < 1e-3, "generator drifted"
+    taps = O.taps_blackman_harris(151)[0]
+    audio, rate = O.chain_stream(x, fs, f_off, taps, 60000)
+    am = O.am_envelope_chunked(audio)
+    crude = {}
+    for name, bits in (("A", O.NOAA_SYNCA), ("B", O.NOAA_SYNCB)):
+        crude[name], _ = O.find_syncs(am, rate, bits)
+        assert np.array_equal(crude[name], g["sync" + name]), name
+    width = int(3 * O.NOAA_T * len(O.NOAA_SYNCA) * fs)
+    for name, bits in (("A", O.NOAA_SYNCA), ("B", O.NOAA_SYNCB)):
+        want = g["async" + name]
+        starts = [int(c) - width for c in crude[name] / rate * fs
+                  if int(c) - width >= 0 and int(c) + width <= len(x)]
+        assert len(starts) == len(want), name                      # the windows the reference accepted (:828-830)
+        for k in sorted({0, 1, len(starts) // 2, len(starts) - 1}):
+            a = starts[k]
+            assert oracle_accurate_window((x[a:a + 2 * width], a, fs, bits)) == int(want[k]), (name, k)
