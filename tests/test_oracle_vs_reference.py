@@ -5,7 +5,9 @@ The committed fixtures (tests/golden) pin fixed cases; here the two run side by 
 property-based generator draws -- chunk sizes that split blocks, decimation factors that do not divide the
 chunk, offsets of either sign, filters of several kinds -- which is what "the oracle restates the
 reference" has to mean for every input, not for nine of them.  CPU only; skipped when no reference is
-reachable.  No GPU code is involved: this validates the checker the GPU tests rely on.
+reachable.  No GPU code is involved: this validates the checker the GPU tests rely on.  The last tests do
+the same for the drop-in's own host-only pieces (the chunker, the filter designers and their errors), which
+need no device either.
 """
 
 import numpy as np
@@ -244,3 +246,70 @@ def test_afsk_front_end_port_equals_reference_intermediates():
         assert np.array_equal(want_ch, seen["changes"])
     else:
         assert np.mean(want_ch == seen["changes"]) > 0.99
+
+
+@settings(max_examples=60, deadline=None, derandomize=True)
+@given(length=st.integers(0, 5000), size=st.integers(1, 1200), names=st.lists(st.sampled_from(["freqoffset", "bwlimFirst", "bwlimabcd", "x"]), max_size=6))
+def test_product_chunker_equals_reference_chunker(length, size, names):
+    """The drop-in's own chunker (product code, pure host logic) next to the reference's (chunker.py:21-84):
+    the chunk list for drawn lengths and chunk sizes -- exact multiples still end with a full-size chunk, an
+    empty source gives [[0, 0]] -- and the variable store: get with / without an initial value, set, KeyError."""
+    ref_chunker = _ref()[0]
+    from directdemod_b200 import chunker as ours
+    a, b = ours.chunker(_Src(length), size), ref_chunker.chunker(_Src(length), size)
+    assert [list(c) for c in a.getChunks] == [list(c) for c in b.getChunks]
+    for k, name in enumerate(names):
+        for obj in (a, b):
+            if k % 3 == 0:
+                obj.set(name, k)
+        outcomes = []
+        for obj in (a, b):
+            try:
+                outcomes.append(("ok", obj.get(name) if k % 2 else obj.get(name, 7 * k)))
+            except KeyError:
+                outcomes.append(("KeyError", None))
+        assert outcomes[0] == outcomes[1], (name, k)
+
+
+@settings(max_examples=60, deadline=None, derandomize=True)
+@given(kind=st.sampled_from(["bh", "hamming", "gauss", "roll", "butter", "remez"]), n=st.integers(1, 200),
+       fs=st.integers(8000, 3000000), ca=st.floats(0.01, 0.49), cb=st.floats(0.01, 0.49),
+       typ=st.integers(-1, 5), sigma=st.floats(0.5, 30.0), with_b=st.booleans())
+def test_product_filter_designers_equal_reference_designers(kind, n, fs, ca, cb, typ, sigma, with_b):
+    """The drop-in's designers (host side of filters.py:95-314; no device involved) next to the reference's:
+    same coefficients bit for bit, same exception types for the same bad arguments (butter without cutoffB
+    for band filters, unknown filter types, remez band / gain mismatches)."""
+    chunker, comm, constants, demod_am, demod_fm, filters = _ref()
+    from directdemod_b200 import filters as ours
+
+    def both(make):
+        out = []
+        for mod in (ours, filters):
+            try:
+                f = make(mod)
+                out.append(("ok", np.asarray(f.getB, dtype=np.float64), np.asarray(f.getA, dtype=np.float64)))
+            except Exception as exc:                         # noqa: BLE001 -- the type is what is compared
+                out.append((type(exc).__name__, None, None))
+        assert out[0][0] == out[1][0], out
+        if out[0][0] == "ok":
+            assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+    if kind == "bh":
+        both(lambda m: m.blackmanHarris(n))
+    elif kind == "hamming":
+        both(lambda m: m.hamming(n))
+    elif kind == "gauss":
+        both(lambda m: m.gaussian(n, sigma))
+    elif kind == "roll":
+        both(lambda m: m.rollingAverage(n))
+    elif kind == "butter":
+        order = 1 + n % 8
+        lo, hi = sorted((ca * fs, cb * fs))
+        if hi - lo < 1e-3 * fs:
+            hi = lo + 1e-3 * fs
+        both(lambda m: m.butter(fs, lo, hi if with_b else None, n=order, typeFlt=typ))
+    else:
+        edge = ca * fs
+        bands = [[0, edge], [min(edge * 1.3 + 1, fs / 2 - 1), fs / 2 - 1]]
+        gains = [1, 0] if with_b else [1]                      # wrong number of gains -> ValueError in both
+        both(lambda m: m.remez(fs, bands if typ != 5 else [[0, edge, 2 * edge]], gains, ntaps=8 + n % 120))
