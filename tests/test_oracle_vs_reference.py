@@ -313,3 +313,50 @@ def test_product_filter_designers_equal_reference_designers(kind, n, fs, ca, cb,
         bands = [[0, edge], [min(edge * 1.3 + 1, fs / 2 - 1), fs / 2 - 1]]
         gains = [1, 0] if with_b else [1]                      # wrong number of gains -> ValueError in both
         both(lambda m: m.remez(fs, bands if typ != 5 else [[0, edge, 2 * edge]], gains, ntaps=8 + n % 120))
+
+
+@settings(max_examples=25, deadline=None, derandomize=True)
+@given(n=st.integers(2, 3000), seed=st.integers(0, 2**16),
+       reads=st.lists(st.tuples(st.integers(-3, 3100), st.one_of(st.none(), st.integers(-3, 3100))), min_size=1, max_size=8),
+       limit=st.one_of(st.none(), st.tuples(st.integers(0, 1500), st.integers(0, 3000))),
+       given_fs=st.one_of(st.none(), st.integers(1000, 4000000)))
+def test_product_sources_equal_reference_sources(tmp_path_factory, n, seed, reads, limit, given_fs):
+    """The drop-in's file sources (product host code, source.py:40-230: 44-byte WAV header, raw .dat, the
+    -127.5 conversion, read / limitData bounds and their ValueErrors) next to the reference's, on drawn
+    files, index pairs and limits."""
+    ref_shim.load()
+    import importlib
+    ref_source = importlib.import_module("directdemod.source")
+    from directdemod_b200 import source as ours
+    from tests.test_host import _write_wav_u8
+    rng = np.random.default_rng(seed)
+    pairs = rng.integers(0, 256, (n, 2), dtype=np.uint8)
+    d = tmp_path_factory.mktemp("src")
+    wav, dat = str(d / "iq.wav"), str(d / "iq.dat")
+    _write_wav_u8(wav, pairs, 2048000)
+    pairs.tofile(dat)
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except Exception as exc:                             # noqa: BLE001 -- the type is what is compared
+            return (type(exc).__name__, None)
+    for cls, path in (("IQwav", wav), ("IQdat", dat)):
+        a = getattr(ours, cls)(path, given_fs) if given_fs else getattr(ours, cls)(path)
+        b = getattr(ref_source, cls)(path, given_fs) if given_fs else getattr(ref_source, cls)(path)
+        assert (a.sampFreq, a.length, a.sourceType) == (b.sampFreq, b.length, b.sourceType)
+        for phase in ("whole", "limited"):
+            if phase == "limited":
+                if limit is None:
+                    break
+                ra, rb = outcome(lambda: a.limitData(*limit)), outcome(lambda: b.limitData(*limit))
+                assert ra[0] == rb[0], (cls, limit)
+                if ra[0] != "ok":
+                    break
+                assert a.length == b.length
+            for lo, hi in reads:
+                ra = outcome(lambda: a.read(lo, hi) if hi is not None else a.read(lo))
+                rb = outcome(lambda: b.read(lo, hi) if hi is not None else b.read(lo))
+                assert ra[0] == rb[0], (cls, phase, lo, hi)
+                if ra[0] == "ok":
+                    assert ra[1].dtype == rb[1].dtype and np.array_equal(ra[1], rb[1]), (cls, phase, lo, hi)
