@@ -66,6 +66,16 @@ def _resample_rows(x, starts, n, num):
     return out
 
 
+def _steadiest(sync, rate, n):
+    """min over all runs of n consecutive sync spacings of the run's largest deviation from half a
+    second (decode_noaa.py:795-799; the reference's list comprehension of ~1800 np.max calls is 4 ms of
+    interpreter time per sync word -- one windowed maximum here)."""
+    dev = np.abs(np.diff(sync) - (rate * 0.5))
+    if len(dev) - n + 1 <= 0:
+        return np.min([])               # the reference's error for a pass with too few syncs
+    return np.min(np.max(np.lib.stride_tricks.sliding_window_view(dev, n), axis=1))
+
+
 def _quantise_rows(image, backup):
     """The pixel rows of decode_noaa.py:432-461 in one vectorised pass.  ``image`` holds (row, slope,
     intercept) for the lines written once a telemetry frame had been seen (:440-452: row * slope +
@@ -433,17 +443,8 @@ class decode_noaa:
             logging.info('Beginning SyncB detection')
             self._syncB = self._correlateAndFindPeaks(sig, constants.NOAA_SYNCB)
             n = constants.NOAA_DETECTCONSSYNCSNUM
-
-            def steadiest(sync):
-                """min over all runs of n consecutive sync spacings of the run's largest deviation from
-                half a second (decode_noaa.py:795-799; the reference's list comprehension of ~1800
-                np.max calls is 4 ms of interpreter time per sync word -- one windowed maximum here)."""
-                dev = np.abs(np.diff(sync) - (self._syncCrudeSampRate * 0.5))
-                if len(dev) - n + 1 <= 0:
-                    return np.min([])               # the reference's error for a pass with too few syncs
-                return np.min(np.max(np.lib.stride_tricks.sliding_window_view(dev, n), axis=1))
-            minSyncAdiff = steadiest(self._syncA)
-            minSyncBdiff = steadiest(self._syncB)
+            minSyncAdiff = _steadiest(self._syncA, self._syncCrudeSampRate, n)
+            minSyncBdiff = _steadiest(self._syncB, self._syncCrudeSampRate, n)
             if minSyncAdiff < constants.NOAA_DETECTMAXCHANGE or minSyncBdiff < constants.NOAA_DETECTMAXCHANGE:
                 logging.info('NOAA Signal was found')
                 self._useful = 1

@@ -376,3 +376,23 @@ def test_image_rows_quantised_in_one_pass_equal_the_line_by_line_form():
     assert got.dtype == np.uint8 and np.array_equal(got, want)
     with pytest.raises(ValueError):                                 # the reference's max() of an empty sequence
         ours._quantise_rows([], [])
+
+
+def test_usefulness_measure_equals_the_reference_expression():
+    """getCrudeSync's "was a NOAA signal found" measure (decode_noaa.py:794-799): the smallest, over all
+    runs of NOAA_DETECTCONSSYNCSNUM consecutive sync spacings, of the run's largest deviation from half a
+    second.  The drop-in takes one windowed maximum instead of a list comprehension of np.max calls: same
+    number, and the same error for a pass with too few syncs."""
+    from directdemod_b200 import constants, decode_noaa as ours
+    n = constants.NOAA_DETECTCONSSYNCSNUM
+    rng = np.random.default_rng(3)
+    rate = 60235
+    for count in (n + 1, n + 2, 40, 300):
+        sync = np.cumsum(rng.integers(rate // 2 - 40, rate // 2 + 40, count))
+        sync[rng.integers(0, count)] += 5000                      # a false detection in the middle
+        dev = np.abs(np.diff(sync) - (rate * 0.5))
+        want = np.min([np.max(dev[i:i + n]) for i in range(len(dev) - n + 1)])
+        assert ours._steadiest(sync, rate, n) == want
+    for count in (2, n):                                          # too few syncs: np.min of an empty list
+        with pytest.raises(ValueError):
+            ours._steadiest(np.arange(count) * (rate // 2), rate, n)
