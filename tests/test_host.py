@@ -396,3 +396,61 @@ def test_usefulness_measure_equals_the_reference_expression():
     for count in (2, n):                                          # too few syncs: np.min of an empty list
         with pytest.raises(ValueError):
             ours._steadiest(np.arange(count) * (rate // 2), rate, n)
+
+
+def test_iir_analysis_runs_on_the_host_and_means_what_the_header_says():
+    """ddm_iir_analyse (include/ddemod.h) is host arithmetic: the warm-up after which a segment started from
+    zero state agrees with the running filter, and the roundoff floor of the float64 transposed direct form
+    II recursion (scipy's lfilter, filters.py:69) against extended precision on white noise -- the number
+    DDM_IIR_AUTO compares with its tolerance.  Checked against an independent measurement (numpy longdouble
+    recursion in this test vs scipy.signal.lfilter) for the three recursive filters the decoders build, and
+    for the two edge cases (FIR: nothing to analyse; unstable: no finite warm-up)."""
+    import scipy.signal as sps
+    from directdemod_b200 import _lib
+    lib = _lib.lib()
+
+    def analyse(b, a):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        w, nf = ctypes.c_int64(), ctypes.c_double()
+        _lib.check(lib.ddm_iir_analyse(b.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(b),
+                                       a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(a),
+                                       ctypes.byref(w), ctypes.byref(nf)), "ddm_iir_analyse")
+        return int(w.value), float(nf.value)
+
+    def measured_floor(b, a, n=30000):
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(n)
+        y64 = sps.lfilter(b, a, x)
+        bl, al = np.asarray(b, dtype=np.longdouble), np.asarray(a, dtype=np.longdouble)
+        bl, al = bl / al[0], al / al[0]
+        k = max(len(bl), len(al))
+        bl, al = np.pad(bl, (0, k - len(bl))), np.pad(al, (0, k - len(al)))
+        z = np.zeros(k, dtype=np.longdouble)                       # transposed direct form II, extended precision
+        y = np.empty(n, dtype=np.longdouble)
+        for i, xi in enumerate(x.astype(np.longdouble)):
+            yi = bl[0] * xi + z[0]
+            z[:-1] = bl[1:] * xi + z[1:] - al[1:] * yi
+            y[i] = yi
+        err = (y64.astype(np.longdouble) - y)[n // 2:]
+        return float(np.sqrt(np.mean(err ** 2)) / np.sqrt(np.mean(y[n // 2:] ** 2)))
+
+    cases = {
+        "C4 low-pass, butter(8) at 100 kHz of 2.4 Msps (parallel under AUTO)": sps.butter(8, 100e3 / 1.2e6),
+        "NOAA band-pass, butter(6) 400-4400 Hz of 60235 (decode_noaa.py:274)": sps.butter(6, [400 / 30117.5, 4400 / 30117.5], btype="band"),
+        "AFSK band-pass, butter(6) 700-2700 Hz of 48000 (decode_afsk1200.py:98)": sps.butter(6, [700 / 24000, 2700 / 24000], btype="band"),
+    }
+    floors = {}
+    for name, (b, a) in cases.items():
+        warm, nf = analyse(b, a)
+        floors[name] = nf
+        r = np.max(np.abs(np.roots(a)))
+        assert 0 < r < 1 and warm > 0
+        assert r ** warm < 1e-6, (name, warm, r)                  # the slowest mode has died out after the warm-up
+        assert warm < 40 * np.log(1e-16) / np.log(r), (name, warm, r)     # ... and it is not absurdly long
+        want = measured_floor(b, a)
+        assert want / 4 <= nf <= want * 4, (name, nf, want)       # measured here: within 25 % for all three
+    lp, noaa, afsk = floors.values()
+    assert lp < 1e-7 < afsk < noaa                                # which side of the AUTO switch each one falls
+    assert analyse(sps.windows.hamming(31), [1.0]) == (0, 0.0)    # FIR: no recursion
+    assert analyse([1.0], [1.0, -1.01])[0] == -1                  # unstable: never segment-parallel
