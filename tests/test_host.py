@@ -454,3 +454,36 @@ def test_iir_analysis_runs_on_the_host_and_means_what_the_header_says():
     assert lp < 1e-7 < afsk < noaa                                # which side of the AUTO switch each one falls
     assert analyse(sps.windows.hamming(31), [1.0]) == (0, 0.0)    # FIR: no recursion
     assert analyse([1.0], [1.0, -1.01])[0] == -1                  # unstable: never segment-parallel
+
+
+def test_c_abi_reports_errors_as_status_plus_message_without_a_device():
+    """The boundary's error convention (include/ddemod.h): every entry point returns an int
+    status, 0 or negative, with the reason in ddm_last_error(); nothing is thrown across the ABI and
+    argument checks come before any device work -- so they can be exercised here, with no GPU."""
+    from directdemod_b200 import _lib
+    lib = _lib.lib()
+    pd = ctypes.POINTER(ctypes.c_double)
+    ones, zi = np.ones(3), np.zeros(4)
+    handle, count = ctypes.c_void_p(), ctypes.c_int64()
+    assert lib.ddm_version() >= 100
+    checks = [
+        (lambda: lib.ddm_lfilter_zi(None, 3, ones.ctypes.data_as(pd), 3, zi.ctypes.data_as(pd)), b"ddm_lfilter_zi"),
+        (lambda: lib.ddm_lfilter_zi(ones.ctypes.data_as(pd), 3, np.array([0.0, 1.0, 1.0]).ctypes.data_as(pd), 3,
+                                    zi.ctypes.data_as(pd)), b"a[0]"),
+        (lambda: lib.ddm_chain_create(0, ones.ctypes.data_as(pd), 3, 0, 0.0, 1000.0, 0, 0, ctypes.byref(handle)),
+         b"decimation"),
+        (lambda: lib.ddm_chain_create(0, ones.ctypes.data_as(pd), 3, 2, 0.0, -1.0, 0, 0, ctypes.byref(handle)),
+         b"sampling rate"),
+        (lambda: lib.ddm_chain_create(0, ones.ctypes.data_as(pd), 3, 2, 0.0, 1000.0, 0, 0, None), b"NULL"),
+        (lambda: lib.ddm_chain_create(0, ones.ctypes.data_as(pd), 3, 2, 0.0, 1000.0, 7, 0, ctypes.byref(handle)),
+         b"out_mode"),
+        (lambda: lib.ddm_chain_apply_dev(None, None, 0, None, 0, ctypes.byref(count), None), b"NULL handle"),
+    ]
+    for call, needle in checks:
+        rc = call()
+        assert rc == _lib.ERR_INVALID, (rc, needle)
+        assert needle in lib.ddm_last_error(), (needle, lib.ddm_last_error())
+        assert not handle.value                              # no half-built handle is handed out
+    with pytest.raises(_lib.DdmError) as info:               # the Python layer turns the status into an exception
+        _lib.check(checks[2][0](), "ddm_chain_create")
+    assert "decimation" in str(info.value)
